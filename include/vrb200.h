@@ -1,0 +1,198 @@
+/*
+ * vrb200.h -- C ABI of libvrb200.so, the B200 (sm_100a) back end of the VolRen volume path tracer.
+ *
+ * This is the drop-in boundary for the reference's GPU seam: everything nihofm/volren does through
+ * OpenGL (texture/SSBO uploads, uniform marshalling, glDispatchCompute, glGetTexImage) is replaced
+ * by the calls below. Each entry point cites the reference interface it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns VRB_OK (0) or a negative vrb_status; nothing throws across the ABI;
+ *     a human-readable message for the last failure of a context is vrb_last_error(ctx).
+ *   - a vrb_ctx is bound to ONE CUDA device and is NOT thread-safe (one host thread per ctx).
+ *   - all work is enqueued on the context's stream; only vrb_sync, vrb_*download* and
+ *     vrb_get_counters block the host.
+ *   - host pointers are borrowed for the duration of the call; device memory is owned by the ctx.
+ *   - matrices are column-major (glm layout), images are bottom-up (row 0 = bottom, GL layout),
+ *     3-D buffers are x-fastest (voldata/src/buf3d.h:27-29).
+ *   - there is NO CPU fallback: without a CUDA device vrb_create fails with VRB_ERR_NO_DEVICE.
+ */
+#ifndef VRB200_H
+#define VRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRB_ABI_VERSION 1
+
+typedef struct vrb_ctx vrb_ctx;
+
+typedef enum vrb_status {
+    VRB_OK = 0,
+    VRB_ERR_INVALID = -1,      /* bad argument (null pointer, bad slot/frame, size 0, ...) */
+    VRB_ERR_NO_DEVICE = -2,    /* no usable CUDA device / wrong architecture */
+    VRB_ERR_CUDA = -3,         /* a CUDA runtime call or kernel failed (see vrb_last_error) */
+    VRB_ERR_OOM = -4,          /* device allocation failed */
+    VRB_ERR_TOO_MANY_BRICKS = -5, /* mirrors "exceeded max brick count of 1024" (grid_brick.cpp:66-67) */
+    VRB_ERR_STATE = -6         /* call order problem: no grid / env / resolution set */
+} vrb_status;
+
+/* grid slots of one frame (renderer.cpp:61-74: "density" and the first of flame|flames|temperature) */
+enum { VRB_SLOT_DENSITY = 0, VRB_SLOT_EMISSION = 1 };
+
+/* accumulation modes of vrb_trace */
+enum {
+    VRB_ACCUM_MEAN = 0, /* reference semantics: color = mix(color, L, 1/current_sample) (pathtracer_brick.glsl:36) */
+    VRB_ACCUM_SUM = 1   /* color += L  (spp-sliced multi-GPU: sum buffers are reduced, then vrb_scale) */
+};
+
+/*
+ * The uniform block that RendererOpenGL::trace uploads (src/renderer.cpp:88-139), field for field.
+ * tf_size, env_imp_inv_dim (1/512) and env_imp_base_mip (9) are owned by the context
+ * (they follow from vrb_tf_upload / vrb_env_upload, as in transferfunc.cpp:28 and renderer.cpp:130-131).
+ */
+typedef struct vrb_params {
+    int32_t bounces;                 /* renderer.cpp:88 */
+    int32_t seed;                    /* :89 (signed: the shader multiplies it as int, pathtracer_brick.glsl:28) */
+    int32_t show_environment;        /* :90 */
+    int32_t frame;                   /* volume->grid_frame_counter (:110) */
+    float cam_pos[3];                /* :93 */
+    float cam_fov;                   /* :94 degrees */
+    float cam_transform[9];          /* :95 inverse(mat3(view)), column-major */
+    float vol_bb_min[3];             /* :99 */
+    float vol_bb_max[3];             /* :100 */
+    float vol_minorant;              /* :101 */
+    float vol_majorant;              /* :102 */
+    float vol_inv_majorant;          /* :103 */
+    float vol_albedo[3];             /* :104 */
+    float vol_phase_g;               /* :105 */
+    float vol_density_scale;         /* :106 */
+    float vol_emission_scale;        /* :107 */
+    float vol_emission_norm;         /* :108 */
+    float vol_density_transform[16];     /* :111 volume.transform * grid.transform */
+    float vol_density_inv_transform[16]; /* :112 */
+    int32_t has_emission;            /* :117 frame < emission_grids.size() */
+    float vol_emission_transform[16];     /* :119 */
+    float vol_emission_inv_transform[16]; /* :120 (all-zero when has_emission == 0: unset GL uniform) */
+    int32_t use_transferfunc;        /* :80 selects pathtracer_brick_tf.glsl */
+    float tf_window_left;            /* transferfunc.cpp:29 */
+    float tf_window_width;           /* transferfunc.cpp:30 */
+    float env_transform[9];          /* renderer.cpp:127 */
+    float env_inv_transform[9];      /* :128 */
+    float env_strength;              /* :129 */
+    int32_t resolution[2];           /* :137,139 */
+} vrb_params;
+
+/* Host view of one brick grid (voldata/src/grid_brick.h:27-33). Pointers may be NULL to skip a copy. */
+typedef struct vrb_brick_view {
+    uint32_t n_bricks[3];            /* grid_brick.h:27 */
+    uint32_t atlas_dim[3];           /* atlas.stride in voxels (pruned in z, grid_brick.cpp:112) */
+    uint64_t brick_count;            /* brick_counter */
+    uint32_t* indirection;           /* n_bricks.x*y*z words, encode_ptr packing (grid_brick.cpp:32-37) */
+    uint32_t* range;                 /* n_bricks.x*y*z words, 2 x fp16 (grid_brick.cpp:24-26) */
+    uint8_t* atlas;                  /* atlas_dim.x*y*z bytes */
+    uint32_t* range_mips[3];         /* level i: (n_bricks >> (i+1)) words (grid_brick.cpp:114-141) */
+} vrb_brick_view;
+
+/* Event counters of the tracking kernels: they define the algorithmic bytes per sample. */
+typedef struct vrb_counters {
+    uint64_t n_samples;   /* path samples (pixel, spp) traced */
+    uint64_t n_maj;       /* majorant DDA steps, camera + shadow rays (common.glsl:425/427, 472/474) */
+    uint64_t n_dens;      /* tentative collisions = density lookups (common.glsl:437-440, 484-487) */
+    uint64_t n_emis;      /* emission-grid lookups actually fetched (common.glsl:489) */
+    uint64_t n_nee;       /* sample_environment calls (common.glsl:616) */
+    uint64_t n_env;       /* escape lookups lookup_environment (+pdf) (common.glsl:646-647) */
+    uint64_t n_real;      /* real collisions = path vertices */
+} vrb_counters;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* replaces cppgl Context::init + RendererOpenGL::init (src/renderer.cpp:29-50) */
+int vrb_create(int device, vrb_ctx** out);
+void vrb_destroy(vrb_ctx* ctx);
+const char* vrb_last_error(vrb_ctx* ctx);
+const char* vrb_status_string(int status);
+int vrb_abi_version(void);
+/* run all work of this context on an existing cudaStream_t (e.g. torch's current stream); NULL = own stream */
+int vrb_set_stream(vrb_ctx* ctx, void* cuda_stream);
+int vrb_sync(vrb_ctx* ctx);
+/* replaces RendererOpenGL::resize / the RGBA32F `color` texture (src/renderer.cpp:46-54); zero-fills */
+int vrb_resize(vrb_ctx* ctx, int w, int h);
+
+/* ---- volume data (src/renderer.cpp:56-76 commit, :159-225 brick_grid_to_textures) --------------- */
+/* commit() starts with density_grids.clear(); emission_grids.clear() (renderer.cpp:57-58) */
+int vrb_grid_clear(vrb_ctx* ctx);
+/* upload an existing BrickGrid verbatim (a loaded .brick file) */
+int vrb_grid_upload_brick(vrb_ctx* ctx, int slot, int frame, const vrb_brick_view* grid);
+/* voldata::BrickGrid::BrickGrid(const Grid&) for a DenseGrid source (voldata/src/grid_brick.cpp:60-142,
+ * grid_dense.cpp:99-103), run on the GPU, bit-exact w.r.t. the serial reference (raster allocation order).
+ * voxels_u8: dim[0]*dim[1]*dim[2] bytes, HOST memory; (vmin, vmax) = DenseGrid::min_value/max_value. */
+int vrb_grid_build_from_dense(vrb_ctx* ctx, int slot, int frame, const uint8_t* voxels_u8,
+                              const uint32_t dim[3], float vmin, float vmax);
+/* same, voxels already resident in DEVICE memory of ctx's device */
+int vrb_grid_build_from_dense_device(vrb_ctx* ctx, int slot, int frame, const void* d_voxels_u8,
+                                     const uint32_t dim[3], float vmin, float vmax);
+/* sizes of an uploaded/built grid; then a second call with buffers allocated copies it back */
+int vrb_grid_info(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* sizes_out);
+int vrb_grid_download(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out);
+/* voldata::DenseGrid(w,h,d,const float*) (voldata/src/grid_dense.cpp:57-95): global min/max + 8-bit quantise.
+ * out_u8 (host, n bytes) and out_minmax[2]; if d_out_u8 != NULL the quantised grid is also left on the device. */
+int vrb_dense_from_float(vrb_ctx* ctx, const float* data, const uint32_t dim[3], uint8_t* out_u8,
+                         float out_minmax[2]);
+
+/* ---- environment (src/environment.cpp:11-33 + shader/env_setup.glsl) ---------------------------- */
+/* rgb: w*h*3 floats, bottom-up (already flipped like cppgl image_load). Builds the 512^2 importance
+ * map and its 9 box-filter mips (glGenerateMipmap). */
+int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h);
+/* read back importance-map level `level` (0..9): (512>>level)^2 floats */
+int vrb_env_download_impmap(vrb_ctx* ctx, int level, float* out);
+
+/* ---- transfer function (src/transferfunc.cpp:26-58) -------------------------------------------- */
+/* rgba: n*4 floats, already CDF-corrected by the host (compute_lut_cdf runs above the ABI) */
+int vrb_tf_upload(vrb_ctx* ctx, const float* rgba, uint32_t n);
+
+/* ---- rendering (src/renderer.cpp:78-145 trace, shader/pathtracer_brick{,_tf}.glsl) -------------- */
+/* Traces samples first_sample .. first_sample+n_samples-1 (1-based, = `current_sample`) for every pixel
+ * of `tile` (x0,y0,x1,y1 half-open; NULL = whole image) and folds them into the colour buffer. */
+int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_samples,
+              const int tile[4], int accum_mode);
+/* deterministic transmittance-only mode (defined by this build, DESIGN.md "T1"): centre ray per pixel,
+ * exact voxel DDA, color = (Tr * Le_env(dir), 1 - Tr) */
+int vrb_trace_deterministic(vrb_ctx* ctx, const vrb_params* params);
+/* color *= s (finalise VRB_ACCUM_SUM buffers) */
+int vrb_scale(vrb_ctx* ctx, float s);
+/* zero the colour buffer */
+int vrb_clear(vrb_ctx* ctx);
+/* enable (1) / disable (0) the counting build of the kernels and reset the counters */
+int vrb_set_counting(vrb_ctx* ctx, int enable);
+int vrb_get_counters(vrb_ctx* ctx, vrb_counters* out);
+
+/* ---- tonemap + readback (shader/tonemap.glsl, tonemap.fs, blit.fs; bindings.cpp:141-166) --------- */
+/* in_place != 0: shader/tonemap.glsl on `color` (src/main.cpp:540-550);
+ * in_place == 0: RendererOpenGL::draw() into the RGBA8 framebuffer (renderer.cpp:147-153):
+ *                tonemapping != 0 -> tonemap.fs, else blit.fs */
+int vrb_tonemap(vrb_ctx* ctx, float exposure, float gamma, int in_place, int tonemapping);
+/* glGetTexImage(color, GL_RGB/GL_RGBA, GL_FLOAT) (bindings.cpp:141-148); channels = 3 or 4 */
+int vrb_download_color(vrb_ctx* ctx, float* out, int channels);
+/* Texture2DImpl::save_ldr readback: color -> unorm8 RGBA (cppgl texture.cpp:107-113) */
+int vrb_download_color_ldr(vrb_ctx* ctx, uint8_t* rgba8);
+/* glReadPixels of the framebuffer written by the last draw (bindings.cpp:149-166) */
+int vrb_download_framebuffer(vrb_ctx* ctx, uint8_t* rgba8);
+/* overwrite the colour buffer from host memory (resume / tile assembly); rgba: w*h*4 floats */
+int vrb_upload_color(vrb_ctx* ctx, const float* rgba);
+/* device pointer of the float4 colour buffer (for NCCL reductions issued by the host runtime) */
+void* vrb_color_device_ptr(vrb_ctx* ctx);
+
+/* ---- multi-GPU (new) --------------------------------------------------------------- */
+/* single-process helper: sum the colour buffers of n contexts (one per device) into ctxs[root]
+ * over peer-to-peer NVLink copies + an add kernel. One-process-per-GPU runs use NCCL on
+ * vrb_color_device_ptr instead (bench.py). */
+int vrb_reduce(vrb_ctx* const* ctxs, int n, int root);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRB200_H */

@@ -1,0 +1,393 @@
+"""ctypes binding of the CPU oracle (oracle/vr_oracle.c) and, when present, of the compiled
+reference voldata sources (oracle/_ref/libvoldata_ref.so).
+
+TEST INFRASTRUCTURE ONLY: import this from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never from volren_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "_build", "libvr_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libvoldata_ref.so")
+
+IMP_DIM = 512
+IMP_LEVELS = 10
+
+
+def build(ref: bool = True) -> None:
+    """(Re)build the oracle (and oracle/_ref when /root/reference is present)."""
+    subprocess.run(["make", "-s", "-C", HERE, "all" if ref else os.path.join(HERE, "_build", "libvr_oracle.so")],
+                   check=True)
+
+
+class Params(C.Structure):
+    """Mirror of vrb_params (include/vrb200.h). Shared by the oracle and the C-ABI tests."""
+    _fields_ = [
+        ("bounces", C.c_int32), ("seed", C.c_int32), ("show_environment", C.c_int32), ("frame", C.c_int32),
+        ("cam_pos", C.c_float * 3), ("cam_fov", C.c_float), ("cam_transform", C.c_float * 9),
+        ("vol_bb_min", C.c_float * 3), ("vol_bb_max", C.c_float * 3),
+        ("vol_minorant", C.c_float), ("vol_majorant", C.c_float), ("vol_inv_majorant", C.c_float),
+        ("vol_albedo", C.c_float * 3), ("vol_phase_g", C.c_float), ("vol_density_scale", C.c_float),
+        ("vol_emission_scale", C.c_float), ("vol_emission_norm", C.c_float),
+        ("vol_density_transform", C.c_float * 16), ("vol_density_inv_transform", C.c_float * 16),
+        ("has_emission", C.c_int32),
+        ("vol_emission_transform", C.c_float * 16), ("vol_emission_inv_transform", C.c_float * 16),
+        ("use_transferfunc", C.c_int32), ("tf_window_left", C.c_float), ("tf_window_width", C.c_float),
+        ("env_transform", C.c_float * 9), ("env_inv_transform", C.c_float * 9), ("env_strength", C.c_float),
+        ("resolution", C.c_int32 * 2),
+    ]
+
+
+class BrickView(C.Structure):
+    """Mirror of vrb_brick_view."""
+    _fields_ = [
+        ("n_bricks", C.c_uint32 * 3), ("atlas_dim", C.c_uint32 * 3), ("brick_count", C.c_uint64),
+        ("indirection", C.c_void_p), ("range", C.c_void_p), ("atlas", C.c_void_p),
+        ("range_mips", C.c_void_p * 3),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_samples", "n_maj", "n_dens", "n_emis", "n_nee", "n_env", "n_real")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class _Grid(C.Structure):
+    _fields_ = [
+        ("n_bricks", C.c_uint32 * 3), ("atlas_dim", C.c_uint32 * 3),
+        ("indirection", C.c_void_p), ("range", C.c_void_p), ("atlas", C.c_void_p), ("range_mips", C.c_void_p * 3),
+    ]
+
+
+class _Scene(C.Structure):
+    _fields_ = [
+        ("density", _Grid), ("emission", _Grid),
+        ("env_rgb", C.c_void_p), ("env_w", C.c_int32), ("env_h", C.c_int32),
+        ("impmap", C.c_void_p), ("tf_lut", C.c_void_p), ("tf_size", C.c_uint32),
+    ]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def mip_dims(n_bricks, level):
+    return tuple(int(n) >> (level + 1) for n in n_bricks)
+
+
+class BrickGridData:
+    """Plain numpy holder of one brick grid (voldata/src/grid_brick.h:27-33); arrays are [z][y][x]."""
+
+    def __init__(self, n_bricks, atlas_dim, brick_count, indirection, range_, atlas, mips, min_maj=(0.0, 0.0),
+                 transform=None):
+        self.n_bricks = tuple(int(v) for v in n_bricks)
+        self.atlas_dim = tuple(int(v) for v in atlas_dim)
+        self.brick_count = int(brick_count)
+        self.indirection = np.ascontiguousarray(indirection, dtype=np.uint32)
+        self.range = np.ascontiguousarray(range_, dtype=np.uint32)
+        self.atlas = np.ascontiguousarray(atlas, dtype=np.uint8)
+        self.mips = [np.ascontiguousarray(m, dtype=np.uint32) for m in mips]
+        self.min_maj = (float(min_maj[0]), float(min_maj[1]))
+        self.transform = np.eye(4, dtype=np.float32) if transform is None else np.asarray(transform, np.float32)
+
+    def view(self) -> BrickView:
+        v = BrickView()
+        v.n_bricks[:] = self.n_bricks
+        v.atlas_dim[:] = self.atlas_dim
+        v.brick_count = self.brick_count
+        v.indirection = _ptr(self.indirection)
+        v.range = _ptr(self.range)
+        v.atlas = _ptr(self.atlas)
+        for i in range(3):
+            v.range_mips[i] = _ptr(self.mips[i])
+        return v
+
+    def _grid(self) -> _Grid:
+        g = _Grid()
+        g.n_bricks[:] = self.n_bricks
+        g.atlas_dim[:] = self.atlas_dim
+        g.indirection = _ptr(self.indirection)
+        g.range = _ptr(self.range)
+        g.atlas = _ptr(self.atlas)
+        for i in range(3):
+            g.range_mips[i] = _ptr(self.mips[i])
+        return g
+
+    def index_extent(self):
+        return tuple(8 * n for n in self.n_bricks)
+
+
+def alloc_brick_arrays(n_bricks, atlas_dim=None):
+    nbx, nby, nbz = (int(v) for v in n_bricks)
+    ad = atlas_dim if atlas_dim is not None else (nbx * 8, nby * 8, nbz * 8)
+    ind = np.zeros((nbz, nby, nbx), np.uint32)
+    rng = np.zeros((nbz, nby, nbx), np.uint32)
+    atlas = np.zeros((int(ad[2]), int(ad[1]), int(ad[0])), np.uint8)
+    mips = [np.zeros((nbz >> (i + 1), nby >> (i + 1), nbx >> (i + 1)), np.uint32) for i in range(3)]
+    return ind, rng, atlas, mips
+
+
+class Oracle:
+    def __init__(self, path: str = ORACLE_SO):
+        if not os.path.exists(path):
+            build(ref=False)
+        L = self.lib = C.CDLL(path)
+        L.vro_tea.restype = C.c_uint32
+        L.vro_tea.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        L.vro_rng_stream.argtypes = [C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        L.vro_to_half.restype = C.c_uint16
+        L.vro_to_half.argtypes = [C.c_float]
+        L.vro_from_half.restype = C.c_float
+        L.vro_from_half.argtypes = [C.c_uint16]
+        L.vro_dense_from_float.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_void_p, C.c_float * 2]
+        L.vro_brick_dims.argtypes = [C.c_uint32 * 3, C.c_uint32 * 3]
+        L.vro_brick_build.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_float, C.c_float, C.POINTER(BrickView)]
+        L.vro_brick_lookup.restype = C.c_float
+        L.vro_lut_upload.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.vro_env_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.vro_env_pyramid_floats.restype = C.c_size_t
+        L.vro_trace.argtypes = [C.POINTER(_Scene), C.POINTER(Params), C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                C.c_void_p, C.POINTER(Counters), C.c_int]
+        L.vro_trace_deterministic.argtypes = [C.POINTER(_Scene), C.POINTER(Params), C.c_void_p, C.c_int]
+        L.vro_tonemap_inplace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.vro_draw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
+        L.vro_color_to_ldr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+
+    # --- integer / bit-exact layer ---
+    def tea(self, v0, v1, n=32):
+        return int(self.lib.vro_tea(v0 & 0xFFFFFFFF, v1 & 0xFFFFFFFF, n))
+
+    def rng_stream(self, seed, n):
+        out = np.empty(n, np.float32)
+        states = np.empty(n, np.uint32)
+        self.lib.vro_rng_stream(seed & 0xFFFFFFFF, n, _ptr(out), _ptr(states))
+        return out, states
+
+    def to_half(self, f):
+        return int(self.lib.vro_to_half(float(f)))
+
+    def from_half(self, h):
+        return float(self.lib.vro_from_half(int(h)))
+
+    def dense_from_float(self, data):
+        data = np.ascontiguousarray(data, np.float32)
+        d, h, w = data.shape
+        out = np.empty(data.shape, np.uint8)
+        mm = (C.c_float * 2)()
+        self.lib.vro_dense_from_float(_ptr(data), (C.c_uint32 * 3)(w, h, d), _ptr(out), mm)
+        return out, (float(mm[0]), float(mm[1]))
+
+    def brick_dims(self, dim):
+        nb = (C.c_uint32 * 3)()
+        st = self.lib.vro_brick_dims((C.c_uint32 * 3)(*dim), nb)
+        return st, tuple(nb)
+
+    def brick_build(self, vox_u8, vmin, vmax) -> BrickGridData:
+        vox = np.ascontiguousarray(vox_u8, np.uint8)
+        d, h, w = vox.shape
+        st, nb = self.brick_dims((w, h, d))
+        if st:
+            raise RuntimeError("exceeded max brick count of 1024")
+        ind, rng, atlas, mips = alloc_brick_arrays(nb)
+        view = BrickView()
+        view.indirection, view.range, view.atlas = _ptr(ind), _ptr(rng), _ptr(atlas)
+        for i in range(3):
+            view.range_mips[i] = _ptr(mips[i])
+        st = self.lib.vro_brick_build(_ptr(vox), (C.c_uint32 * 3)(w, h, d), vmin, vmax, C.byref(view))
+        assert st == 0
+        ad = tuple(view.atlas_dim)
+        atlas = np.ascontiguousarray(atlas[: ad[2]])
+        return BrickGridData(nb, ad, view.brick_count, ind, rng, atlas, mips, (vmin, vmax))
+
+    def lut_upload(self, rgba):
+        rgba = np.ascontiguousarray(rgba, np.float32).reshape(-1, 4)
+        out = np.empty_like(rgba)
+        changed = self.lib.vro_lut_upload(_ptr(rgba), rgba.shape[0], _ptr(out))
+        return out, bool(changed)
+
+    # --- shader layer ---
+    def env_build(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        h, w, _ = rgb.shape
+        pyr = np.empty(self.lib.vro_env_pyramid_floats(), np.float32)
+        self.lib.vro_env_build(_ptr(rgb), w, h, _ptr(pyr))
+        return pyr
+
+    @staticmethod
+    def pyramid_level(pyr, level):
+        off = sum((IMP_DIM >> l) ** 2 for l in range(level))
+        d = IMP_DIM >> level
+        return pyr[off: off + d * d].reshape(d, d)
+
+    def make_scene(self, density: BrickGridData, env_rgb, impmap, lut=None, emission: BrickGridData | None = None):
+        sc = _Scene()
+        sc.density = density._grid()
+        if emission is not None:
+            sc.emission = emission._grid()
+        env_rgb = np.ascontiguousarray(env_rgb, np.float32)
+        sc.env_rgb = _ptr(env_rgb)
+        sc.env_h, sc.env_w = env_rgb.shape[0], env_rgb.shape[1]
+        sc.impmap = _ptr(impmap)
+        keep = [density, emission, env_rgb, impmap]
+        if lut is not None:
+            lut = np.ascontiguousarray(lut, np.float32).reshape(-1, 4)
+            sc.tf_lut = _ptr(lut)
+            sc.tf_size = lut.shape[0]
+            keep.append(lut)
+        sc._keep = keep
+        return sc
+
+    def trace(self, scene, params: Params, first_sample, n_samples, color=None, tile=None, accum_mode=0,
+              n_threads=0):
+        W, H = params.resolution[0], params.resolution[1]
+        if color is None:
+            color = np.zeros((H, W, 4), np.float32)
+        cnt = Counters()
+        t = None if tile is None else (C.c_int * 4)(*tile)
+        self.lib.vro_trace(C.byref(scene), C.byref(params), first_sample, n_samples, t, accum_mode, _ptr(color),
+                           C.byref(cnt), n_threads)
+        return color, cnt
+
+    def trace_deterministic(self, scene, params: Params, n_threads=0):
+        W, H = params.resolution[0], params.resolution[1]
+        color = np.zeros((H, W, 4), np.float32)
+        self.lib.vro_trace_deterministic(C.byref(scene), C.byref(params), _ptr(color), n_threads)
+        return color
+
+    def tonemap_inplace(self, color, exposure, gamma):
+        color = np.ascontiguousarray(color, np.float32).copy()
+        self.lib.vro_tonemap_inplace(_ptr(color), color.shape[1], color.shape[0], exposure, gamma)
+        return color
+
+    def draw(self, color, exposure, gamma, tonemapping=True):
+        color = np.ascontiguousarray(color, np.float32)
+        out = np.empty(color.shape[:2] + (4,), np.uint8)
+        self.lib.vro_draw(_ptr(color), color.shape[1], color.shape[0], exposure, gamma, int(tonemapping), _ptr(out))
+        return out
+
+    def color_to_ldr(self, color):
+        color = np.ascontiguousarray(color, np.float32)
+        out = np.empty(color.shape[:2] + (4,), np.uint8)
+        self.lib.vro_color_to_ldr(_ptr(color), color.shape[1], color.shape[0], _ptr(out))
+        return out
+
+    def max_threads(self):
+        return int(self.lib.vro_max_threads())
+
+
+class VoldataRef:
+    """The compiled, unmodified reference voldata (oracle/_ref). None-able: check available()."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        L = self.lib = C.CDLL(REF_SO)
+        L.ref_to_half.restype = C.c_uint16
+        L.ref_to_half.argtypes = [C.c_float]
+        L.ref_from_half.restype = C.c_float
+        L.ref_from_half.argtypes = [C.c_uint16]
+        for name in ("ref_dense_from_float", "ref_dense_from_u8"):
+            getattr(L, name).restype = C.c_void_p
+            getattr(L, name).argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.ref_dense_set_range.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.ref_dense_info.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_float * 2]
+        L.ref_dense_voxels.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_dense_free.argtypes = [C.c_void_p]
+        L.ref_dense_load.restype = C.c_void_p
+        L.ref_dense_load.argtypes = [C.c_char_p]
+        L.ref_dense_write.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_brick_from_dense.restype = C.c_void_p
+        L.ref_brick_from_dense.argtypes = [C.c_void_p]
+        L.ref_brick_load.restype = C.c_void_p
+        L.ref_brick_load.argtypes = [C.c_char_p]
+        L.ref_brick_write.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_brick_info.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_uint32 * 3, C.c_float * 2,
+                                     C.POINTER(C.c_uint64), C.c_float * 16, C.POINTER(C.c_uint32)]
+        L.ref_brick_copy.argtypes = [C.c_void_p] * 7
+        L.ref_brick_decode_all.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_brick_free.argtypes = [C.c_void_p]
+
+    def to_half(self, f):
+        return int(self.lib.ref_to_half(float(f)))
+
+    def from_half(self, h):
+        return float(self.lib.ref_from_half(int(h)))
+
+    def dense_from_float(self, data):
+        data = np.ascontiguousarray(data, np.float32)
+        d, h, w = data.shape
+        g = self.lib.ref_dense_from_float(w, h, d, _ptr(data))
+        out = np.empty(data.shape, np.uint8)
+        dim = (C.c_uint32 * 3)()
+        mm = (C.c_float * 2)()
+        self.lib.ref_dense_info(g, dim, mm)
+        self.lib.ref_dense_voxels(g, _ptr(out))
+        self.lib.ref_dense_free(g)
+        return out, (float(mm[0]), float(mm[1]))
+
+    def _brick_to_data(self, b) -> BrickGridData:
+        nb = (C.c_uint32 * 3)()
+        ad = (C.c_uint32 * 3)()
+        mm = (C.c_float * 2)()
+        cnt = C.c_uint64()
+        tr = (C.c_float * 16)()
+        nm = C.c_uint32()
+        self.lib.ref_brick_info(b, nb, ad, mm, C.byref(cnt), tr, C.byref(nm))
+        ind, rng, atlas, mips = alloc_brick_arrays(tuple(nb), tuple(ad))
+        self.lib.ref_brick_copy(b, _ptr(ind), _ptr(rng), _ptr(atlas), _ptr(mips[0]), _ptr(mips[1]), _ptr(mips[2]))
+        transform = np.array(list(tr), np.float32).reshape(4, 4)  # rows of this array = glm columns
+        return BrickGridData(tuple(nb), tuple(ad), cnt.value, ind, rng, atlas, mips, (mm[0], mm[1]), transform)
+
+    def brick_build(self, vox_u8, vmin, vmax, decode=False):
+        vox = np.ascontiguousarray(vox_u8, np.uint8)
+        d, h, w = vox.shape
+        g = self.lib.ref_dense_from_u8(w, h, d, _ptr(vox))
+        self.lib.ref_dense_set_range(g, vmin, vmax)
+        b = self.lib.ref_brick_from_dense(g)
+        self.lib.ref_dense_free(g)
+        if not b:
+            raise RuntimeError("exceeded max brick count of 1024")
+        data = self._brick_to_data(b)
+        dec = None
+        if decode:
+            e = data.index_extent()
+            dec = np.empty((e[2], e[1], e[0]), np.float32)
+            self.lib.ref_brick_decode_all(b, _ptr(dec))
+        self.lib.ref_brick_free(b)
+        return (data, dec) if decode else data
+
+    def brick_load(self, path) -> BrickGridData:
+        b = self.lib.ref_brick_load(path.encode())
+        if not b:
+            raise RuntimeError("cannot load " + path)
+        data = self._brick_to_data(b)
+        self.lib.ref_brick_free(b)
+        return data
+
+    def brick_roundtrip_write(self, vox_u8, vmin, vmax, path):
+        vox = np.ascontiguousarray(vox_u8, np.uint8)
+        d, h, w = vox.shape
+        g = self.lib.ref_dense_from_u8(w, h, d, _ptr(vox))
+        self.lib.ref_dense_set_range(g, vmin, vmax)
+        b = self.lib.ref_brick_from_dense(g)
+        self.lib.ref_brick_write(b, path.encode())
+        self.lib.ref_brick_free(b)
+        self.lib.ref_dense_free(g)
+
+    def dense_write(self, vox_u8, vmin, vmax, path):
+        vox = np.ascontiguousarray(vox_u8, np.uint8)
+        d, h, w = vox.shape
+        g = self.lib.ref_dense_from_u8(w, h, d, _ptr(vox))
+        self.lib.ref_dense_set_range(g, vmin, vmax)
+        self.lib.ref_dense_write(g, path.encode())
+        self.lib.ref_dense_free(g)

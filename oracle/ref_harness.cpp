@@ -1,0 +1,130 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into the product.
+//
+// C-callable harness around the *unmodified* reference voldata sources
+// (/root/reference/submodules/voldata/src/{grid,grid_dense,grid_brick}.cpp), which are compiled
+// where they lie by oracle/Makefile into oracle/_ref/libvoldata_ref.so. It is used to
+//   (1) pin oracle/vr_oracle.c (the CPU restatement) bit-exactly, and
+//   (2) generate the golden vectors under tests/golden/ (tests/golden/make_golden.py).
+// It cannot travel to the GPU box as source (it needs /root/reference at compile time); the
+// built .so does travel, but the -m gpu tests only rely on vr_oracle.c + committed goldens.
+//
+// The cereal archive layout is the one declared at voldata/src/serialization.cpp:16-43 (that file
+// itself cannot be compiled here because it drags in OpenVDB/NanoVDB headers), so the field order
+// is re-declared below against the reference's own cereal headers.
+
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <string>
+
+#include "grid_dense.h"
+#include "grid_brick.h"
+
+#include <cereal/types/utility.hpp>
+#include <cereal/types/atomic.hpp>
+#include <cereal/types/vector.hpp>
+#include <cereal/archives/portable_binary.hpp>
+#include <glm/detail/type_half.hpp>
+
+namespace cereal {
+    template <class Archive> void serialize(Archive& ar, glm::uvec3& v) { ar(v.x, v.y, v.z); }
+    template <class Archive> void serialize(Archive& ar, glm::vec4& v) { ar(v.x, v.y, v.z, v.w); }
+    template <class Archive> void serialize(Archive& ar, glm::mat4& m) { ar(m[0], m[1], m[2], m[3]); }
+}
+namespace voldata {
+    template <class Archive, typename T> void serialize(Archive& ar, Buf3D<T>& buf) { ar(buf.stride, buf.data); }
+    template <class Archive> void serialize(Archive& ar, DenseGrid& g) {
+        ar(g.transform, g.n_voxels, g.min_value, g.max_value, g.voxel_data);
+    }
+    template <class Archive> void serialize(Archive& ar, BrickGrid& g) {
+        ar(g.transform, g.n_bricks, g.min_maj, g.brick_counter, g.indirection, g.range, g.atlas, g.range_mipmaps);
+    }
+}
+
+using namespace voldata;
+
+extern "C" {
+
+// ---- glm half conversion (glm/detail/type_half.inl) ----
+uint16_t ref_to_half(float f) { return uint16_t(glm::detail::toFloat16(f)); }
+float ref_from_half(uint16_t h) { return glm::detail::toFloat32(glm::detail::hdata(h)); }
+
+// ---- DenseGrid ----
+void* ref_dense_from_float(uint32_t w, uint32_t h, uint32_t d, const float* data) { return new DenseGrid(w, h, d, data); }
+void* ref_dense_from_u8(uint32_t w, uint32_t h, uint32_t d, const uint8_t* data) { return new DenseGrid(w, h, d, data); }
+void ref_dense_set_range(void* g, float lo, float hi) { ((DenseGrid*)g)->min_value = lo; ((DenseGrid*)g)->max_value = hi; }
+void ref_dense_info(void* g, uint32_t dim[3], float minmax[2]) {
+    auto* gr = (DenseGrid*)g;
+    dim[0] = gr->n_voxels.x; dim[1] = gr->n_voxels.y; dim[2] = gr->n_voxels.z;
+    minmax[0] = gr->min_value; minmax[1] = gr->max_value;
+}
+void ref_dense_voxels(void* g, uint8_t* out) { auto* gr = (DenseGrid*)g; memcpy(out, gr->voxel_data.data(), gr->voxel_data.size()); }
+float ref_dense_lookup(void* g, uint32_t x, uint32_t y, uint32_t z) { return ((DenseGrid*)g)->lookup(glm::uvec3(x, y, z)); }
+void ref_dense_free(void* g) { delete (DenseGrid*)g; }
+void* ref_dense_load(const char* path) {
+    std::ifstream file(path, std::ios::binary);
+    if (!file.is_open()) return nullptr;
+    cereal::PortableBinaryInputArchive archive(file);
+    auto* g = new DenseGrid();
+    archive(*g);
+    return g;
+}
+int ref_dense_write(void* g, const char* path) {
+    std::ofstream file(path, std::ios::binary);
+    if (!file.is_open()) return -1;
+    cereal::PortableBinaryOutputArchive archive(file);
+    archive(*(DenseGrid*)g);
+    return 0;
+}
+
+// ---- BrickGrid ----
+void* ref_brick_from_dense(void* dense) {
+    try { return new BrickGrid(*(DenseGrid*)dense); } catch (std::runtime_error&) { return nullptr; }
+}
+void* ref_brick_load(const char* path) {
+    std::ifstream file(path, std::ios::binary);
+    if (!file.is_open()) return nullptr;
+    cereal::PortableBinaryInputArchive archive(file);
+    auto* g = new BrickGrid();
+    archive(*g);
+    return g;
+}
+int ref_brick_write(void* g, const char* path) {
+    std::ofstream file(path, std::ios::binary);
+    if (!file.is_open()) return -1;
+    cereal::PortableBinaryOutputArchive archive(file);
+    archive(*(BrickGrid*)g);
+    return 0;
+}
+void ref_brick_info(void* g, uint32_t n_bricks[3], uint32_t atlas_dim[3], float min_maj[2], uint64_t* counter,
+                    float transform[16], uint32_t* n_mips) {
+    auto* b = (BrickGrid*)g;
+    n_bricks[0] = b->n_bricks.x; n_bricks[1] = b->n_bricks.y; n_bricks[2] = b->n_bricks.z;
+    atlas_dim[0] = b->atlas.stride.x; atlas_dim[1] = b->atlas.stride.y; atlas_dim[2] = b->atlas.stride.z;
+    min_maj[0] = b->min_maj.first; min_maj[1] = b->min_maj.second;
+    *counter = b->brick_counter;
+    memcpy(transform, &b->transform[0][0], 64);
+    *n_mips = uint32_t(b->range_mipmaps.size());
+}
+void ref_brick_copy(void* g, uint32_t* indirection, uint32_t* range, uint8_t* atlas, uint32_t* mip0, uint32_t* mip1, uint32_t* mip2) {
+    auto* b = (BrickGrid*)g;
+    if (indirection) memcpy(indirection, b->indirection.data.data(), b->indirection.data.size() * 4);
+    if (range) memcpy(range, b->range.data.data(), b->range.data.size() * 4);
+    if (atlas) memcpy(atlas, b->atlas.data.data(), b->atlas.data.size());
+    uint32_t* mips[3] = { mip0, mip1, mip2 };
+    for (size_t i = 0; i < 3 && i < b->range_mipmaps.size(); ++i)
+        if (mips[i]) memcpy(mips[i], b->range_mipmaps[i].data.data(), b->range_mipmaps[i].data.size() * 4);
+}
+float ref_brick_lookup(void* g, uint32_t x, uint32_t y, uint32_t z) { return ((BrickGrid*)g)->lookup(glm::uvec3(x, y, z)); }
+// decode every voxel of the padded index extent through BrickGrid::lookup (grid_brick.cpp:148-154)
+void ref_brick_decode_all(void* g, float* out) {
+    auto* b = (BrickGrid*)g;
+    const glm::uvec3 e = b->index_extent();
+    size_t i = 0;
+    for (uint32_t z = 0; z < e.z; ++z) for (uint32_t y = 0; y < e.y; ++y) for (uint32_t x = 0; x < e.x; ++x)
+        out[i++] = b->lookup(glm::uvec3(x, y, z));
+}
+void ref_brick_free(void* g) { delete (BrickGrid*)g; }
+
+}
