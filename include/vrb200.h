@@ -185,6 +185,9 @@ int vrb_download_framebuffer(vrb_ctx* ctx, uint8_t* rgba8);
 int vrb_upload_color(vrb_ctx* ctx, const float* rgba);
 /* device pointer of the float4 colour buffer (for NCCL reductions issued by the host runtime) */
 void* vrb_color_device_ptr(vrb_ctx* ctx);
+/* render into a caller-owned device buffer (w*h float4, e.g. a torch tensor that NCCL reduces) instead of
+ * the context's own; the caller keeps ownership and must outlive the binding (undone by vrb_resize) */
+int vrb_bind_color(vrb_ctx* ctx, void* device_rgba32f);
 
 /* ---- multi-GPU (new) --------------------------------------------------------------- */
 /* single-process helper: sum the colour buffers of n contexts (one per device) into ctxs[root]

@@ -26,38 +26,8 @@ def build(ref: bool = True) -> None:
                    check=True)
 
 
-class Params(C.Structure):
-    """Mirror of vrb_params (include/vrb200.h). Shared by the oracle and the C-ABI tests."""
-    _fields_ = [
-        ("bounces", C.c_int32), ("seed", C.c_int32), ("show_environment", C.c_int32), ("frame", C.c_int32),
-        ("cam_pos", C.c_float * 3), ("cam_fov", C.c_float), ("cam_transform", C.c_float * 9),
-        ("vol_bb_min", C.c_float * 3), ("vol_bb_max", C.c_float * 3),
-        ("vol_minorant", C.c_float), ("vol_majorant", C.c_float), ("vol_inv_majorant", C.c_float),
-        ("vol_albedo", C.c_float * 3), ("vol_phase_g", C.c_float), ("vol_density_scale", C.c_float),
-        ("vol_emission_scale", C.c_float), ("vol_emission_norm", C.c_float),
-        ("vol_density_transform", C.c_float * 16), ("vol_density_inv_transform", C.c_float * 16),
-        ("has_emission", C.c_int32),
-        ("vol_emission_transform", C.c_float * 16), ("vol_emission_inv_transform", C.c_float * 16),
-        ("use_transferfunc", C.c_int32), ("tf_window_left", C.c_float), ("tf_window_width", C.c_float),
-        ("env_transform", C.c_float * 9), ("env_inv_transform", C.c_float * 9), ("env_strength", C.c_float),
-        ("resolution", C.c_int32 * 2),
-    ]
-
-
-class BrickView(C.Structure):
-    """Mirror of vrb_brick_view."""
-    _fields_ = [
-        ("n_bricks", C.c_uint32 * 3), ("atlas_dim", C.c_uint32 * 3), ("brick_count", C.c_uint64),
-        ("indirection", C.c_void_p), ("range", C.c_void_p), ("atlas", C.c_void_p),
-        ("range_mips", C.c_void_p * 3),
-    ]
-
-
-class Counters(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("n_samples", "n_maj", "n_dens", "n_emis", "n_nee", "n_env", "n_real")]
-
-    def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+from volren_b200._capi import BrickView, Counters, Params  # shared PODs (include/vrb200.h)
+from volren_b200.formats import BrickGridData as _BGD
 
 
 class _Grid(C.Structure):
@@ -83,20 +53,8 @@ def mip_dims(n_bricks, level):
     return tuple(int(n) >> (level + 1) for n in n_bricks)
 
 
-class BrickGridData:
-    """Plain numpy holder of one brick grid (voldata/src/grid_brick.h:27-33); arrays are [z][y][x]."""
-
-    def __init__(self, n_bricks, atlas_dim, brick_count, indirection, range_, atlas, mips, min_maj=(0.0, 0.0),
-                 transform=None):
-        self.n_bricks = tuple(int(v) for v in n_bricks)
-        self.atlas_dim = tuple(int(v) for v in atlas_dim)
-        self.brick_count = int(brick_count)
-        self.indirection = np.ascontiguousarray(indirection, dtype=np.uint32)
-        self.range = np.ascontiguousarray(range_, dtype=np.uint32)
-        self.atlas = np.ascontiguousarray(atlas, dtype=np.uint8)
-        self.mips = [np.ascontiguousarray(m, dtype=np.uint32) for m in mips]
-        self.min_maj = (float(min_maj[0]), float(min_maj[1]))
-        self.transform = np.eye(4, dtype=np.float32) if transform is None else np.asarray(transform, np.float32)
+class BrickGridData(_BGD):
+    """formats.BrickGridData + the ctypes views the oracle needs."""
 
     def view(self) -> BrickView:
         v = BrickView()
@@ -110,19 +68,17 @@ class BrickGridData:
             v.range_mips[i] = _ptr(self.mips[i])
         return v
 
-    def _grid(self) -> _Grid:
-        g = _Grid()
-        g.n_bricks[:] = self.n_bricks
-        g.atlas_dim[:] = self.atlas_dim
-        g.indirection = _ptr(self.indirection)
-        g.range = _ptr(self.range)
-        g.atlas = _ptr(self.atlas)
+    @staticmethod
+    def grid_of(g) -> "_Grid":
+        out = _Grid()
+        out.n_bricks[:] = g.n_bricks
+        out.atlas_dim[:] = g.atlas_dim
+        out.indirection = _ptr(g.indirection)
+        out.range = _ptr(g.range)
+        out.atlas = _ptr(g.atlas)
         for i in range(3):
-            g.range_mips[i] = _ptr(self.mips[i])
-        return g
-
-    def index_extent(self):
-        return tuple(8 * n for n in self.n_bricks)
+            out.range_mips[i] = _ptr(g.mips[i])
+        return out
 
 
 def alloc_brick_arrays(n_bricks, atlas_dim=None):
@@ -229,9 +185,9 @@ class Oracle:
 
     def make_scene(self, density: BrickGridData, env_rgb, impmap, lut=None, emission: BrickGridData | None = None):
         sc = _Scene()
-        sc.density = density._grid()
+        sc.density = BrickGridData.grid_of(density)
         if emission is not None:
-            sc.emission = emission._grid()
+            sc.emission = BrickGridData.grid_of(emission)
         env_rgb = np.ascontiguousarray(env_rgb, np.float32)
         sc.env_rgb = _ptr(env_rgb)
         sc.env_h, sc.env_w = env_rgb.shape[0], env_rgb.shape[1]

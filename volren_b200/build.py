@@ -1,0 +1,70 @@
+"""Build script for the native parts of volren_b200 (in-tree, sm_100a only).
+
+    python -m volren_b200.build [--host] [--force]
+
+libvrb200.so   : CUDA kernels + C ABI (include/vrb200.h)          <- volren_b200/csrc/*.cu
+volpy*.so, volren (with --host): C++ host mirroring the reference Renderer/CLI/pybind surface
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+HOST = os.path.join(PKG, "host")
+LIB = os.path.join(PKG, "libvrb200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build_cuda(force=False, verbose=False):
+    sources = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "vrb200.h")]
+    if not force and not _newer(LIB, sources):
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "vrb200.cu")]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def host_targets():
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    return os.path.join(PKG, "volpy" + ext), os.path.join(PKG, "volren")
+
+
+def build_host(force=False):
+    if not os.path.isdir(HOST) or not os.path.exists(os.path.join(HOST, "Makefile")):
+        return None
+    subprocess.run(["make", "-s", "-C", HOST] + (["-B"] if force else []), check=True)
+    return host_targets()
+
+
+def build_all(force=False):
+    build_cuda(force)
+    build_host(force)
+
+
+if __name__ == "__main__":
+    force = "--force" in sys.argv
+    build_cuda(force, verbose="-v" in sys.argv)
+    if "--host" in sys.argv:
+        build_host(force)
+    print("built", LIB)

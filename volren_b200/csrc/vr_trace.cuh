@@ -1,0 +1,493 @@
+// The tracking kernels: shader/pathtracer_brick.glsl + pathtracer_brick_tf.glsl + the parts of
+// shader/common.glsl they reach (USE_DDA): brick-DDA majorant delta tracking, envmap NEE with MIS,
+// Russian roulette, Henyey-Greenstein, LUT transfer function. One template, two variants (TF on/off),
+// plus a counting build (COUNT) that emits the event counters defining the algorithmic bytes.
+#pragma once
+
+#include "vr_common.cuh"
+#include "vr_env.cuh"
+#include "../../include/vrb200.h"
+
+namespace vr {
+
+struct GridView {
+    uint3 nb;                  // n_bricks (level 0)
+    const uint2* rec;          // {atlas slot, range word} per brick
+    const uint32_t* mips[3];   // range words of levels 1..3 (dims nb >> level)
+    const uint8_t* atlas_lin;  // slot * 512 + z*64 + y*8 + x
+};
+
+struct TraceArgs {
+    vrb_params p;
+    GridView density, emission;
+    EnvView env;
+    const float4* lut;
+    uint32_t tf_size;
+    float4* color;
+    int x0, y0, x1, y1;
+    int first_sample, n_samples, accum_mode;
+    unsigned long long* counters;  // 7 x u64 (vrb_counters order) or nullptr
+    Mat4 emis_from_density;        // vol_emission_inv_transform * vol_density_transform (common.glsl:325)
+};
+
+template <bool COUNT> struct Cnt;
+template <> struct Cnt<false> {
+    VR_DEV void maj() {} VR_DEV void dens() {} VR_DEV void emis() {} VR_DEV void nee() {} VR_DEV void env() {} VR_DEV void real() {} VR_DEV void samp() {}
+};
+template <> struct Cnt<true> {
+    uint32_t n_samp = 0, n_maj = 0, n_dens = 0, n_emis = 0, n_nee = 0, n_env = 0, n_real = 0;
+    VR_DEV void maj() { ++n_maj; } VR_DEV void dens() { ++n_dens; } VR_DEV void emis() { ++n_emis; } VR_DEV void nee() { ++n_nee; }
+    VR_DEV void env() { ++n_env; } VR_DEV void real() { ++n_real; } VR_DEV void samp() { ++n_samp; }
+};
+
+// exact u8 / 255.f (GL unorm8 -> float) without a divide: reciprocal multiply + one FMA correction step
+VR_DEV float unorm8_to_float(uint32_t u) {
+    const float x = float(u);
+    const float r = 1.f / 255.f;
+    const float q = x * r;
+    const float rem = fmaf(-q, 255.f, x);
+    return fmaf(rem, r, q);
+}
+
+// texelFetch chain of lookup_density_brick / lookup_temperature_brick (common.glsl:268-275, :314-321);
+// out-of-bounds fetches return 0 (robust access), which makes the value 0 + 0 * (0 - 0).
+VR_DEV float brick_value(const GridView& g, int x, int y, int z) {
+    const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+    if (unsigned(bx) >= g.nb.x || unsigned(by) >= g.nb.y || unsigned(bz) >= g.nb.z) return 0.f;
+    const uint2 r = __ldg(g.rec + (size_t(bz) * g.nb.y + by) * g.nb.x + bx);
+    const float lo = range_lo(r.y), hi = range_hi(r.y);
+    float unorm = 0.f;
+    if (r.x != 0xffffffffu)
+        unorm = unorm8_to_float(__ldg(g.atlas_lin + size_t(r.x) * 512u + uint32_t(((z & 7) << 6) | ((y & 7) << 3) | (x & 7))));
+    return lo + unorm * (hi - lo);
+}
+
+// lookup_majorant (common.glsl:278-281) without the density_scale factor
+VR_DEV float brick_majorant(const GridView& g, float3 ipos, int mip) {
+    const int bx = int(floorf(ipos.x)) >> (3 + mip), by = int(floorf(ipos.y)) >> (3 + mip), bz = int(floorf(ipos.z)) >> (3 + mip);
+    const uint32_t nx = g.nb.x >> mip, ny = g.nb.y >> mip, nz = g.nb.z >> mip;
+    if (unsigned(bx) >= nx || unsigned(by) >= ny || unsigned(bz) >= nz) return 0.f;
+    const size_t i = (size_t(bz) * ny + by) * nx + bx;
+    const uint32_t w = mip == 0 ? __ldg(&g.rec[i].y) : __ldg(g.mips[mip - 1] + i);
+    return range_hi(w);
+}
+
+// stochastic_tricubic_filter (common.glsl:221-244): 9 draws, weighted reservoir over the 4 B-spline taps
+VR_DEV int3 stochastic_tricubic_filter(float3 ipos, uint32_t& seed) {
+    const float qx = ipos.x - 0.5f, qy = ipos.y - 0.5f, qz = ipos.z - 0.5f;
+    const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+    const float t[3] = { qx - fx, qy - fy, qz - fz };
+    int idx[3];
+    float r[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r[i] = rng(seed);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float t1 = t[a], t2 = t1 * t1;
+        float w = (1.f / 6.f) * (-t1 * t2 + 3 * t2 - 3 * t1 + 1);
+        float sum = w;
+        int k = 0;
+        w = (1.f / 6.f) * (3 * t1 * t2 - 6 * t2 + 4);
+        sum = w + sum;
+        if (r[a] < w / fmaxf(1e-3f, sum)) k = 1;
+        w = (1.f / 6.f) * (-3 * t1 * t2 + 3 * t2 + 3 * t1 + 1);
+        sum = w + sum;
+        if (r[3 + a] < w / fmaxf(1e-3f, sum)) k = 2;
+        w = (1.f / 6.f) * t1 * t2;
+        sum = w + sum;
+        if (r[6 + a] < w / fmaxf(1e-3f, sum)) k = 3;
+        idx[a] = k;
+    }
+    return make_int3(int(fx) + idx[0] - 1, int(fy) + idx[1] - 1, int(fz) + idx[2] - 1);
+}
+
+// tf_window + tf_lookup (common.glsl:203-212)
+VR_DEV float4 tf_lookup(const TraceArgs& a, float d) {
+    const float tc = fminf(fmaxf((d - a.p.tf_window_left) / a.p.tf_window_width, 0.0f), 1.0f - 1e-6f);
+    const float s = tc * float(a.tf_size);
+    const float fl = floorf(s);
+    const int idx = int(fl);
+    const float f = s - fl;
+    const uint32_t idx1 = min(uint32_t(idx + 1), a.tf_size - 1u);
+    const float4 A = __ldg(a.lut + idx), B = __ldg(a.lut + idx1);
+    return make_float4(mixf(A.x, B.x, f), mixf(A.y, B.y, f), mixf(A.z, B.z, f), mixf(A.w, B.w, f));
+}
+// only the alpha channel (majorant mapping, common.glsl:425/472)
+VR_DEV float tf_lookup_alpha(const TraceArgs& a, float d) {
+    const float tc = fminf(fmaxf((d - a.p.tf_window_left) / a.p.tf_window_width, 0.0f), 1.0f - 1e-6f);
+    const float s = tc * float(a.tf_size);
+    const float fl = floorf(s);
+    const int idx = int(fl);
+    const float f = s - fl;
+    const uint32_t idx1 = min(uint32_t(idx + 1), a.tf_size - 1u);
+    return mixf(__ldg(&a.lut[idx].w), __ldg(&a.lut[idx1].w), f);
+}
+
+// lookup_density_trilinear (common.glsl:289-297) without density_scale
+VR_DEV float density_trilinear(const GridView& g, float3 ipos) {
+    const float qx = ipos.x - 0.5f, qy = ipos.y - 0.5f, qz = ipos.z - 0.5f;
+    const float flx = floorf(qx), fly = floorf(qy), flz = floorf(qz);
+    const float fx = qx - flx, fy = qy - fly, fz = qz - flz;
+    const int x = int(flx), y = int(fly), z = int(flz);
+    const float lx0 = mixf(brick_value(g, x, y, z), brick_value(g, x + 1, y, z), fx);
+    const float lx1 = mixf(brick_value(g, x, y + 1, z), brick_value(g, x + 1, y + 1, z), fx);
+    const float hx0 = mixf(brick_value(g, x, y, z + 1), brick_value(g, x + 1, y, z + 1), fx);
+    const float hx1 = mixf(brick_value(g, x, y + 1, z + 1), brick_value(g, x + 1, y + 1, z + 1), fx);
+    return mixf(mixf(lx0, lx1, fy), mixf(hx0, hx1, fy), fz);
+}
+
+// lookup_emission (common.glsl:324-328). Without an emission grid the samplers are unbound (value 0) but the
+// tricubic filter still consumes 9 draws: that case is an O(1) LCG jump.
+VR_DEV float3 lookup_emission(const TraceArgs& a, float3 ipos, uint32_t& seed, bool& fetched) {
+    fetched = false;
+    if (!a.p.has_emission) { rng_skip<9>(seed); return f3(0.f); }
+    const float3 ipos_e = mul_point(a.emis_from_density, ipos);
+    const int3 tap = stochastic_tricubic_filter(ipos_e, seed);
+    fetched = true;
+    const float t = brick_value(a.emission, tap.x, tap.y, tap.z) * a.p.vol_emission_norm;
+    return a.p.vol_emission_scale * f3(sqr(t), sqr(sqr(t)), sqr(sqr(sqr(t))));
+}
+
+// intersect_box (common.glsl:157-165)
+VR_DEV bool intersect_box(float3 pos, float3 dir, const float* bb_min, const float* bb_max, float& tnear, float& tfar) {
+    const float3 inv = f3(1.f / dir.x, 1.f / dir.y, 1.f / dir.z);
+    const float3 lo = (f3(bb_min[0], bb_min[1], bb_min[2]) - pos) * inv;
+    const float3 hi = (f3(bb_max[0], bb_max[1], bb_max[2]) - pos) * inv;
+    const float3 tmin = f3(fminf(lo.x, hi.x), fminf(lo.y, hi.y), fminf(lo.z, hi.z));
+    const float3 tmax = f3(fmaxf(lo.x, hi.x), fmaxf(lo.y, hi.y), fmaxf(lo.z, hi.z));
+    tnear = fmaxf(0.f, fmaxf(tmin.x, fmaxf(tmin.y, tmin.z)));
+    tfar = fminf(tmax.x, fminf(tmax.y, tmax.z));
+    return tnear <= tfar;
+}
+
+// stepDDA (common.glsl:404-409)
+VR_DEV float step_dda(float3 pos, float3 ri, int mip) {
+    const float dim = float(8 << mip), inv_dim = 1.f / dim;  // exact powers of two
+    const float ox = ri.x >= 0.f ? dim + 0.5f : -0.5f;
+    const float oy = ri.y >= 0.f ? dim + 0.5f : -0.5f;
+    const float oz = ri.z >= 0.f ? dim + 0.5f : -0.5f;
+    const float tx = (floorf(pos.x * inv_dim) * dim + ox - pos.x) * ri.x;
+    const float ty = (floorf(pos.y * inv_dim) * dim + oy - pos.y) * ri.y;
+    const float tz = (floorf(pos.z * inv_dim) * dim + oz - pos.z) * ri.z;
+    return fminf(tx, fminf(ty, tz));
+}
+
+// GLSL round() is implementation-defined at .5; Mesa lowers it to round-half-even
+VR_DEV int round_mip(float mip) { return __float2int_rn(mip); }
+
+VR_DEV float phase_hg(float cos_t, float g) {  // common.glsl:172-175
+    const float denom = 1 + sqr(g) + 2 * g * cos_t;
+    return INV_4PI * (1 - sqr(g)) / (denom * sqrtf(denom));
+}
+VR_DEV float3 align_to(float3 N, float3 v) {  // common.glsl:25-33
+    const float3 T = fabsf(N.x) > fabsf(N.y) ? f3(-N.z, 0.f, N.x) / sqrtf(N.x * N.x + N.z * N.z)
+                                             : f3(0.f, N.z, -N.y) / sqrtf(N.y * N.y + N.z * N.z);
+    const float3 B = cross(N, T);
+    return normalize(v.x * T + v.y * B + v.z * N);
+}
+VR_DEV float3 sample_phase_hg(float3 dir, float g, float s0, float s1) {  // common.glsl:184-190
+    const float cos_t = fabsf(g) < 1e-4f ? 1.f - 2.f * s0 : (1 + sqr(g) - sqr((1 - sqr(g)) / (1 - g + 2 * g * s0))) / (2 * g);
+    const float sin_t = sqrtf(fmaxf(0.f, 1.f - sqr(cos_t)));
+    const float phi = 2.f * PI_F * s1;
+    float sp, cp;
+    sincosf(phi, &sp, &cp);
+    return align_to(dir, f3(sin_t * cp, sin_t * sp, cos_t));
+}
+
+// lookup_environment (common.glsl:93-98)
+VR_DEV float3 lookup_environment(const TraceArgs& a, float3 dir) {
+    const float3 idir = mul(*reinterpret_cast<const Mat3*>(a.p.env_inv_transform), dir);
+    const float u = atan2f(idir.z, idir.x) / (2 * PI_F) + 0.5f;
+    const float v = 1.f - acosf(fminf(fmaxf(idir.y, -1.f), 1.f)) / PI_F;
+    return a.p.env_strength * env_texture(a.env, u, v);
+}
+// pdf_environment (common.glsl:148-152)
+VR_DEV float pdf_environment(const TraceArgs& a, float3 Le_dir) {
+    const float avg_w = __ldg(a.env.impmap + imp_offset(9));
+    return luma(Le_dir) / avg_w * INV_4PI;
+}
+
+// sample_environment (common.glsl:100-146): hierarchical 2x2 warping down the importance pyramid
+VR_DEV float4 sample_environment(const TraceArgs& a, float px, float py, float3& w_i) {
+    int posx = 0, posy = 0;
+    uint32_t off = imp_offset(9);
+#pragma unroll
+    for (int mip = 8; mip >= 0; --mip) {
+        posx *= 2; posy *= 2;
+        const int d = IMP_DIM >> mip;
+        off -= uint32_t(d) * uint32_t(d);   // offset of level `mip`
+        const float* base = a.env.impmap + off + size_t(posy) * d + posx;
+        const float2 r0 = __ldg(reinterpret_cast<const float2*>(base));        // w[0], w[1]
+        const float2 r1 = __ldg(reinterpret_cast<const float2*>(base + d));    // w[2], w[3]
+        const float q0 = r0.x + r1.x, q1 = r0.y + r1.y;
+        const float dsplit = q0 / fmaxf(1e-8f, q0 + q1);
+        int off_x;
+        if (px < dsplit) { off_x = 0; px = px / dsplit; }
+        else { off_x = 1; px = (px - dsplit) / (1.f - dsplit); }
+        posx += off_x;
+        const float e = (off_x ? r0.y : r0.x) / (off_x ? q1 : q0);
+        if (py < e) { py = py / e; }
+        else { posy += 1; py = (py - e) / (1.f - e); }
+    }
+    const float uvx = (float(posx) + px) * (1.f / IMP_DIM), uvy = (float(posy) + py) * (1.f / IMP_DIM);
+    const float theta = saturate(1.f - uvy) * PI_F;
+    const float phi = (saturate(uvx) * 2.f - 1.f) * PI_F;
+    float st, ct, sp, cp;
+    sincosf(theta, &st, &ct);
+    sincosf(phi, &sp, &cp);
+    w_i = mul(*reinterpret_cast<const Mat3*>(a.p.env_transform), f3(st * cp, ct, st * sp));
+    const float3 Le = a.p.env_strength * env_texture(a.env, uvx, uvy);
+    const float avg_w = __ldg(a.env.impmap + imp_offset(9));
+    const float pdf = __ldg(a.env.impmap + size_t(posy) * IMP_DIM + posx) / avg_w;
+    return make_float4(Le.x, Le.y, Le.z, pdf * INV_4PI);
+}
+
+struct Ray {
+    float3 ipos, idir, ri;
+    float tnear, tfar;
+};
+VR_DEV bool setup_ray(const TraceArgs& a, float3 wpos, float3 wdir, Ray& r) {
+    if (!intersect_box(wpos, wdir, a.p.vol_bb_min, a.p.vol_bb_max, r.tnear, r.tfar)) return false;
+    const Mat4& M = *reinterpret_cast<const Mat4*>(a.p.vol_density_inv_transform);
+    r.ipos = mul_point(M, wpos);
+    r.idir = mul_dir(M, wdir);  // non-normalised
+    r.ri = f3(1.f / r.idir.x, 1.f / r.idir.y, 1.f / r.idir.z);
+    return true;
+}
+
+constexpr int MAX_DDA_ITERS = 1 << 22;  // hang guard only; never reached by finite rays
+
+template <bool TF, bool COUNT>
+VR_DEV float majorant_at(const TraceArgs& a, float3 curr, int mip, Cnt<COUNT>& cnt) {
+    cnt.maj();
+    const float m = a.p.vol_density_scale * brick_majorant(a.density, curr, mip);
+    if (TF) return a.p.vol_majorant * tf_lookup_alpha(a, m * a.p.vol_inv_majorant);
+    return m;
+}
+
+// transmittanceDDA (common.glsl:412-455)
+template <bool TF, bool COUNT>
+VR_DEV float transmittance_dda(const TraceArgs& a, float3 wpos, float3 wdir, uint32_t& seed, Cnt<COUNT>& cnt) {
+    Ray r;
+    if (!setup_ray(a, wpos, wdir, r)) return 1.f;
+    float t = r.tnear + 1e-6f, Tr = 1.f, tau = -logf(1.f - rng(seed)), mip = 3.f;
+    for (int it = 0; t < r.tfar && it < MAX_DDA_ITERS; ++it) {
+        const float3 curr = r.ipos + t * r.idir;
+        const int m = round_mip(mip);
+        const float majorant = majorant_at<TF, COUNT>(a, curr, m, cnt);
+        const float dt = step_dda(curr, r.ri, m);
+        t += dt;
+        tau -= majorant * dt;
+        mip = fminf(mip + 0.25f, 3.f);
+        if (tau > 0) continue;
+        t += tau / majorant;
+        if (t >= r.tfar) break;
+        cnt.dens();
+        float d;
+        if (TF) d = a.p.vol_majorant * tf_lookup_alpha(a, a.p.vol_density_scale * density_trilinear(a.density, r.ipos + t * r.idir) * a.p.vol_inv_majorant);
+        else {
+            const int3 tap = stochastic_tricubic_filter(r.ipos + t * r.idir, seed);
+            d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
+        }
+        if (rng(seed) * majorant < d) {
+            Tr *= fmaxf(0.f, 1.f - a.p.vol_majorant / majorant);
+            if (Tr < .1f) {
+                const float prob = 1 - Tr;
+                if (rng(seed) < prob) return 0.f;
+                Tr /= 1 - prob;
+            }
+        }
+        tau = -logf(1.f - rng(seed));
+        mip = fmaxf(0.f, mip - 2.f);
+    }
+    return Tr;
+}
+
+// sample_volumeDDA (common.glsl:458-501)
+template <bool TF, bool COUNT>
+VR_DEV bool sample_volume_dda(const TraceArgs& a, float3 wpos, float3 wdir, float& t_out, float3& throughput, float3& Le, uint32_t& seed, Cnt<COUNT>& cnt) {
+    Ray r;
+    if (!setup_ray(a, wpos, wdir, r)) return false;
+    const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+    float t = r.tnear + 1e-6f, tau = -logf(1.f - rng(seed)), mip = 3.f;
+    for (int it = 0; t < r.tfar && it < MAX_DDA_ITERS; ++it) {
+        const float3 curr = r.ipos + t * r.idir;
+        const int m = round_mip(mip);
+        const float majorant = majorant_at<TF, COUNT>(a, curr, m, cnt);
+        const float dt = step_dda(curr, r.ri, m);
+        t += dt;
+        tau -= majorant * dt;
+        mip = fminf(mip + 0.25f, 3.f);
+        if (tau > 0) continue;
+        t += tau / majorant;
+        if (t >= r.tfar) break;
+        cnt.dens();
+        const float3 at = r.ipos + t * r.idir;
+        float d;
+        float3 tf_rgb = f3(1.f);
+        if (TF) {
+            const float4 rgba = tf_lookup(a, a.p.vol_density_scale * density_trilinear(a.density, at) * a.p.vol_inv_majorant);
+            d = a.p.vol_majorant * rgba.w;
+            tf_rgb = f3(rgba.x, rgba.y, rgba.z);
+        } else {
+            const int3 tap = stochastic_tricubic_filter(at, seed);
+            d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
+        }
+        bool fetched;
+        const float3 em = lookup_emission(a, at, seed, fetched);
+        if (fetched) {
+            cnt.emis();
+            Le = Le + throughput * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant;
+        }
+        if (rng(seed) * majorant < d) {
+            throughput = throughput * albedo;
+            if (TF) throughput = throughput * tf_rgb;
+            t_out = t;
+            return true;
+        }
+        tau = -logf(1.f - rng(seed));
+        mip = fmaxf(0.f, mip - 2.f);
+    }
+    return false;
+}
+
+// trace_path (common.glsl:599-652)
+template <bool TF, bool COUNT>
+VR_DEV float4 trace_path(const TraceArgs& a, float3 pos, float3 dir, uint32_t& seed, Cnt<COUNT>& cnt) {
+    float3 L = f3(0.f), throughput = f3(1.f);
+    bool free_path = true;
+    uint32_t n_paths = 0;
+    float t = 0.f, f_p = 0.f;
+    while (sample_volume_dda<TF, COUNT>(a, pos, dir, t, throughput, L, seed, cnt)) {
+        cnt.real();
+        pos = pos + t * dir;
+        float3 w_i;
+        const float r0 = rng(seed), r1 = rng(seed);
+        cnt.nee();
+        const float4 Le_pdf = sample_environment(a, r0, r1, w_i);
+        if (Le_pdf.w > 0) {
+            f_p = phase_hg(dot(-dir, w_i), a.p.vol_phase_g);
+            const float mis_weight = a.p.show_environment > 0 ? power_heuristic(Le_pdf.w, f_p) : 1.f;
+            const float Tr = transmittance_dda<TF, COUNT>(a, pos, w_i, seed, cnt);
+            L = L + throughput * mis_weight * f_p * Tr * f3(Le_pdf.x, Le_pdf.y, Le_pdf.z) / Le_pdf.w;
+        }
+        if (++n_paths >= uint32_t(a.p.bounces)) { free_path = false; break; }
+        const float rr_val = luma(throughput);
+        if (rr_val < .1f) {
+            const float prob = 1 - rr_val;
+            if (rng(seed) < prob) { free_path = false; break; }
+            throughput = throughput / (1 - prob);
+        }
+        const float s0 = rng(seed), s1 = rng(seed);
+        const float3 scatter_dir = sample_phase_hg(dir, a.p.vol_phase_g, s0, s1);
+        f_p = phase_hg(dot(-dir, scatter_dir), a.p.vol_phase_g);
+        dir = scatter_dir;
+    }
+    if (free_path && a.p.show_environment > 0) {
+        cnt.env();
+        const float3 Le = lookup_environment(a, dir);
+        const float mis_weight = n_paths > 0 ? power_heuristic(f_p, pdf_environment(a, Le)) : 1.f;
+        L = L + throughput * mis_weight * Le;
+    }
+    return make_float4(L.x, L.y, L.z, fminf(float(n_paths), 1.f));
+}
+
+// view_dir (common.glsl:76-80)
+VR_DEV float3 view_dir(const TraceArgs& a, int x, int y, float sx, float sy) {
+    const float w = float(a.p.resolution[0]), h = float(a.p.resolution[1]);
+    const float px = (float(x) + sx - w * .5f) / h, py = (float(y) + sy - h * .5f) / h;
+    const float z = -.5f / tanf(.5f * PI_F * a.p.cam_fov / 180.f);
+    return normalize(mul(*reinterpret_cast<const Mat3*>(a.p.cam_transform), normalize(f3(px, py, z))));
+}
+
+// running mean of pathtracer_brick.glsl:36, unfused so that it matches mix() = x*(1-a) + y*a bit for bit
+VR_DEV float mix_rn(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, __fsub_rn(1.f, a)), __fmul_rn(y, a)); }
+
+VR_DEV void flush_counters(const TraceArgs&, const Cnt<false>&) {}
+VR_DEV void flush_counters(const TraceArgs& a, const Cnt<true>& c) {
+    const uint32_t v[7] = { c.n_samp, c.n_maj, c.n_dens, c.n_emis, c.n_nee, c.n_env, c.n_real };
+#pragma unroll
+    for (int i = 0; i < 7; ++i) atomicAdd(a.counters + i, (unsigned long long)v[i]);
+}
+
+// main() of pathtracer_brick.glsl:23-37, one thread per pixel, all requested samples of that pixel in
+// sample order (so the running mean is evaluated exactly like n successive dispatches).
+// Warps cover 8x4 pixel tiles for ray coherence.
+template <bool TF, bool COUNT>
+__global__ void __launch_bounds__(256) k_trace_pixels(const __grid_constant__ TraceArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = a.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = a.y0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    if (x >= a.x1 || y >= a.y1) return;
+    Cnt<COUNT> cnt;
+    const int W = a.p.resolution[0];
+    float4* px = a.color + size_t(y) * W + x;
+    float4 acc = *px;
+    const float3 cam = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
+    for (int s = a.first_sample; s < a.first_sample + a.n_samples; ++s) {
+        uint32_t seed = tea32(uint32_t(a.p.seed) * uint32_t(y * W + x), uint32_t(s));
+        const float jx = rng(seed), jy = rng(seed);
+        const float3 dir = view_dir(a, x, y, jx, jy);
+        float4 L = trace_path<TF, COUNT>(a, cam, dir, seed, cnt);
+        L.x = sanitize(L.x); L.y = sanitize(L.y); L.z = sanitize(L.z); L.w = sanitize(L.w);
+        cnt.samp();
+        if (a.accum_mode == VRB_ACCUM_MEAN) {
+            const float w = 1.f / float(s);
+            acc.x = mix_rn(acc.x, L.x, w); acc.y = mix_rn(acc.y, L.y, w); acc.z = mix_rn(acc.z, L.z, w); acc.w = mix_rn(acc.w, L.w, w);
+        } else {
+            acc.x += L.x; acc.y += L.y; acc.z += L.z; acc.w += L.w;
+        }
+    }
+    *px = acc;
+    flush_counters(a, cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic transmittance-only mode ("T1"): centre ray, exact voxel DDA with empty-brick
+// skipping, color = (Tr * Le_env(dir), 1 - Tr). fp32 on the device; the oracle evaluates it in fp64.
+__global__ void __launch_bounds__(256) k_trace_deterministic(const __grid_constant__ TraceArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    if (x >= a.p.resolution[0] || y >= a.p.resolution[1]) return;
+    const float3 dir = view_dir(a, x, y, .5f, .5f);
+    const float3 pos = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
+    Ray r;
+    float tau = 0.f;
+    if (setup_ray(a, pos, dir, r)) {
+        float t = r.tnear;
+        const GridView& g = a.density;
+        for (int it = 0; t < r.tfar && it < MAX_DDA_ITERS; ++it) {
+            const float tp = t + 1e-6f * (1.f + fabsf(t));
+            const float3 q = r.ipos + tp * r.idir;
+            const int vx = int(floorf(q.x)), vy = int(floorf(q.y)), vz = int(floorf(q.z));
+            // brick-level skip when the whole brick is empty (or out of bounds): cell size 8, else 1
+            const int bx = vx >> 3, by = vy >> 3, bz = vz >> 3;
+            bool empty = true;
+            uint2 rec = make_uint2(0xffffffffu, 0u);
+            if (unsigned(bx) < g.nb.x && unsigned(by) < g.nb.y && unsigned(bz) < g.nb.z) {
+                rec = __ldg(g.rec + (size_t(bz) * g.nb.y + by) * g.nb.x + bx);
+                empty = range_lo(rec.y) == 0.f && range_hi(rec.y) == 0.f;
+            }
+            const int cs = empty ? 8 : 1;
+            const int cx = empty ? bx * 8 : vx, cy = empty ? by * 8 : vy, cz = empty ? bz * 8 : vz;
+            float tnext = r.tfar;
+            if (r.idir.x > 0.f) tnext = fminf(tnext, (float(cx + cs) - r.ipos.x) * r.ri.x); else if (r.idir.x < 0.f) tnext = fminf(tnext, (float(cx) - r.ipos.x) * r.ri.x);
+            if (r.idir.y > 0.f) tnext = fminf(tnext, (float(cy + cs) - r.ipos.y) * r.ri.y); else if (r.idir.y < 0.f) tnext = fminf(tnext, (float(cy) - r.ipos.y) * r.ri.y);
+            if (r.idir.z > 0.f) tnext = fminf(tnext, (float(cz + cs) - r.ipos.z) * r.ri.z); else if (r.idir.z < 0.f) tnext = fminf(tnext, (float(cz) - r.ipos.z) * r.ri.z);
+            if (tnext <= t) tnext = tp;
+            if (!empty) {
+                const float lo = range_lo(rec.y), hi = range_hi(rec.y);
+                float unorm = 0.f;
+                if (rec.x != 0xffffffffu) unorm = unorm8_to_float(__ldg(g.atlas_lin + size_t(rec.x) * 512u + uint32_t(((vz & 7) << 6) | ((vy & 7) << 3) | (vx & 7))));
+                tau += (lo + unorm * (hi - lo)) * (tnext - t);
+            }
+            t = tnext;
+        }
+    }
+    const float Tr = expf(-a.p.vol_density_scale * tau);
+    const float3 Le = lookup_environment(a, dir);
+    a.color[size_t(y) * a.p.resolution[0] + x] = make_float4(Tr * Le.x, Tr * Le.y, Tr * Le.z, 1.f - Tr);
+}
+
+}  // namespace vr

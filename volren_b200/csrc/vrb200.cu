@@ -1,0 +1,696 @@
+// libvrb200.so -- C ABI (include/vrb200.h) over the sm_100a kernels. No CPU fallback: every entry
+// point either runs on the context's CUDA device or returns an error status.
+#include "../../include/vrb200.h"
+
+#include "vr_common.cuh"
+#include "vr_brick.cuh"
+#include "vr_env.cuh"
+#include "vr_trace.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace vr;
+
+// ------------------------------------------------------------------------------------------------
+// context
+
+namespace {
+
+struct DeviceGrid {
+    bool valid = false;
+    uint3 nb = { 0, 0, 0 };
+    uint3 atlas_dim = { 0, 0, 0 };
+    uint64_t brick_count = 0;
+    // canonical voldata buffers (download / bit-exact contract)
+    uint32_t* indirection = nullptr;
+    uint32_t* range = nullptr;
+    uint8_t* atlas = nullptr;
+    uint32_t* mips[3] = { nullptr, nullptr, nullptr };
+    // tracer layout
+    uint2* rec = nullptr;
+    uint8_t* atlas_lin = nullptr;
+    size_t n_slots = 0;
+};
+
+struct Frame {
+    DeviceGrid slot[2];
+};
+
+}  // namespace
+
+struct vrb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int w = 0, h = 0;
+    float4* color = nullptr;
+    bool color_external = false;
+    uchar4* fb = nullptr;
+    uchar4* ldr = nullptr;
+    std::map<int, Frame> frames;
+    float4* env_rgb = nullptr;
+    int env_w = 0, env_h = 0;
+    float* impmap = nullptr;
+    float4* lut = nullptr;
+    uint32_t tf_size = 0;
+    unsigned long long* counters = nullptr;
+    bool counting = false;
+    std::string err;
+};
+
+namespace {
+
+int fail(vrb_ctx* c, int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return status;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? VRB_ERR_OOM : VRB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                          \
+    } while (0)
+
+#define CK_LAUNCH() CK(cudaGetLastError())
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void free_grid(DeviceGrid& g) {
+    cudaFree(g.indirection); cudaFree(g.range); cudaFree(g.atlas);
+    for (auto& m : g.mips) cudaFree(m);
+    cudaFree(g.rec); cudaFree(g.atlas_lin);
+    g = DeviceGrid();
+}
+
+inline int grid_for(size_t n, int block, int sm_count, int per_sm = 16) {
+    const size_t need = (n + block - 1) / block;
+    const size_t cap = size_t(sm_count) * per_sm;
+    return int(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+size_t mip_words(const uint3& nb, int level) { return size_t(nb.x >> (level + 1)) * (nb.y >> (level + 1)) * (nb.z >> (level + 1)); }
+
+// builds the tracer layout (records + brick-linear atlas) from the canonical buffers
+int finalize_grid(vrb_ctx* ctx, DeviceGrid& g) {
+    const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
+    const uint3 ab = make_uint3(g.atlas_dim.x >> 3, g.atlas_dim.y >> 3, g.atlas_dim.z >> 3);
+    g.n_slots = size_t(ab.x) * ab.y * ab.z;
+    CK(cudaMalloc(&g.rec, n * sizeof(uint2)));
+    CK(cudaMalloc(&g.atlas_lin, (g.n_slots ? g.n_slots : 1) * 512));
+    k_make_records<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.indirection, g.range, n, ab, g.rec);
+    CK_LAUNCH();
+    if (g.n_slots) {
+        k_linearize_atlas<<<grid_for(g.n_slots * 64, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.atlas, g.atlas_dim, g.atlas_lin, g.n_slots);
+        CK_LAUNCH();
+    }
+    g.valid = true;
+    return VRB_OK;
+}
+
+int check_slot_frame(vrb_ctx* ctx, int slot, int frame) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (slot != VRB_SLOT_DENSITY && slot != VRB_SLOT_EMISSION) return fail(ctx, VRB_ERR_INVALID, "bad grid slot %d", slot);
+    if (frame < 0) return fail(ctx, VRB_ERR_INVALID, "bad frame %d", frame);
+    return VRB_OK;
+}
+
+int compute_n_bricks(const uint32_t dim[3], uint3& nb) {
+    uint32_t out[3];
+    for (int a = 0; a < 3; ++a) {
+        // div_round_up goes through float (grid_brick.cpp:54-56); "* 1u << 3" parses as (x * 1u) << 3 (:62)
+        const uint32_t b = uint32_t(std::ceil(float(dim[a]) / 8.f));
+        const uint32_t c = uint32_t(std::ceil(float(b) / 8.f));
+        out[a] = (c * 1u) << 3;
+        if (out[a] >= 1024u) return VRB_ERR_TOO_MANY_BRICKS;
+    }
+    nb = make_uint3(out[0], out[1], out[2]);
+    return VRB_OK;
+}
+
+int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d_vox, const uint32_t dim[3], float vmin, float vmax) {
+    uint3 nb;
+    if (compute_n_bricks(dim, nb) != VRB_OK)
+        return fail(ctx, VRB_ERR_TOO_MANY_BRICKS, "exceeded max brick count of 1024");
+    DeviceGrid& g = ctx->frames[frame].slot[slot];
+    free_grid(g);
+    g.nb = nb;
+    const size_t n = size_t(nb.x) * nb.y * nb.z;
+    const uint3 vdim = make_uint3(dim[0], dim[1], dim[2]);
+    uint32_t *flags = nullptr, *brick_id = nullptr, *block_sums = nullptr;
+    unsigned long long* d_total = nullptr;
+    const int n_blocks = int((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    CK(cudaMalloc(&g.indirection, n * 4));
+    CK(cudaMalloc(&g.range, n * 4));
+    CK(cudaMalloc(&flags, n * 4));
+    CK(cudaMalloc(&brick_id, n * 4));
+    CK(cudaMalloc(&block_sums, size_t(n_blocks) * 4));
+    CK(cudaMalloc(&d_total, 8));
+    // A: ranges
+    k_brick_range<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_vox, vdim, vmin, vmax, nb, g.range, flags);
+    CK_LAUNCH();
+    // B: ordered allocation
+    k_scan_block_sums<<<n_blocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, n, block_sums);
+    CK_LAUNCH();
+    k_scan_sums<<<1, 1024, 0, ctx->stream>>>(block_sums, n_blocks, d_total);
+    CK_LAUNCH();
+    k_scan_assign<<<n_blocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, n, block_sums, nb, g.indirection, brick_id);
+    CK_LAUNCH();
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    g.brick_count = total;
+    // atlas pruned in z: 8 * round(ceil(count / float(nbx * nby)))  (grid_brick.cpp:112; float arithmetic)
+    const uint32_t az = 8u * uint32_t(std::round(std::ceil(float(total) / float(nb.x * nb.y))));
+    g.atlas_dim = make_uint3(nb.x * 8, nb.y * 8, az);
+    const size_t atlas_bytes = size_t(g.atlas_dim.x) * g.atlas_dim.y * g.atlas_dim.z;
+    CK(cudaMalloc(&g.atlas, atlas_bytes ? atlas_bytes : 8));
+    if (atlas_bytes) CK(cudaMemsetAsync(g.atlas, 0, atlas_bytes, ctx->stream));
+    // C: encode
+    if (total) {
+        k_brick_encode<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_vox, vdim, vmin, vmax, nb, g.range, brick_id, g.atlas, g.atlas_dim);
+        CK_LAUNCH();
+    }
+    // D: range mips
+    const uint32_t* src = g.range;
+    uint3 sdim = nb;
+    for (int i = 0; i < 3; ++i) {
+        const uint3 ddim = make_uint3(nb.x >> (i + 1), nb.y >> (i + 1), nb.z >> (i + 1));
+        const size_t words = mip_words(nb, i);
+        CK(cudaMalloc(&g.mips[i], words * 4));
+        k_range_mip<<<grid_for(words, 256, ctx->sm_count), 256, 0, ctx->stream>>>(src, sdim, g.mips[i], ddim);
+        CK_LAUNCH();
+        src = g.mips[i];
+        sdim = ddim;
+    }
+    const int st = finalize_grid(ctx, g);
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(flags); cudaFree(brick_id); cudaFree(block_sums); cudaFree(d_total);
+    return st;
+}
+
+GridView make_view(const DeviceGrid& g) {
+    GridView v;
+    v.nb = g.nb;
+    v.rec = g.rec;
+    for (int i = 0; i < 3; ++i) v.mips[i] = g.mips[i];
+    v.atlas_lin = g.atlas_lin;
+    return v;
+}
+
+void mat4_mul(const float* a, const float* b, float* out) {
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r)
+            out[c * 4 + r] = a[0 * 4 + r] * b[c * 4 + 0] + a[1 * 4 + r] * b[c * 4 + 1] + a[2 * 4 + r] * b[c * 4 + 2] + a[3 * 4 + r] * b[c * 4 + 3];
+}
+
+int fill_trace_args(vrb_ctx* ctx, const vrb_params* p, TraceArgs& a) {
+    if (!p) return fail(ctx, VRB_ERR_INVALID, "params is NULL");
+    if (!ctx->color || ctx->w <= 0) return fail(ctx, VRB_ERR_STATE, "no colour buffer: call vrb_resize first");
+    if (p->resolution[0] != ctx->w || p->resolution[1] != ctx->h)
+        return fail(ctx, VRB_ERR_INVALID, "params.resolution %dx%d != colour buffer %dx%d", p->resolution[0], p->resolution[1], ctx->w, ctx->h);
+    auto it = ctx->frames.find(p->frame);
+    if (it == ctx->frames.end() || !it->second.slot[VRB_SLOT_DENSITY].valid)
+        return fail(ctx, VRB_ERR_STATE, "no density grid uploaded for frame %d", p->frame);
+    if (!ctx->env_rgb) return fail(ctx, VRB_ERR_STATE, "no environment uploaded");
+    if (p->use_transferfunc && (!ctx->lut || ctx->tf_size == 0)) return fail(ctx, VRB_ERR_STATE, "use_transferfunc set but no LUT uploaded");
+    memset(&a, 0, sizeof(a));
+    a.p = *p;
+    a.density = make_view(it->second.slot[VRB_SLOT_DENSITY]);
+    if (p->has_emission) {
+        if (!it->second.slot[VRB_SLOT_EMISSION].valid) return fail(ctx, VRB_ERR_STATE, "has_emission set but no emission grid for frame %d", p->frame);
+        a.emission = make_view(it->second.slot[VRB_SLOT_EMISSION]);
+        mat4_mul(p->vol_emission_inv_transform, p->vol_density_transform, a.emis_from_density.m);
+    }
+    a.env.rgb = ctx->env_rgb;
+    a.env.w = ctx->env_w;
+    a.env.h = ctx->env_h;
+    a.env.impmap = ctx->impmap;
+    a.lut = ctx->lut;
+    a.tf_size = ctx->tf_size;
+    a.color = ctx->color;
+    a.counters = ctx->counters;
+    return VRB_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+
+extern "C" {
+
+int vrb_abi_version(void) { return VRB_ABI_VERSION; }
+
+const char* vrb_status_string(int status) {
+    switch (status) {
+        case VRB_OK: return "ok";
+        case VRB_ERR_INVALID: return "invalid argument";
+        case VRB_ERR_NO_DEVICE: return "no usable CUDA device";
+        case VRB_ERR_CUDA: return "CUDA error";
+        case VRB_ERR_OOM: return "out of device memory";
+        case VRB_ERR_TOO_MANY_BRICKS: return "exceeded max brick count of 1024";
+        case VRB_ERR_STATE: return "invalid state";
+        default: return "unknown status";
+    }
+}
+
+int vrb_create(int device, vrb_ctx** out) {
+    if (!out) return VRB_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return VRB_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VRB_ERR_NO_DEVICE;
+    if (prop.major != 10) {  // the library only carries sm_100a SASS
+        fprintf(stderr, "vrb200: device %d is sm_%d%d, this build targets sm_100a only\n", device, prop.major, prop.minor);
+        return VRB_ERR_NO_DEVICE;
+    }
+    vrb_ctx* ctx = new vrb_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    DeviceGuard guard(device);
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->counters, 7 * sizeof(unsigned long long)) != cudaSuccess) {
+        delete ctx;
+        return VRB_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream);
+    *out = ctx;
+    return VRB_OK;
+}
+
+void vrb_destroy(vrb_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& f : ctx->frames) { free_grid(f.second.slot[0]); free_grid(f.second.slot[1]); }
+    if (!ctx->color_external) cudaFree(ctx->color);
+    cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->lut); cudaFree(ctx->counters);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* vrb_last_error(vrb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vrb_set_stream(vrb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return VRB_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? cudaStream_t(cuda_stream) : ctx->own_stream;
+    return VRB_OK;
+}
+
+int vrb_sync(vrb_ctx* ctx) {
+    if (!ctx) return VRB_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VRB_OK;
+}
+
+int vrb_resize(vrb_ctx* ctx, int w, int h) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (w <= 0 || h <= 0) return fail(ctx, VRB_ERR_INVALID, "bad resolution %dx%d", w, h);
+    DeviceGuard guard(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->color_external) cudaFree(ctx->color);
+    cudaFree(ctx->fb); cudaFree(ctx->ldr);
+    ctx->color = nullptr; ctx->fb = nullptr; ctx->ldr = nullptr; ctx->color_external = false;
+    ctx->w = w; ctx->h = h;
+    const size_t n = size_t(w) * h;
+    CK(cudaMalloc(&ctx->color, n * sizeof(float4)));
+    CK(cudaMalloc(&ctx->fb, n * sizeof(uchar4)));
+    CK(cudaMalloc(&ctx->ldr, n * sizeof(uchar4)));
+    CK(cudaMemsetAsync(ctx->color, 0, n * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(ctx->fb, 0, n * sizeof(uchar4), ctx->stream));
+    return VRB_OK;
+}
+
+int vrb_bind_color(vrb_ctx* ctx, void* device_rgba32f) {
+    if (!ctx || ctx->w <= 0) return ctx ? fail(ctx, VRB_ERR_STATE, "vrb_resize first") : VRB_ERR_INVALID;
+    if (!device_rgba32f) return fail(ctx, VRB_ERR_INVALID, "NULL colour buffer");
+    DeviceGuard guard(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->color_external) cudaFree(ctx->color);
+    ctx->color = reinterpret_cast<float4*>(device_rgba32f);
+    ctx->color_external = true;
+    return VRB_OK;
+}
+
+int vrb_grid_clear(vrb_ctx* ctx) {
+    if (!ctx) return VRB_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& f : ctx->frames) { free_grid(f.second.slot[0]); free_grid(f.second.slot[1]); }
+    ctx->frames.clear();
+    return VRB_OK;
+}
+
+int vrb_grid_upload_brick(vrb_ctx* ctx, int slot, int frame, const vrb_brick_view* v) {
+    int st = check_slot_frame(ctx, slot, frame);
+    if (st) return st;
+    if (!v || !v->indirection || !v->range || !v->range_mips[0] || !v->range_mips[1] || !v->range_mips[2])
+        return fail(ctx, VRB_ERR_INVALID, "brick view has NULL buffers");
+    for (int a = 0; a < 3; ++a) {
+        if (v->n_bricks[a] == 0 || v->n_bricks[a] >= 1024u || (v->n_bricks[a] & 7u)) return fail(ctx, VRB_ERR_INVALID, "n_bricks[%d] = %u must be a multiple of 8 in [8, 1016]", a, v->n_bricks[a]);
+        if (v->atlas_dim[a] & 7u) return fail(ctx, VRB_ERR_INVALID, "atlas_dim[%d] = %u must be a multiple of 8", a, v->atlas_dim[a]);
+    }
+    const size_t atlas_bytes = size_t(v->atlas_dim[0]) * v->atlas_dim[1] * v->atlas_dim[2];
+    if (atlas_bytes && !v->atlas) return fail(ctx, VRB_ERR_INVALID, "atlas is NULL");
+    DeviceGuard guard(ctx->device);
+    DeviceGrid& g = ctx->frames[frame].slot[slot];
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_grid(g);
+    g.nb = make_uint3(v->n_bricks[0], v->n_bricks[1], v->n_bricks[2]);
+    g.atlas_dim = make_uint3(v->atlas_dim[0], v->atlas_dim[1], v->atlas_dim[2]);
+    g.brick_count = v->brick_count;
+    const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
+    CK(cudaMalloc(&g.indirection, n * 4));
+    CK(cudaMalloc(&g.range, n * 4));
+    CK(cudaMalloc(&g.atlas, atlas_bytes ? atlas_bytes : 8));
+    CK(cudaMemcpyAsync(g.indirection, v->indirection, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g.range, v->range, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (atlas_bytes) CK(cudaMemcpyAsync(g.atlas, v->atlas, atlas_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    for (int i = 0; i < 3; ++i) {
+        const size_t words = mip_words(g.nb, i);
+        CK(cudaMalloc(&g.mips[i], words * 4));
+        CK(cudaMemcpyAsync(g.mips[i], v->range_mips[i], words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    st = finalize_grid(ctx, g);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return st;
+}
+
+int vrb_grid_build_from_dense_device(vrb_ctx* ctx, int slot, int frame, const void* d_voxels_u8, const uint32_t dim[3], float vmin, float vmax) {
+    int st = check_slot_frame(ctx, slot, frame);
+    if (st) return st;
+    if (!d_voxels_u8 || !dim || !dim[0] || !dim[1] || !dim[2]) return fail(ctx, VRB_ERR_INVALID, "bad dense grid");
+    DeviceGuard guard(ctx->device);
+    return build_from_device_voxels(ctx, slot, frame, static_cast<const uint8_t*>(d_voxels_u8), dim, vmin, vmax);
+}
+
+int vrb_grid_build_from_dense(vrb_ctx* ctx, int slot, int frame, const uint8_t* voxels_u8, const uint32_t dim[3], float vmin, float vmax) {
+    int st = check_slot_frame(ctx, slot, frame);
+    if (st) return st;
+    if (!voxels_u8 || !dim || !dim[0] || !dim[1] || !dim[2]) return fail(ctx, VRB_ERR_INVALID, "bad dense grid");
+    uint3 nb;
+    if (compute_n_bricks(dim, nb) != VRB_OK) return fail(ctx, VRB_ERR_TOO_MANY_BRICKS, "exceeded max brick count of 1024");
+    DeviceGuard guard(ctx->device);
+    const size_t n = size_t(dim[0]) * dim[1] * dim[2];
+    uint8_t* d_vox = nullptr;
+    CK(cudaMalloc(&d_vox, n));
+    cudaError_t e = cudaMemcpyAsync(d_vox, voxels_u8, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d_vox); return fail(ctx, VRB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+    st = build_from_device_voxels(ctx, slot, frame, d_vox, dim, vmin, vmax);
+    cudaFree(d_vox);
+    return st;
+}
+
+int vrb_grid_info(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out) {
+    int st = check_slot_frame(ctx, slot, frame);
+    if (st) return st;
+    auto it = ctx->frames.find(frame);
+    if (!out || it == ctx->frames.end() || !it->second.slot[slot].valid) return fail(ctx, VRB_ERR_STATE, "no grid in slot %d frame %d", slot, frame);
+    const DeviceGrid& g = it->second.slot[slot];
+    out->n_bricks[0] = g.nb.x; out->n_bricks[1] = g.nb.y; out->n_bricks[2] = g.nb.z;
+    out->atlas_dim[0] = g.atlas_dim.x; out->atlas_dim[1] = g.atlas_dim.y; out->atlas_dim[2] = g.atlas_dim.z;
+    out->brick_count = g.brick_count;
+    return VRB_OK;
+}
+
+int vrb_grid_download(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out) {
+    int st = vrb_grid_info(ctx, slot, frame, out);
+    if (st) return st;
+    DeviceGuard guard(ctx->device);
+    const DeviceGrid& g = ctx->frames[frame].slot[slot];
+    const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
+    const size_t atlas_bytes = size_t(g.atlas_dim.x) * g.atlas_dim.y * g.atlas_dim.z;
+    if (out->indirection) CK(cudaMemcpyAsync(out->indirection, g.indirection, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->range) CK(cudaMemcpyAsync(out->range, g.range, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->atlas && atlas_bytes) CK(cudaMemcpyAsync(out->atlas, g.atlas, atlas_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int i = 0; i < 3; ++i)
+        if (out->range_mips[i]) CK(cudaMemcpyAsync(out->range_mips[i], g.mips[i], mip_words(g.nb, i) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VRB_OK;
+}
+
+int vrb_dense_from_float(vrb_ctx* ctx, const float* data, const uint32_t dim[3], uint8_t* out_u8, float out_minmax[2]) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!data || !dim || !out_u8 || !out_minmax || !dim[0] || !dim[1] || !dim[2]) return fail(ctx, VRB_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(ctx->device);
+    const size_t n = size_t(dim[0]) * dim[1] * dim[2];
+    float *d_data = nullptr, *d_bmin = nullptr, *d_bmax = nullptr, *d_mm = nullptr;
+    uint8_t* d_out = nullptr;
+    const int blocks = grid_for(n, 256, ctx->sm_count, 8);
+    CK(cudaMalloc(&d_data, n * 4));
+    CK(cudaMalloc(&d_out, n));
+    CK(cudaMalloc(&d_bmin, blocks * 4));
+    CK(cudaMalloc(&d_bmax, blocks * 4));
+    CK(cudaMalloc(&d_mm, 8));
+    CK(cudaMemcpyAsync(d_data, data, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_dense_minmax<<<blocks, 256, 0, ctx->stream>>>(d_data, n, d_bmin, d_bmax);
+    CK_LAUNCH();
+    k_dense_minmax_final<<<1, 32, 0, ctx->stream>>>(d_bmin, d_bmax, blocks, d_mm);
+    CK_LAUNCH();
+    k_dense_quantize<<<blocks, 256, 0, ctx->stream>>>(d_data, n, d_mm, d_out);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(out_u8, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_minmax, d_mm, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_data); cudaFree(d_out); cudaFree(d_bmin); cudaFree(d_bmax); cudaFree(d_mm);
+    return VRB_OK;
+}
+
+int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!rgb || w <= 0 || h <= 0) return fail(ctx, VRB_ERR_INVALID, "bad environment map");
+    DeviceGuard guard(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->env_rgb); ctx->env_rgb = nullptr;
+    if (!ctx->impmap) CK(cudaMalloc(&ctx->impmap, size_t(imp_offset(IMP_LEVELS)) * 4));
+    const size_t n = size_t(w) * h;
+    float* d_rgb = nullptr;
+    CK(cudaMalloc(&d_rgb, n * 12));
+    CK(cudaMalloc(&ctx->env_rgb, n * sizeof(float4)));
+    CK(cudaMemcpyAsync(d_rgb, rgb, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    k_env_pad<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(d_rgb, ctx->env_rgb, n);
+    CK_LAUNCH();
+    ctx->env_w = w; ctx->env_h = h;
+    EnvView e { ctx->env_rgb, w, h, ctx->impmap };
+    k_env_impmap<<<dim3(IMP_DIM / 16, IMP_DIM / 16), 256, 0, ctx->stream>>>(e, ctx->impmap);
+    CK_LAUNCH();
+    for (int l = 1; l < IMP_LEVELS; ++l) {
+        const int d = IMP_DIM >> l;
+        const dim3 block(16, 16), grid((d + 15) / 16, (d + 15) / 16);
+        k_env_mip<<<grid, block, 0, ctx->stream>>>(ctx->impmap + imp_offset(l - 1), d * 2, ctx->impmap + imp_offset(l), d);
+        CK_LAUNCH();
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_rgb);
+    return VRB_OK;
+}
+
+int vrb_env_download_impmap(vrb_ctx* ctx, int level, float* out) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!ctx->impmap || !ctx->env_rgb) return fail(ctx, VRB_ERR_STATE, "no environment uploaded");
+    if (level < 0 || level >= IMP_LEVELS || !out) return fail(ctx, VRB_ERR_INVALID, "bad level %d", level);
+    DeviceGuard guard(ctx->device);
+    const int d = IMP_DIM >> level;
+    CK(cudaMemcpyAsync(out, ctx->impmap + imp_offset(level), size_t(d) * d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VRB_OK;
+}
+
+int vrb_tf_upload(vrb_ctx* ctx, const float* rgba, uint32_t n) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!rgba || n == 0) return fail(ctx, VRB_ERR_INVALID, "empty LUT");
+    DeviceGuard guard(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->lut); ctx->lut = nullptr;
+    CK(cudaMalloc(&ctx->lut, size_t(n) * 16));
+    CK(cudaMemcpyAsync(ctx->lut, rgba, size_t(n) * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tf_size = n;
+    return VRB_OK;
+}
+
+int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_samples, const int tile[4], int accum_mode) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (first_sample < 1 || n_samples < 0) return fail(ctx, VRB_ERR_INVALID, "first_sample must be >= 1 (1-based current_sample)");
+    if (accum_mode != VRB_ACCUM_MEAN && accum_mode != VRB_ACCUM_SUM) return fail(ctx, VRB_ERR_INVALID, "bad accum_mode");
+    if (n_samples == 0) return VRB_OK;
+    TraceArgs a;
+    const int st = fill_trace_args(ctx, params, a);
+    if (st) return st;
+    a.x0 = tile ? tile[0] : 0; a.y0 = tile ? tile[1] : 0; a.x1 = tile ? tile[2] : ctx->w; a.y1 = tile ? tile[3] : ctx->h;
+    if (a.x0 < 0 || a.y0 < 0 || a.x1 > ctx->w || a.y1 > ctx->h || a.x0 >= a.x1 || a.y0 >= a.y1) return fail(ctx, VRB_ERR_INVALID, "bad tile");
+    a.first_sample = first_sample; a.n_samples = n_samples; a.accum_mode = accum_mode;
+    DeviceGuard guard(ctx->device);
+    const dim3 grid((a.x1 - a.x0 + 15) / 16, (a.y1 - a.y0 + 15) / 16);
+    const bool tf = params->use_transferfunc != 0;
+    if (ctx->counting) {
+        if (tf) k_trace_pixels<true, true><<<grid, 256, 0, ctx->stream>>>(a);
+        else k_trace_pixels<false, true><<<grid, 256, 0, ctx->stream>>>(a);
+    } else {
+        if (tf) k_trace_pixels<true, false><<<grid, 256, 0, ctx->stream>>>(a);
+        else k_trace_pixels<false, false><<<grid, 256, 0, ctx->stream>>>(a);
+    }
+    CK_LAUNCH();
+    return VRB_OK;
+}
+
+int vrb_trace_deterministic(vrb_ctx* ctx, const vrb_params* params) {
+    if (!ctx) return VRB_ERR_INVALID;
+    TraceArgs a;
+    const int st = fill_trace_args(ctx, params, a);
+    if (st) return st;
+    DeviceGuard guard(ctx->device);
+    const dim3 grid((ctx->w + 15) / 16, (ctx->h + 15) / 16);
+    k_trace_deterministic<<<grid, 256, 0, ctx->stream>>>(a);
+    CK_LAUNCH();
+    return VRB_OK;
+}
+
+int vrb_scale(vrb_ctx* ctx, float s) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!ctx->color) return fail(ctx, VRB_ERR_STATE, "no colour buffer");
+    DeviceGuard guard(ctx->device);
+    const size_t n = size_t(ctx->w) * ctx->h;
+    k_scale<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->color, n, s);
+    CK_LAUNCH();
+    return VRB_OK;
+}
+
+int vrb_clear(vrb_ctx* ctx) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!ctx->color) return fail(ctx, VRB_ERR_STATE, "no colour buffer");
+    DeviceGuard guard(ctx->device);
+    CK(cudaMemsetAsync(ctx->color, 0, size_t(ctx->w) * ctx->h * sizeof(float4), ctx->stream));
+    return VRB_OK;
+}
+
+int vrb_set_counting(vrb_ctx* ctx, int enable) {
+    if (!ctx) return VRB_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    ctx->counting = enable != 0;
+    CK(cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream));
+    return VRB_OK;
+}
+
+int vrb_get_counters(vrb_ctx* ctx, vrb_counters* out) {
+    if (!ctx || !out) return VRB_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    unsigned long long v[7];
+    CK(cudaMemcpyAsync(v, ctx->counters, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->n_samples = v[0]; out->n_maj = v[1]; out->n_dens = v[2]; out->n_emis = v[3]; out->n_nee = v[4]; out->n_env = v[5]; out->n_real = v[6];
+    return VRB_OK;
+}
+
+int vrb_tonemap(vrb_ctx* ctx, float exposure, float gamma, int in_place, int tonemapping) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!ctx->color) return fail(ctx, VRB_ERR_STATE, "no colour buffer");
+    DeviceGuard guard(ctx->device);
+    const size_t n = size_t(ctx->w) * ctx->h;
+    const int blocks = grid_for(n, 256, ctx->sm_count);
+    if (in_place) k_tonemap_inplace<<<blocks, 256, 0, ctx->stream>>>(ctx->color, n, exposure, 1.f / gamma);
+    else k_draw<<<blocks, 256, 0, ctx->stream>>>(ctx->color, ctx->fb, n, exposure, 1.f / gamma, tonemapping);
+    CK_LAUNCH();
+    return VRB_OK;
+}
+
+int vrb_download_color(vrb_ctx* ctx, float* out, int channels) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!ctx->color) return fail(ctx, VRB_ERR_STATE, "no colour buffer");
+    if (!out || (channels != 3 && channels != 4)) return fail(ctx, VRB_ERR_INVALID, "channels must be 3 or 4");
+    DeviceGuard guard(ctx->device);
+    const size_t n = size_t(ctx->w) * ctx->h;
+    if (channels == 4) {
+        CK(cudaMemcpyAsync(out, ctx->color, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        CK(cudaMemcpy2DAsync(out, 12, ctx->color, 16, 12, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return VRB_OK;
+}
+
+int vrb_download_color_ldr(vrb_ctx* ctx, uint8_t* rgba8) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!ctx->color) return fail(ctx, VRB_ERR_STATE, "no colour buffer");
+    if (!rgba8) return fail(ctx, VRB_ERR_INVALID, "NULL output");
+    DeviceGuard guard(ctx->device);
+    const size_t n = size_t(ctx->w) * ctx->h;
+    k_color_to_ldr<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->color, ctx->ldr, n);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(rgba8, ctx->ldr, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VRB_OK;
+}
+
+int vrb_download_framebuffer(vrb_ctx* ctx, uint8_t* rgba8) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!ctx->fb) return fail(ctx, VRB_ERR_STATE, "no framebuffer");
+    if (!rgba8) return fail(ctx, VRB_ERR_INVALID, "NULL output");
+    DeviceGuard guard(ctx->device);
+    CK(cudaMemcpyAsync(rgba8, ctx->fb, size_t(ctx->w) * ctx->h * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VRB_OK;
+}
+
+int vrb_upload_color(vrb_ctx* ctx, const float* rgba) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!ctx->color) return fail(ctx, VRB_ERR_STATE, "no colour buffer");
+    if (!rgba) return fail(ctx, VRB_ERR_INVALID, "NULL input");
+    DeviceGuard guard(ctx->device);
+    CK(cudaMemcpyAsync(ctx->color, rgba, size_t(ctx->w) * ctx->h * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VRB_OK;
+}
+
+void* vrb_color_device_ptr(vrb_ctx* ctx) { return ctx ? ctx->color : nullptr; }
+
+int vrb_reduce(vrb_ctx* const* ctxs, int n, int root) {
+    if (!ctxs || n <= 0 || root < 0 || root >= n) return VRB_ERR_INVALID;
+    vrb_ctx* ctx = ctxs[root];
+    if (!ctx || !ctx->color) return VRB_ERR_INVALID;
+    const size_t px = size_t(ctx->w) * ctx->h;
+    for (int i = 0; i < n; ++i)
+        if (!ctxs[i] || !ctxs[i]->color || ctxs[i]->w != ctx->w || ctxs[i]->h != ctx->h) return fail(ctx, VRB_ERR_INVALID, "context %d does not match the root resolution", i);
+    DeviceGuard guard(ctx->device);
+    float4* staging = nullptr;
+    CK(cudaMalloc(&staging, px * sizeof(float4)));
+    for (int i = 0; i < n; ++i) {
+        if (i == root) continue;
+        { DeviceGuard g2(ctxs[i]->device); cudaStreamSynchronize(ctxs[i]->stream); }
+        CK(cudaMemcpyPeerAsync(staging, ctx->device, ctxs[i]->color, ctxs[i]->device, px * sizeof(float4), ctx->stream));
+        k_add<<<grid_for(px, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->color, staging, px);
+        CK_LAUNCH();
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(staging);
+    return VRB_OK;
+}
+
+}  // extern "C"
