@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- path samples/s of the B200 volume path tracer on BASELINE.json's metric config.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload at every N: BASELINE.json configs[1] -- data/smoke.brick + data/lut.txt transfer function
+(pathtracer_brick_tf), 1920x1080, 128 bounces. One "step" = one batch of --spp-per-step samples for every
+pixel (the full config is 1024 spp = 1024/spp-per-step such steps; samples are independent).
+N > 1: spp-sliced weak scaling -- every rank traces its own --spp-per-step slice of sample indices for all
+pixels into a SUM buffer, the float4 buffers are reduced to rank 0 with NCCL (the one real exchange step).
+
+value  : whole-job samples/s with volume/env/LUT resident in HBM (CUDA events around the K steps, max over ranks)
+e2e    : same metric through the C ABI with HOST buffers: per step the brick grid, environment and LUT are
+         uploaded from host memory, traced, and the RGBA32F image is read back (H2D/D2H inside the timed region)
+roofline: algorithmic bytes (event counters x per-event bytes) / kernel time vs the measured HBM peak
+cpu_baseline: the CPU oracle (port of the reference shaders) on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ASSETS = os.path.join(ROOT, "tests", "golden", "assets")
+W, H, BOUNCES, FULL_SPP = 1920, 1080, 128, 1024
+METRIC = "path samples/sec (1080p, 128 bounces)"
+UNIT = "samples/s"
+
+
+def load_workload():
+    from volren_b200 import formats
+    from helpers import default_scene
+    grid = formats.load_brick(os.path.join(ASSETS, "smoke.brick"))
+    env = formats.load_hdr(os.path.join(ASSETS, "table_mountain_2_puresky_1k.hdr"))
+    lut = formats.lut_for_upload(formats.load_lut_txt(os.path.join(ASSETS, "lut.txt")))
+    # `./volren data/smoke.brick <hdr> data/lut.txt -w 1920 -h 1080 --render --bounces 128`
+    params = default_scene(grid, W, H, bounces=BOUNCES, use_tf=True)
+    return grid, env, lut, params
+
+
+def algorithmic_bytes(c: dict, use_tf: bool) -> float:
+    """bytes the algorithm must touch, from the event counters (per launch)."""
+    if use_tf:
+        per_maj, per_dens = 4 + 32, 8 * 9 + 32
+    else:
+        per_maj, per_dens = 4, 9
+    return (per_maj * c["n_maj"] + per_dens * c["n_dens"] + 9 * c["n_emis"] + 200 * c["n_nee"] + 100 * c["n_env"]
+            + 32 * c["n_samples"])
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.samples.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path. The GLSL renderer needs a GL context that
+    neither this container nor the GPU box has, so this is the oracle port of the shaders with all host threads
+    (kind = "port"); each step is a bounded crop of the same workload."""
+    if rank != 0:
+        return
+    from oracle.binding import Oracle
+    grid, env, lut, params = load_workload()
+    o = Oracle()
+    pyr = o.env_build(env)
+    sc = o.make_scene(grid, env, pyr, lut=lut)
+    cores = o.max_threads()
+    # bounded sample: a centred crop of the 1080p image at 1 spp per step, sized for ~3 s per step
+    cw, ch = 480, 270
+    tile = ((W - cw) // 2, (H - ch) // 2, (W + cw) // 2, (H + ch) // 2)
+    color = np.zeros((H, W, 4), np.float32)
+    t0 = time.perf_counter()
+    o.trace(sc, params, 1, 1, color=color, tile=tile)
+    probe = time.perf_counter() - t0
+    spp = max(1, int(3.0 / max(probe, 1e-3)))
+    for i in range(args.warmup):
+        o.trace(sc, params, 1 + i, 1, color=color, tile=tile)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        o.trace(sc, params, 1 + k * spp, spp, color=color, tile=tile)
+    dt = time.perf_counter() - t0
+    samples = cw * ch * spp * args.steps
+    v = samples / dt
+    sample = f"{cw}x{ch} centre crop of the 1080p frame, {spp} spp per step, {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "reference assets (smoke.brick, lut.txt, hdr) committed under tests/golden/assets",
+        "config": {"workload": "configs[1]: smoke.brick + lut.txt TF (pathtracer_brick_tf), 1920x1080, 128 bounces", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spp-per-step", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import volren_b200 as vr
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: volren_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    grid, env, lut, params = load_workload()
+    S = args.spp_per_step
+
+    ctx = vr.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)          # kernels run on torch's current stream: torch.cuda.Event sees them
+    ctx.resize(W, H)
+    color = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    ctx.bind_color(color.data_ptr())            # NCCL reduces this tensor in place
+    ctx.grid_upload_brick(grid)
+    ctx.env_upload(env)
+    ctx.tf_upload(lut)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k):
+        """one step: this rank's spp slice for all pixels, then the accumulation-buffer reduce"""
+        first = 1 + (k * world + rank) * S
+        if world > 1:
+            ctx.trace(params, first, S, accum_mode=vr._capi.ACCUM_SUM)
+            dist.reduce(color, dst=0, op=dist.ReduceOp.SUM)
+        else:
+            ctx.trace(params, first, S)
+
+    # ---- counting pass (defines the algorithmic bytes of one launch) ----
+    ctx.set_counting(True)
+    ctx.trace(params, 1, S)
+    counters = ctx.get_counters().as_dict()
+    ctx.set_counting(False)
+    alg_bytes = algorithmic_bytes(counters, use_tf=True)
+
+    # ---- device-resident throughput ----
+    color.zero_()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                   # L2 flush between timed iterations (not timed)
+        barrier()
+        ev[k][0].record()
+        first = 1 + ((args.warmup + k) * world + rank) * S
+        kev[k][0].record()
+        ctx.trace(params, first, S, accum_mode=vr._capi.ACCUM_SUM if world > 1 else vr._capi.ACCUM_MEAN)
+        kev[k][1].record()
+        if world > 1:
+            dist.reduce(color, dst=0, op=dist.ReduceOp.SUM)
+        ev[k][1].record()
+        barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    kms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    samples_per_step = W * H * S * world
+    value = samples_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ----
+    host_img = np.empty((H, W, 4), np.float32)
+    h2d = grid.indirection.nbytes + grid.range.nbytes + grid.atlas.nbytes + sum(m.nbytes for m in grid.mips) + env.nbytes + lut.nbytes
+    d2h = host_img.nbytes if rank == 0 else 0
+
+    def e2e_step(k):
+        ctx.grid_upload_brick(grid)             # host -> device: indirection, range, atlas, mips
+        ctx.env_upload(env)                     # host -> device + importance pyramid rebuild
+        ctx.tf_upload(lut)
+        first = 1 + (k * world + rank) * S
+        if world > 1:
+            ctx.trace(params, first, S, accum_mode=vr._capi.ACCUM_SUM)
+            dist.reduce(color, dst=0, op=dist.ReduceOp.SUM)
+        else:
+            ctx.trace(params, first, S)
+        if rank == 0:
+            ctx.lib.vrb_download_color(ctx.handle, host_img.ctypes.data, 4)   # device -> host (blocks)
+        else:
+            ctx.sync()
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_step(k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = samples_per_step * args.steps / float(t.item())
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "reference assets (smoke.brick, lut.txt, hdr) committed under tests/golden/assets",
+            "config": {
+                "workload": "configs[1]: smoke.brick + lut.txt TF (pathtracer_brick_tf), 1920x1080, 128 bounces",
+                "spp_per_step": S, "full_config_spp": FULL_SPP, "partition": "spp slices + NCCL reduce" if world > 1 else "single GPU",
+                "l2": "flushed between timed iterations (256 MiB fill); the 1.9 MB volume is L2-resident by nature",
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": None, "peak_kind": peak_kind, "kernel": "k_trace_pixels<TF>", "kernel_ms": kms,
+                "algorithmic_bytes_per_sample": alg_bytes / counters["n_samples"], "counters_per_sample": {k: v / counters["n_samples"] for k, v in counters.items()},
+                "note": "latency-bound gather workload on an L2-resident volume: see DESIGN.md for the L2 roofline",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": args.steps * 1,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle.binding import Oracle
+            o = Oracle()
+            pyr = o.env_build(env)
+            sc = o.make_scene(grid, env, pyr, lut=lut)
+            cw, ch = 480, 270
+            tile = ((W - cw) // 2, (H - ch) // 2, (W + cw) // 2, (H + ch) // 2)
+            img = np.zeros((H, W, 4), np.float32)
+            t0 = time.perf_counter()
+            o.trace(sc, params, 1, 1, color=img, tile=tile)
+            probe = time.perf_counter() - t0
+            spp = max(1, int(12.0 / max(probe, 1e-3)))
+            t0 = time.perf_counter()
+            o.trace(sc, params, 2, spp, color=img, tile=tile)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": cw * ch * spp / dt, "unit": UNIT, "cores": o.max_threads(), "kind": "port",
+                                   "sample": f"{cw}x{ch} centre crop of the 1080p frame, {spp} spp (oracle/vr_oracle.c, OpenMP)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

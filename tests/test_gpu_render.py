@@ -136,12 +136,11 @@ def test_accumulate_matches_oracle_given_same_L(smoke_ctx, oracle, smoke_grid, e
 def test_synthetic_dense_volume_end_to_end(ctx, oracle, env_rgb, env_pyramid):
     """DenseGrid -> GPU brick build -> trace, against the oracle built from the oracle's own brick grid."""
     vox, lo, hi = blob_volume(48)
-    ctx.grid_clear()
-    ctx.grid_build_from_dense(vox, lo, hi)
+    ctx.grid_build_from_dense(vox, lo, hi, frame=3)     # frame 3: leaves the module's smoke grid (frame 0) alone
     ctx.env_upload(env_rgb)
     g = oracle.brick_build(vox, lo, hi)
     W, H, SPP = 64, 64, 128
-    p = default_scene(g, W, H, bounces=64, index_extent=(48, 48, 48), density_scale=8.0)
+    p = default_scene(g, W, H, bounces=64, index_extent=(48, 48, 48), density_scale=8.0, frame=3)
     sc = oracle.make_scene(g, env_rgb, env_pyramid)
     ref_a, _ = oracle.trace(sc, p, 1, SPP)
     p2 = p.copy()
