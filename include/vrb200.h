@@ -162,6 +162,10 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
 /* deterministic transmittance-only mode (defined by this build, DESIGN.md "T1"): centre ray per pixel,
  * exact voxel DDA, color = (Tr * Le_env(dir), 1 - Tr) */
 int vrb_trace_deterministic(vrb_ctx* ctx, const vrb_params* params);
+/* kernel selection: 0 = persistent-thread kernel with MUFU fast math (default, production);
+ * 1 = the straightforward one-thread-per-pixel kernel with IEEE math; 2 = the persistent kernel with IEEE math.
+ * 1 and 2 are cross-checks: 2 must reproduce 1 (same paths, same counters), 0 is compared statistically */
+int vrb_set_kernel(vrb_ctx* ctx, int kind);
 /* color *= s (finalise VRB_ACCUM_SUM buffers) */
 int vrb_scale(vrb_ctx* ctx, float s);
 /* zero the colour buffer */

@@ -21,6 +21,7 @@ ap.add_argument("--h", type=int, default=1080)
 ap.add_argument("--spp", type=int, default=4)
 ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--count", type=int, default=0)
+ap.add_argument("--kernel", type=int, default=0)
 a = ap.parse_args()
 A = os.path.join(ROOT, "tests", "golden", "assets")
 grid = formats.load_brick(os.path.join(A, "smoke.brick"))
@@ -33,6 +34,7 @@ ctx.env_upload(env)
 ctx.tf_upload(lut)
 p = default_scene(grid, a.w, a.h, bounces=128, use_tf=True) if a.tf else readme_scene(grid, a.w, a.h)
 import time
+ctx.set_kernel(a.kernel)
 if a.count:
     ctx.set_counting(True)
 for i in range(a.launches):

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libvrb200.so")
+LIB_PATH = os.environ.get("VRB200_LIB") or os.path.join(PKG, "libvrb200.so")   # VRB200_LIB: tuning builds (tools/sweep.py)
 
 VRB_OK = 0
 VRB_ERR_INVALID, VRB_ERR_NO_DEVICE, VRB_ERR_CUDA, VRB_ERR_OOM, VRB_ERR_TOO_MANY_BRICKS, VRB_ERR_STATE = -1, -2, -3, -4, -5, -6
@@ -20,7 +20,7 @@ SYMBOLS = [
     "vrb_create", "vrb_destroy", "vrb_last_error", "vrb_status_string", "vrb_abi_version", "vrb_set_stream", "vrb_sync",
     "vrb_resize", "vrb_grid_clear", "vrb_grid_upload_brick", "vrb_grid_build_from_dense",
     "vrb_grid_build_from_dense_device", "vrb_grid_info", "vrb_grid_download", "vrb_dense_from_float",
-    "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_scale",
+    "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_scale",
     "vrb_clear", "vrb_set_counting", "vrb_get_counters", "vrb_tonemap", "vrb_download_color", "vrb_download_color_ldr",
     "vrb_download_framebuffer", "vrb_upload_color", "vrb_color_device_ptr", "vrb_bind_color", "vrb_reduce",
 ]
@@ -111,6 +111,7 @@ def load_library(path: str = LIB_PATH):
     L.vrb_tf_upload.argtypes = [vp, vp, C.c_uint32]
     L.vrb_trace.argtypes = [vp, C.POINTER(Params), ci, ci, vp, ci]
     L.vrb_trace_deterministic.argtypes = [vp, C.POINTER(Params)]
+    L.vrb_set_kernel.argtypes = [vp, ci]
     L.vrb_scale.argtypes = [vp, cf]
     L.vrb_clear.argtypes = [vp]
     L.vrb_set_counting.argtypes = [vp, ci]
@@ -242,6 +243,9 @@ class Context:
 
     def trace_deterministic(self, params: Params):
         self._ck(self.lib.vrb_trace_deterministic(self.handle, C.byref(params)))
+
+    def set_kernel(self, kind):
+        self._ck(self.lib.vrb_set_kernel(self.handle, kind))
 
     def scale(self, s):
         self._ck(self.lib.vrb_scale(self.handle, s))

@@ -1,7 +1,15 @@
-// The tracking kernels: shader/pathtracer_brick.glsl + pathtracer_brick_tf.glsl + the parts of
+// The tracking code: shader/pathtracer_brick.glsl + pathtracer_brick_tf.glsl + the parts of
 // shader/common.glsl they reach (USE_DDA): brick-DDA majorant delta tracking, envmap NEE with MIS,
-// Russian roulette, Henyey-Greenstein, LUT transfer function. One template, two variants (TF on/off),
-// plus a counting build (COUNT) that emits the event counters defining the algorithmic bytes.
+// Russian roulette, Henyey-Greenstein, LUT transfer function.
+//
+// Every helper is a template over a math policy MT:
+//   StrictMath : IEEE division / sqrt and the accurate libdevice log / sincos -- the arithmetic of the CPU oracle
+//                up to FMA contraction; used by the cross-check kernels (vrb_set_kernel 1 and 2);
+//   FastMath   : MUFU-based rcp / rsqrt / lg2 / sin / cos (what a GLSL compiler emits for these built-ins on a GPU);
+//                used by the production kernel. Besides speed this is about CODE SIZE: with IEEE sequences the
+//                persistent kernel is 73 KB of SASS and stalls on instruction fetch (profiles/r01_v3_*).
+// This file also holds the straightforward one-thread-per-pixel kernel (k_trace_pixels) and the deterministic
+// transmittance-only mode; the production persistent kernel lives in vr_trace2.cuh.
 #pragma once
 
 #include "vr_common.cuh"
@@ -9,6 +17,25 @@
 #include "../../include/vrb200.h"
 
 namespace vr {
+
+struct StrictMath {
+    static constexpr bool fast = false;
+    static VR_DEV float div(float a, float b) { return a / b; }
+    static VR_DEV float rcp(float a) { return 1.f / a; }
+    static VR_DEV float sqrt(float a) { return sqrtf(a); }
+    static VR_DEV float log(float a) { return logf(a); }
+    static VR_DEV void sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+    static VR_DEV float3 normalize(float3 v) { return v / sqrtf(dot(v, v)); }
+};
+struct FastMath {
+    static constexpr bool fast = true;
+    static VR_DEV float rcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+    static VR_DEV float div(float a, float b) { return a * rcp(b); }
+    static VR_DEV float sqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+    static VR_DEV float log(float a) { return __logf(a); }
+    static VR_DEV void sincos(float a, float* s, float* c) { __sincosf(a, s, c); }
+    static VR_DEV float3 normalize(float3 v) { return v * rsqrtf(dot(v, v)); }
+};
 
 struct GridView {
     uint3 nb;                  // n_bricks (level 0)
@@ -28,6 +55,12 @@ struct TraceArgs {
     int first_sample, n_samples, accum_mode;
     unsigned long long* counters;  // 7 x u64 (vrb_counters order) or nullptr
     Mat4 emis_from_density;        // vol_emission_inv_transform * vol_density_transform (common.glsl:325)
+    float cam_z;                   // view_dir's z = -.5f / tan(.5f * M_PI * cam_fov / 180.f) (common.glsl:78), host libm
+    // persistent kernel only
+    const float* maj[4];           // per-level majorant tables (final value used by the tracking loop)
+    const float* maj_oob;          // majorant of an out-of-bounds fetch (one float)
+    unsigned int* job_counter;     // pixel ticket
+    int tiles_x, n_jobs;
 };
 
 template <bool COUNT> struct Cnt;
@@ -39,6 +72,12 @@ template <> struct Cnt<true> {
     VR_DEV void maj() { ++n_maj; } VR_DEV void dens() { ++n_dens; } VR_DEV void emis() { ++n_emis; } VR_DEV void nee() { ++n_nee; }
     VR_DEV void env() { ++n_env; } VR_DEV void real() { ++n_real; } VR_DEV void samp() { ++n_samp; }
 };
+VR_DEV void flush_counters(const TraceArgs&, const Cnt<false>&) {}
+VR_DEV void flush_counters(const TraceArgs& a, const Cnt<true>& c) {
+    const uint32_t v[7] = { c.n_samp, c.n_maj, c.n_dens, c.n_emis, c.n_nee, c.n_env, c.n_real };
+#pragma unroll
+    for (int i = 0; i < 7; ++i) atomicAdd(a.counters + i, (unsigned long long)v[i]);
+}
 
 // exact u8 / 255.f (GL unorm8 -> float) without a divide: reciprocal multiply + one FMA correction step
 VR_DEV float unorm8_to_float(uint32_t u) {
@@ -72,7 +111,9 @@ VR_DEV float brick_majorant(const GridView& g, float3 ipos, int mip) {
     return range_hi(w);
 }
 
-// stochastic_tricubic_filter (common.glsl:221-244): 9 draws, weighted reservoir over the 4 B-spline taps
+// stochastic_tricubic_filter (common.glsl:221-244): 9 draws, weighted reservoir over the 4 B-spline taps.
+// FastMath tests `r * max(1e-3, sum) < w` instead of `r < w / max(1e-3, sum)` (no division).
+template <class MT>
 VR_DEV int3 stochastic_tricubic_filter(float3 ipos, uint32_t& seed) {
     const float qx = ipos.x - 0.5f, qy = ipos.y - 0.5f, qz = ipos.z - 0.5f;
     const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
@@ -89,21 +130,22 @@ VR_DEV int3 stochastic_tricubic_filter(float3 ipos, uint32_t& seed) {
         int k = 0;
         w = (1.f / 6.f) * (3 * t1 * t2 - 6 * t2 + 4);
         sum = w + sum;
-        if (r[a] < w / fmaxf(1e-3f, sum)) k = 1;
+        if (MT::fast ? (r[a] * fmaxf(1e-3f, sum) < w) : (r[a] < w / fmaxf(1e-3f, sum))) k = 1;
         w = (1.f / 6.f) * (-3 * t1 * t2 + 3 * t2 + 3 * t1 + 1);
         sum = w + sum;
-        if (r[3 + a] < w / fmaxf(1e-3f, sum)) k = 2;
+        if (MT::fast ? (r[3 + a] * fmaxf(1e-3f, sum) < w) : (r[3 + a] < w / fmaxf(1e-3f, sum))) k = 2;
         w = (1.f / 6.f) * t1 * t2;
         sum = w + sum;
-        if (r[6 + a] < w / fmaxf(1e-3f, sum)) k = 3;
+        if (MT::fast ? (r[6 + a] * fmaxf(1e-3f, sum) < w) : (r[6 + a] < w / fmaxf(1e-3f, sum))) k = 3;
         idx[a] = k;
     }
     return make_int3(int(fx) + idx[0] - 1, int(fy) + idx[1] - 1, int(fz) + idx[2] - 1);
 }
 
 // tf_window + tf_lookup (common.glsl:203-212)
+template <class MT>
 VR_DEV float4 tf_lookup(const TraceArgs& a, float d) {
-    const float tc = fminf(fmaxf((d - a.p.tf_window_left) / a.p.tf_window_width, 0.0f), 1.0f - 1e-6f);
+    const float tc = fminf(fmaxf(MT::div(d - a.p.tf_window_left, a.p.tf_window_width), 0.0f), 1.0f - 1e-6f);
     const float s = tc * float(a.tf_size);
     const float fl = floorf(s);
     const int idx = int(fl);
@@ -112,7 +154,7 @@ VR_DEV float4 tf_lookup(const TraceArgs& a, float d) {
     const float4 A = __ldg(a.lut + idx), B = __ldg(a.lut + idx1);
     return make_float4(mixf(A.x, B.x, f), mixf(A.y, B.y, f), mixf(A.z, B.z, f), mixf(A.w, B.w, f));
 }
-// only the alpha channel (majorant mapping, common.glsl:425/472)
+// only the alpha channel (majorant mapping, common.glsl:425/472); always IEEE: it fills the majorant tables
 VR_DEV float tf_lookup_alpha(const TraceArgs& a, float d) {
     const float tc = fminf(fmaxf((d - a.p.tf_window_left) / a.p.tf_window_width, 0.0f), 1.0f - 1e-6f);
     const float s = tc * float(a.tf_size);
@@ -123,34 +165,62 @@ VR_DEV float tf_lookup_alpha(const TraceArgs& a, float d) {
     return mixf(__ldg(&a.lut[idx].w), __ldg(&a.lut[idx1].w), f);
 }
 
-// lookup_density_trilinear (common.glsl:289-297) without density_scale
+// lookup_density_trilinear (common.glsl:289-297) without density_scale. When the 2x2x2 footprint lies inside one
+// brick (67 % of the positions) the eight taps share one record and come from four 8-byte rows of the
+// brick-linear atlas; otherwise the four x-pairs are fetched in a rolled loop (code size).
 VR_DEV float density_trilinear(const GridView& g, float3 ipos) {
     const float qx = ipos.x - 0.5f, qy = ipos.y - 0.5f, qz = ipos.z - 0.5f;
     const float flx = floorf(qx), fly = floorf(qy), flz = floorf(qz);
     const float fx = qx - flx, fy = qy - fly, fz = qz - flz;
     const int x = int(flx), y = int(fly), z = int(flz);
-    const float lx0 = mixf(brick_value(g, x, y, z), brick_value(g, x + 1, y, z), fx);
-    const float lx1 = mixf(brick_value(g, x, y + 1, z), brick_value(g, x + 1, y + 1, z), fx);
-    const float hx0 = mixf(brick_value(g, x, y, z + 1), brick_value(g, x + 1, y, z + 1), fx);
-    const float hx1 = mixf(brick_value(g, x, y + 1, z + 1), brick_value(g, x + 1, y + 1, z + 1), fx);
-    return mixf(mixf(lx0, lx1, fy), mixf(hx0, hx1, fy), fz);
+    const int lx = x & 7, ly = y & 7, lz = z & 7;
+    const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+    if (lx < 7 && ly < 7 && lz < 7 && unsigned(bx) < g.nb.x && unsigned(by) < g.nb.y && unsigned(bz) < g.nb.z) {
+        const uint2 r = __ldg(g.rec + (size_t(bz) * g.nb.y + by) * g.nb.x + bx);
+        const float lo = range_lo(r.y), span = range_hi(r.y) - lo;
+        uint32_t b00 = 0, b10 = 0, b01 = 0, b11 = 0;
+        if (r.x != 0xffffffffu) {
+            const uint2* rows = reinterpret_cast<const uint2*>(g.atlas_lin + size_t(r.x) * 512u) + (lz * 8 + ly);
+            const uint2 r00 = __ldg(rows), r10 = __ldg(rows + 1), r01 = __ldg(rows + 8), r11 = __ldg(rows + 9);
+            const int sh = lx * 8;
+            b00 = uint32_t((((unsigned long long)r00.y << 32) | r00.x) >> sh); b10 = uint32_t((((unsigned long long)r10.y << 32) | r10.x) >> sh);
+            b01 = uint32_t((((unsigned long long)r01.y << 32) | r01.x) >> sh); b11 = uint32_t((((unsigned long long)r11.y << 32) | r11.x) >> sh);
+        }
+        const float lx0 = mixf(lo + unorm8_to_float(b00 & 255u) * span, lo + unorm8_to_float((b00 >> 8) & 255u) * span, fx);
+        const float lx1 = mixf(lo + unorm8_to_float(b10 & 255u) * span, lo + unorm8_to_float((b10 >> 8) & 255u) * span, fx);
+        const float hx0 = mixf(lo + unorm8_to_float(b01 & 255u) * span, lo + unorm8_to_float((b01 >> 8) & 255u) * span, fx);
+        const float hx1 = mixf(lo + unorm8_to_float(b11 & 255u) * span, lo + unorm8_to_float((b11 >> 8) & 255u) * span, fx);
+        return mixf(mixf(lx0, lx1, fy), mixf(hx0, hx1, fy), fz);
+    }
+    float lo_z = 0.f, prev = 0.f, out = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int yy = y + (k & 1), zz = z + (k >> 1);
+        const float row = mixf(brick_value(g, x, yy, zz), brick_value(g, x + 1, yy, zz), fx);
+        if (k == 1) lo_z = mixf(prev, row, fy);
+        if (k == 3) out = mixf(lo_z, mixf(prev, row, fy), fz);
+        prev = row;
+    }
+    return out;
 }
 
 // lookup_emission (common.glsl:324-328). Without an emission grid the samplers are unbound (value 0) but the
 // tricubic filter still consumes 9 draws: that case is an O(1) LCG jump.
+template <class MT>
 VR_DEV float3 lookup_emission(const TraceArgs& a, float3 ipos, uint32_t& seed, bool& fetched) {
     fetched = false;
     if (!a.p.has_emission) { rng_skip<9>(seed); return f3(0.f); }
     const float3 ipos_e = mul_point(a.emis_from_density, ipos);
-    const int3 tap = stochastic_tricubic_filter(ipos_e, seed);
+    const int3 tap = stochastic_tricubic_filter<MT>(ipos_e, seed);
     fetched = true;
     const float t = brick_value(a.emission, tap.x, tap.y, tap.z) * a.p.vol_emission_norm;
     return a.p.vol_emission_scale * f3(sqr(t), sqr(sqr(t)), sqr(sqr(sqr(t))));
 }
 
 // intersect_box (common.glsl:157-165)
+template <class MT>
 VR_DEV bool intersect_box(float3 pos, float3 dir, const float* bb_min, const float* bb_max, float& tnear, float& tfar) {
-    const float3 inv = f3(1.f / dir.x, 1.f / dir.y, 1.f / dir.z);
+    const float3 inv = f3(MT::rcp(dir.x), MT::rcp(dir.y), MT::rcp(dir.z));
     const float3 lo = (f3(bb_min[0], bb_min[1], bb_min[2]) - pos) * inv;
     const float3 hi = (f3(bb_max[0], bb_max[1], bb_max[2]) - pos) * inv;
     const float3 tmin = f3(fminf(lo.x, hi.x), fminf(lo.y, hi.y), fminf(lo.z, hi.z));
@@ -162,7 +232,7 @@ VR_DEV bool intersect_box(float3 pos, float3 dir, const float* bb_min, const flo
 
 // stepDDA (common.glsl:404-409)
 VR_DEV float step_dda(float3 pos, float3 ri, int mip) {
-    const float dim = float(8 << mip), inv_dim = 1.f / dim;  // exact powers of two
+    const float dim = float(8 << mip), inv_dim = __uint_as_float(0x3e000000u - (uint32_t(mip) << 23));  // 1/dim, exact power of two
     const float ox = ri.x >= 0.f ? dim + 0.5f : -0.5f;
     const float oy = ri.y >= 0.f ? dim + 0.5f : -0.5f;
     const float oz = ri.z >= 0.f ? dim + 0.5f : -0.5f;
@@ -175,23 +245,47 @@ VR_DEV float step_dda(float3 pos, float3 ri, int mip) {
 // GLSL round() is implementation-defined at .5; Mesa lowers it to round-half-even
 VR_DEV int round_mip(float mip) { return __float2int_rn(mip); }
 
+template <class MT>
 VR_DEV float phase_hg(float cos_t, float g) {  // common.glsl:172-175
     const float denom = 1 + sqr(g) + 2 * g * cos_t;
-    return INV_4PI * (1 - sqr(g)) / (denom * sqrtf(denom));
+    return MT::div(INV_4PI * (1 - sqr(g)), denom * MT::sqrt(denom));
 }
+template <class MT>
 VR_DEV float3 align_to(float3 N, float3 v) {  // common.glsl:25-33
-    const float3 T = fabsf(N.x) > fabsf(N.y) ? f3(-N.z, 0.f, N.x) / sqrtf(N.x * N.x + N.z * N.z)
-                                             : f3(0.f, N.z, -N.y) / sqrtf(N.y * N.y + N.z * N.z);
+    float3 T;
+    if (fabsf(N.x) > fabsf(N.y)) T = MT::fast ? f3(-N.z, 0.f, N.x) * rsqrtf(N.x * N.x + N.z * N.z) : f3(-N.z, 0.f, N.x) / sqrtf(N.x * N.x + N.z * N.z);
+    else T = MT::fast ? f3(0.f, N.z, -N.y) * rsqrtf(N.y * N.y + N.z * N.z) : f3(0.f, N.z, -N.y) / sqrtf(N.y * N.y + N.z * N.z);
     const float3 B = cross(N, T);
-    return normalize(v.x * T + v.y * B + v.z * N);
+    return MT::normalize(v.x * T + v.y * B + v.z * N);
 }
+template <class MT>
 VR_DEV float3 sample_phase_hg(float3 dir, float g, float s0, float s1) {  // common.glsl:184-190
-    const float cos_t = fabsf(g) < 1e-4f ? 1.f - 2.f * s0 : (1 + sqr(g) - sqr((1 - sqr(g)) / (1 - g + 2 * g * s0))) / (2 * g);
-    const float sin_t = sqrtf(fmaxf(0.f, 1.f - sqr(cos_t)));
+    const float cos_t = fabsf(g) < 1e-4f ? 1.f - 2.f * s0 : MT::div(1 + sqr(g) - sqr(MT::div(1 - sqr(g), 1 - g + 2 * g * s0)), 2 * g);
+    const float sin_t = MT::sqrt(fmaxf(0.f, 1.f - sqr(cos_t)));
     const float phi = 2.f * PI_F * s1;
     float sp, cp;
-    sincosf(phi, &sp, &cp);
-    return align_to(dir, f3(sin_t * cp, sin_t * sp, cos_t));
+    MT::sincos(phi, &sp, &cp);
+    return align_to<MT>(dir, f3(sin_t * cp, sin_t * sp, cos_t));
+}
+
+// bilinear REPEAT fetch with a cheap wrap (uv in [-1, 2] never needs the integer modulo)
+VR_DEV int wrap_fast(int i, int n) {
+    if (i < 0) i += n; else if (i >= n) i -= n;
+    while (i < 0) i += n;        // only for |uv| > 2: never taken by the tracer's own lookups
+    while (i >= n) i -= n;
+    return i;
+}
+VR_DEV float3 env_texture_fw(const EnvView& e, float u, float v) {
+    const float x = u * float(e.w) - 0.5f, y = v * float(e.h) - 0.5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float ax = x - fx, ay = y - fy;
+    const int x0 = wrap_fast(int(fx), e.w), y0 = wrap_fast(int(fy), e.h);
+    const int x1 = x0 + 1 == e.w ? 0 : x0 + 1, y1 = y0 + 1 == e.h ? 0 : y0 + 1;
+    const float4 t00 = __ldg(e.rgb + size_t(y0) * e.w + x0), t10 = __ldg(e.rgb + size_t(y0) * e.w + x1);
+    const float4 t01 = __ldg(e.rgb + size_t(y1) * e.w + x0), t11 = __ldg(e.rgb + size_t(y1) * e.w + x1);
+    return f3(mixf(mixf(t00.x, t10.x, ax), mixf(t01.x, t11.x, ax), ay),
+              mixf(mixf(t00.y, t10.y, ax), mixf(t01.y, t11.y, ax), ay),
+              mixf(mixf(t00.z, t10.z, ax), mixf(t01.z, t11.z, ax), ay));
 }
 
 // lookup_environment (common.glsl:93-98)
@@ -199,19 +293,21 @@ VR_DEV float3 lookup_environment(const TraceArgs& a, float3 dir) {
     const float3 idir = mul(*reinterpret_cast<const Mat3*>(a.p.env_inv_transform), dir);
     const float u = atan2f(idir.z, idir.x) / (2 * PI_F) + 0.5f;
     const float v = 1.f - acosf(fminf(fmaxf(idir.y, -1.f), 1.f)) / PI_F;
-    return a.p.env_strength * env_texture(a.env, u, v);
+    return a.p.env_strength * env_texture_fw(a.env, u, v);
 }
-// pdf_environment (common.glsl:148-152)
+// pdf_environment (common.glsl:148-152), given Le = lookup_environment(dir)
+template <class MT>
 VR_DEV float pdf_environment(const TraceArgs& a, float3 Le_dir) {
     const float avg_w = __ldg(a.env.impmap + imp_offset(9));
-    return luma(Le_dir) / avg_w * INV_4PI;
+    return MT::div(luma(Le_dir), avg_w) * INV_4PI;
 }
 
-// sample_environment (common.glsl:100-146): hierarchical 2x2 warping down the importance pyramid
+// sample_environment (common.glsl:100-146): hierarchical 2x2 warping down the importance pyramid (rolled: code size)
+template <class MT>
 VR_DEV float4 sample_environment(const TraceArgs& a, float px, float py, float3& w_i) {
     int posx = 0, posy = 0;
     uint32_t off = imp_offset(9);
-#pragma unroll
+#pragma unroll 1
     for (int mip = 8; mip >= 0; --mip) {
         posx *= 2; posy *= 2;
         const int d = IMP_DIM >> mip;
@@ -220,25 +316,25 @@ VR_DEV float4 sample_environment(const TraceArgs& a, float px, float py, float3&
         const float2 r0 = __ldg(reinterpret_cast<const float2*>(base));        // w[0], w[1]
         const float2 r1 = __ldg(reinterpret_cast<const float2*>(base + d));    // w[2], w[3]
         const float q0 = r0.x + r1.x, q1 = r0.y + r1.y;
-        const float dsplit = q0 / fmaxf(1e-8f, q0 + q1);
-        int off_x;
-        if (px < dsplit) { off_x = 0; px = px / dsplit; }
-        else { off_x = 1; px = (px - dsplit) / (1.f - dsplit); }
-        posx += off_x;
-        const float e = (off_x ? r0.y : r0.x) / (off_x ? q1 : q0);
-        if (py < e) { py = py / e; }
-        else { posy += 1; py = (py - e) / (1.f - e); }
+        const float dsplit = MT::div(q0, fmaxf(1e-8f, q0 + q1));
+        const bool right = !(px < dsplit);
+        px = right ? MT::div(px - dsplit, 1.f - dsplit) : MT::div(px, dsplit);
+        posx += right ? 1 : 0;
+        const float e = MT::div(right ? r0.y : r0.x, right ? q1 : q0);
+        const bool top = !(py < e);
+        py = top ? MT::div(py - e, 1.f - e) : MT::div(py, e);
+        posy += top ? 1 : 0;
     }
     const float uvx = (float(posx) + px) * (1.f / IMP_DIM), uvy = (float(posy) + py) * (1.f / IMP_DIM);
     const float theta = saturate(1.f - uvy) * PI_F;
     const float phi = (saturate(uvx) * 2.f - 1.f) * PI_F;
     float st, ct, sp, cp;
-    sincosf(theta, &st, &ct);
-    sincosf(phi, &sp, &cp);
+    MT::sincos(theta, &st, &ct);
+    MT::sincos(phi, &sp, &cp);
     w_i = mul(*reinterpret_cast<const Mat3*>(a.p.env_transform), f3(st * cp, ct, st * sp));
-    const float3 Le = a.p.env_strength * env_texture(a.env, uvx, uvy);
+    const float3 Le = a.p.env_strength * env_texture_fw(a.env, uvx, uvy);
     const float avg_w = __ldg(a.env.impmap + imp_offset(9));
-    const float pdf = __ldg(a.env.impmap + size_t(posy) * IMP_DIM + posx) / avg_w;
+    const float pdf = MT::div(__ldg(a.env.impmap + size_t(posy) * IMP_DIM + posx), avg_w);
     return make_float4(Le.x, Le.y, Le.z, pdf * INV_4PI);
 }
 
@@ -246,12 +342,13 @@ struct Ray {
     float3 ipos, idir, ri;
     float tnear, tfar;
 };
+template <class MT>
 VR_DEV bool setup_ray(const TraceArgs& a, float3 wpos, float3 wdir, Ray& r) {
-    if (!intersect_box(wpos, wdir, a.p.vol_bb_min, a.p.vol_bb_max, r.tnear, r.tfar)) return false;
+    if (!intersect_box<MT>(wpos, wdir, a.p.vol_bb_min, a.p.vol_bb_max, r.tnear, r.tfar)) return false;
     const Mat4& M = *reinterpret_cast<const Mat4*>(a.p.vol_density_inv_transform);
     r.ipos = mul_point(M, wpos);
     r.idir = mul_dir(M, wdir);  // non-normalised
-    r.ri = f3(1.f / r.idir.x, 1.f / r.idir.y, 1.f / r.idir.z);
+    r.ri = f3(MT::rcp(r.idir.x), MT::rcp(r.idir.y), MT::rcp(r.idir.z));
     return true;
 }
 
@@ -266,11 +363,11 @@ VR_DEV float majorant_at(const TraceArgs& a, float3 curr, int mip, Cnt<COUNT>& c
 }
 
 // transmittanceDDA (common.glsl:412-455)
-template <bool TF, bool COUNT>
+template <bool TF, bool COUNT, class MT>
 VR_DEV float transmittance_dda(const TraceArgs& a, float3 wpos, float3 wdir, uint32_t& seed, Cnt<COUNT>& cnt) {
     Ray r;
-    if (!setup_ray(a, wpos, wdir, r)) return 1.f;
-    float t = r.tnear + 1e-6f, Tr = 1.f, tau = -logf(1.f - rng(seed)), mip = 3.f;
+    if (!setup_ray<MT>(a, wpos, wdir, r)) return 1.f;
+    float t = r.tnear + 1e-6f, Tr = 1.f, tau = -MT::log(1.f - rng(seed)), mip = 3.f;
     for (int it = 0; t < r.tfar && it < MAX_DDA_ITERS; ++it) {
         const float3 curr = r.ipos + t * r.idir;
         const int m = round_mip(mip);
@@ -280,36 +377,36 @@ VR_DEV float transmittance_dda(const TraceArgs& a, float3 wpos, float3 wdir, uin
         tau -= majorant * dt;
         mip = fminf(mip + 0.25f, 3.f);
         if (tau > 0) continue;
-        t += tau / majorant;
+        t += MT::div(tau, majorant);
         if (t >= r.tfar) break;
         cnt.dens();
         float d;
-        if (TF) d = a.p.vol_majorant * tf_lookup_alpha(a, a.p.vol_density_scale * density_trilinear(a.density, r.ipos + t * r.idir) * a.p.vol_inv_majorant);
+        if (TF) d = a.p.vol_majorant * tf_lookup<MT>(a, a.p.vol_density_scale * density_trilinear(a.density, r.ipos + t * r.idir) * a.p.vol_inv_majorant).w;
         else {
-            const int3 tap = stochastic_tricubic_filter(r.ipos + t * r.idir, seed);
+            const int3 tap = stochastic_tricubic_filter<MT>(r.ipos + t * r.idir, seed);
             d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
         }
         if (rng(seed) * majorant < d) {
-            Tr *= fmaxf(0.f, 1.f - a.p.vol_majorant / majorant);
+            Tr *= fmaxf(0.f, 1.f - MT::div(a.p.vol_majorant, majorant));
             if (Tr < .1f) {
                 const float prob = 1 - Tr;
                 if (rng(seed) < prob) return 0.f;
-                Tr /= 1 - prob;
+                Tr = MT::div(Tr, 1 - prob);
             }
         }
-        tau = -logf(1.f - rng(seed));
+        tau = -MT::log(1.f - rng(seed));
         mip = fmaxf(0.f, mip - 2.f);
     }
     return Tr;
 }
 
 // sample_volumeDDA (common.glsl:458-501)
-template <bool TF, bool COUNT>
+template <bool TF, bool COUNT, class MT>
 VR_DEV bool sample_volume_dda(const TraceArgs& a, float3 wpos, float3 wdir, float& t_out, float3& throughput, float3& Le, uint32_t& seed, Cnt<COUNT>& cnt) {
     Ray r;
-    if (!setup_ray(a, wpos, wdir, r)) return false;
+    if (!setup_ray<MT>(a, wpos, wdir, r)) return false;
     const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-    float t = r.tnear + 1e-6f, tau = -logf(1.f - rng(seed)), mip = 3.f;
+    float t = r.tnear + 1e-6f, tau = -MT::log(1.f - rng(seed)), mip = 3.f;
     for (int it = 0; t < r.tfar && it < MAX_DDA_ITERS; ++it) {
         const float3 curr = r.ipos + t * r.idir;
         const int m = round_mip(mip);
@@ -319,22 +416,22 @@ VR_DEV bool sample_volume_dda(const TraceArgs& a, float3 wpos, float3 wdir, floa
         tau -= majorant * dt;
         mip = fminf(mip + 0.25f, 3.f);
         if (tau > 0) continue;
-        t += tau / majorant;
+        t += MT::div(tau, majorant);
         if (t >= r.tfar) break;
         cnt.dens();
         const float3 at = r.ipos + t * r.idir;
         float d;
         float3 tf_rgb = f3(1.f);
         if (TF) {
-            const float4 rgba = tf_lookup(a, a.p.vol_density_scale * density_trilinear(a.density, at) * a.p.vol_inv_majorant);
+            const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * density_trilinear(a.density, at) * a.p.vol_inv_majorant);
             d = a.p.vol_majorant * rgba.w;
             tf_rgb = f3(rgba.x, rgba.y, rgba.z);
         } else {
-            const int3 tap = stochastic_tricubic_filter(at, seed);
+            const int3 tap = stochastic_tricubic_filter<MT>(at, seed);
             d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
         }
         bool fetched;
-        const float3 em = lookup_emission(a, at, seed, fetched);
+        const float3 em = lookup_emission<MT>(a, at, seed, fetched);
         if (fetched) {
             cnt.emis();
             Le = Le + throughput * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant;
@@ -345,76 +442,73 @@ VR_DEV bool sample_volume_dda(const TraceArgs& a, float3 wpos, float3 wdir, floa
             t_out = t;
             return true;
         }
-        tau = -logf(1.f - rng(seed));
+        tau = -MT::log(1.f - rng(seed));
         mip = fmaxf(0.f, mip - 2.f);
     }
     return false;
 }
 
 // trace_path (common.glsl:599-652)
-template <bool TF, bool COUNT>
+template <bool TF, bool COUNT, class MT>
 VR_DEV float4 trace_path(const TraceArgs& a, float3 pos, float3 dir, uint32_t& seed, Cnt<COUNT>& cnt) {
     float3 L = f3(0.f), throughput = f3(1.f);
     bool free_path = true;
     uint32_t n_paths = 0;
     float t = 0.f, f_p = 0.f;
-    while (sample_volume_dda<TF, COUNT>(a, pos, dir, t, throughput, L, seed, cnt)) {
+    while (sample_volume_dda<TF, COUNT, MT>(a, pos, dir, t, throughput, L, seed, cnt)) {
         cnt.real();
         pos = pos + t * dir;
         float3 w_i;
         const float r0 = rng(seed), r1 = rng(seed);
         cnt.nee();
-        const float4 Le_pdf = sample_environment(a, r0, r1, w_i);
+        const float4 Le_pdf = sample_environment<MT>(a, r0, r1, w_i);
         if (Le_pdf.w > 0) {
-            f_p = phase_hg(dot(-dir, w_i), a.p.vol_phase_g);
-            const float mis_weight = a.p.show_environment > 0 ? power_heuristic(Le_pdf.w, f_p) : 1.f;
-            const float Tr = transmittance_dda<TF, COUNT>(a, pos, w_i, seed, cnt);
-            L = L + throughput * mis_weight * f_p * Tr * f3(Le_pdf.x, Le_pdf.y, Le_pdf.z) / Le_pdf.w;
+            f_p = phase_hg<MT>(dot(-dir, w_i), a.p.vol_phase_g);
+            const float mis_weight = a.p.show_environment > 0 ? MT::div(sqr(Le_pdf.w), sqr(Le_pdf.w) + sqr(f_p)) : 1.f;
+            const float Tr = transmittance_dda<TF, COUNT, MT>(a, pos, w_i, seed, cnt);
+            const float3 c = throughput * mis_weight * f_p * Tr * f3(Le_pdf.x, Le_pdf.y, Le_pdf.z);
+            L = L + f3(MT::div(c.x, Le_pdf.w), MT::div(c.y, Le_pdf.w), MT::div(c.z, Le_pdf.w));
         }
         if (++n_paths >= uint32_t(a.p.bounces)) { free_path = false; break; }
         const float rr_val = luma(throughput);
         if (rr_val < .1f) {
             const float prob = 1 - rr_val;
             if (rng(seed) < prob) { free_path = false; break; }
-            throughput = throughput / (1 - prob);
+            const float k = 1 - prob;
+            throughput = f3(MT::div(throughput.x, k), MT::div(throughput.y, k), MT::div(throughput.z, k));
         }
         const float s0 = rng(seed), s1 = rng(seed);
-        const float3 scatter_dir = sample_phase_hg(dir, a.p.vol_phase_g, s0, s1);
-        f_p = phase_hg(dot(-dir, scatter_dir), a.p.vol_phase_g);
+        const float3 scatter_dir = sample_phase_hg<MT>(dir, a.p.vol_phase_g, s0, s1);
+        f_p = phase_hg<MT>(dot(-dir, scatter_dir), a.p.vol_phase_g);
         dir = scatter_dir;
     }
     if (free_path && a.p.show_environment > 0) {
         cnt.env();
         const float3 Le = lookup_environment(a, dir);
-        const float mis_weight = n_paths > 0 ? power_heuristic(f_p, pdf_environment(a, Le)) : 1.f;
+        const float pe = pdf_environment<MT>(a, Le);
+        const float mis_weight = n_paths > 0 ? MT::div(sqr(f_p), sqr(f_p) + sqr(pe)) : 1.f;
         L = L + throughput * mis_weight * Le;
     }
     return make_float4(L.x, L.y, L.z, fminf(float(n_paths), 1.f));
 }
 
 // view_dir (common.glsl:76-80)
+template <class MT>
 VR_DEV float3 view_dir(const TraceArgs& a, int x, int y, float sx, float sy) {
     const float w = float(a.p.resolution[0]), h = float(a.p.resolution[1]);
-    const float px = (float(x) + sx - w * .5f) / h, py = (float(y) + sy - h * .5f) / h;
-    const float z = -.5f / tanf(.5f * PI_F * a.p.cam_fov / 180.f);
-    return normalize(mul(*reinterpret_cast<const Mat3*>(a.p.cam_transform), normalize(f3(px, py, z))));
+    const float px = MT::div(float(x) + sx - w * .5f, h), py = MT::div(float(y) + sy - h * .5f, h);
+    return MT::normalize(mul(*reinterpret_cast<const Mat3*>(a.p.cam_transform), MT::normalize(f3(px, py, a.cam_z))));
 }
 
 // running mean of pathtracer_brick.glsl:36, unfused so that it matches mix() = x*(1-a) + y*a bit for bit
 VR_DEV float mix_rn(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, __fsub_rn(1.f, a)), __fmul_rn(y, a)); }
 
-VR_DEV void flush_counters(const TraceArgs&, const Cnt<false>&) {}
-VR_DEV void flush_counters(const TraceArgs& a, const Cnt<true>& c) {
-    const uint32_t v[7] = { c.n_samp, c.n_maj, c.n_dens, c.n_emis, c.n_nee, c.n_env, c.n_real };
-#pragma unroll
-    for (int i = 0; i < 7; ++i) atomicAdd(a.counters + i, (unsigned long long)v[i]);
-}
-
 // main() of pathtracer_brick.glsl:23-37, one thread per pixel, all requested samples of that pixel in
 // sample order (so the running mean is evaluated exactly like n successive dispatches).
-// Warps cover 8x4 pixel tiles for ray coherence.
+// Warps cover 8x4 pixel tiles for ray coherence. Cross-check kernel (StrictMath), not the production path.
 template <bool TF, bool COUNT>
 __global__ void __launch_bounds__(256) k_trace_pixels(const __grid_constant__ TraceArgs a) {
+    using MT = StrictMath;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = a.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int y = a.y0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
@@ -427,8 +521,8 @@ __global__ void __launch_bounds__(256) k_trace_pixels(const __grid_constant__ Tr
     for (int s = a.first_sample; s < a.first_sample + a.n_samples; ++s) {
         uint32_t seed = tea32(uint32_t(a.p.seed) * uint32_t(y * W + x), uint32_t(s));
         const float jx = rng(seed), jy = rng(seed);
-        const float3 dir = view_dir(a, x, y, jx, jy);
-        float4 L = trace_path<TF, COUNT>(a, cam, dir, seed, cnt);
+        const float3 dir = view_dir<MT>(a, x, y, jx, jy);
+        float4 L = trace_path<TF, COUNT, MT>(a, cam, dir, seed, cnt);
         L.x = sanitize(L.x); L.y = sanitize(L.y); L.z = sanitize(L.z); L.w = sanitize(L.w);
         cnt.samp();
         if (a.accum_mode == VRB_ACCUM_MEAN) {
@@ -446,15 +540,16 @@ __global__ void __launch_bounds__(256) k_trace_pixels(const __grid_constant__ Tr
 // deterministic transmittance-only mode ("T1"): centre ray, exact voxel DDA with empty-brick
 // skipping, color = (Tr * Le_env(dir), 1 - Tr). fp32 on the device; the oracle evaluates it in fp64.
 __global__ void __launch_bounds__(256) k_trace_deterministic(const __grid_constant__ TraceArgs a) {
+    using MT = StrictMath;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int y = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
     if (x >= a.p.resolution[0] || y >= a.p.resolution[1]) return;
-    const float3 dir = view_dir(a, x, y, .5f, .5f);
+    const float3 dir = view_dir<MT>(a, x, y, .5f, .5f);
     const float3 pos = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
     Ray r;
     float tau = 0.f;
-    if (setup_ray(a, pos, dir, r)) {
+    if (setup_ray<MT>(a, pos, dir, r)) {
         float t = r.tnear;
         const GridView& g = a.density;
         for (int it = 0; t < r.tfar && it < MAX_DDA_ITERS; ++it) {

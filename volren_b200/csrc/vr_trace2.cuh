@@ -1,0 +1,314 @@
+// Persistent-thread tracking kernel (the production path of vrb_trace).
+//
+// Same per-path algorithm and random-number order as the straightforward kernel in vr_trace.cuh
+// (kept as the in-library cross-check, vrb_set_kernel(ctx, 1)), restructured for the SIMT machine:
+//   * one lane owns one PIXEL for all samples of the launch (running mean stays in registers, in sample
+//     order, exactly like n successive dispatches of pathtracer_brick.glsl) and fetches the next pixel from
+//     a global ticket when it is done -> no tail of idle SMs behind the few long pixels;
+//   * camera segments and shadow rays share ONE brick-DDA loop body (common.glsl:412-501 differ only in what
+//     happens at a collision), so a warp's lanes step convergently whatever kind of ray they are on;
+//   * path events are scheduled wavefront-style INSIDE the warp: a lane whose ray ended parks in one of three
+//     queues (NEE / SCATTER / FINISH); a queue's stage runs when enough lanes wait in it (or nothing else can
+//     make progress), so the heavy, rare stages (importance-pyramid warp, phase sampling, escape lookup + TEA
+//     reseed) execute with many active lanes instead of one or two; every new ray (camera, shadow, scattered)
+//     is started at ONE shared site after the stages;
+//   * per-level majorants are read from float tables precomputed per (grid, params) with the identical
+//     expression (the TF variant otherwise evaluates a LUT lerp and a divide on every DDA step);
+//   * MT = FastMath in production (MUFU rcp/rsqrt/lg2/sin/cos): 3x less SASS than the IEEE sequences, which
+//     matters because the kernel was instruction-fetch bound (profiles/r01_v3_*: stall_no_instruction 50 %).
+#pragma once
+
+#include "vr_trace.cuh"
+
+namespace vr {
+
+// lane stages
+enum : int { SG_STEP = 0, SG_NEE = 1, SG_SCATTER = 2, SG_FINISH = 3, SG_IDLE = 4 };
+
+// fills one level of the majorant table: exactly majorant_at() of vr_trace.cuh, hoisted out of the DDA loop
+template <bool TF>
+__global__ void k_majorant_table(const __grid_constant__ TraceArgs a, int level, float* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const uint32_t w = level == 0 ? a.density.rec[i].y : a.density.mips[level - 1][i];
+        const float m = a.p.vol_density_scale * range_hi(w);
+        out[i] = TF ? a.p.vol_majorant * tf_lookup_alpha(a, m * a.p.vol_inv_majorant) : m;
+    }
+    if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) {   // out-of-bounds texelFetch returns 0 (robust access)
+        const float m = a.p.vol_density_scale * 0.f;
+        out[n] = TF ? a.p.vol_majorant * tf_lookup_alpha(a, m * a.p.vol_inv_majorant) : m;
+    }
+}
+
+VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
+    const int bx = int(floorf(ipos.x)) >> (3 + mip), by = int(floorf(ipos.y)) >> (3 + mip), bz = int(floorf(ipos.z)) >> (3 + mip);
+    const uint32_t nx = a.density.nb.x >> mip, ny = a.density.nb.y >> mip, nz = a.density.nb.z >> mip;
+    if (unsigned(bx) >= nx || unsigned(by) >= ny || unsigned(bz) >= nz) return __ldg(a.maj_oob);
+    return __ldg(a.maj[mip] + (size_t(bz) * ny + by) * nx + bx);
+}
+
+#ifndef VR_TRACE_BLOCK
+#define VR_TRACE_BLOCK 128
+#endif
+#ifndef VR_TRACE_MIN_BLOCKS
+#define VR_TRACE_MIN_BLOCKS 6
+#endif
+#ifndef VR_K_NEE
+#define VR_K_NEE 12       // lanes that must wait for next-event estimation before the stage runs
+#endif
+#ifndef VR_K_SCATTER
+#define VR_K_SCATTER 12
+#endif
+#ifndef VR_K_FINISH
+#define VR_K_FINISH 12
+#endif
+#ifndef VR_MIN_STEP
+#define VR_MIN_STEP 10    // fewer stepping lanes than this: drain the fullest queue even below its threshold
+#endif
+constexpr int MAX_RAY_STEPS = 1 << 20;  // hang guard only: no finite ray takes this many DDA steps
+
+template <bool TF, bool COUNT, class MT>
+__global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_persistent(const __grid_constant__ TraceArgs a) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int W = a.p.resolution[0];
+    const int s_end = a.first_sample + a.n_samples;
+    Cnt<COUNT> cnt;
+
+    // ---- lane state ----
+    int stage = SG_FINISH;         // everybody starts by fetching a pixel
+    bool shadow = false;           // kind of the ray being stepped
+    bool escaped = false;          // FINISH entered because the camera segment left the volume (-> environment)
+    bool have_pixel = false;
+    int px = 0, py = 0, s = 0, steps = 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t seed = 0, n_paths = 0;
+    float3 pos = f3(0.f), dir = f3(0.f, 0.f, -1.f), thr = f3(1.f), L = f3(0.f), pend = f3(0.f);
+    float3 ipos = f3(0.f), idir = f3(1.f), ri = f3(1.f);
+    float t = 0.f, tfar = -1.f, tau = 0.f, mip = 3.f, f_p = 0.f, Tr = 1.f;
+
+    while (true) {
+        // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) + tentative collision =================
+        if (stage == SG_STEP) {
+            bool collide = false;
+            float majorant = 0.f;
+            if (t < tfar) {
+                const float3 curr = ipos + t * idir;
+                const int m = round_mip(mip);
+                cnt.maj();
+                majorant = table_majorant(a, curr, m);
+                const float dt = step_dda(curr, ri, m);
+                t += dt;
+                tau -= majorant * dt;
+                mip = fminf(mip + 0.25f, 3.f);
+                if (!(tau > 0.f)) {
+                    t += MT::div(tau, majorant);
+                    collide = t < tfar;
+                }
+                if (++steps > MAX_RAY_STEPS) { t = INFINITY; collide = false; }
+            }
+            if (collide) {   // common.glsl:436-452 / 483-498
+                cnt.dens();
+                const float3 at = ipos + t * idir;
+                float d;
+                float3 tf_rgb = f3(1.f);
+                if (TF) {
+                    const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * density_trilinear(a.density, at) * a.p.vol_inv_majorant);
+                    d = a.p.vol_majorant * rgba.w;
+                    tf_rgb = f3(rgba.x, rgba.y, rgba.z);
+                } else {
+                    const int3 tap = stochastic_tricubic_filter<MT>(at, seed);
+                    d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
+                }
+                bool parked = false;
+                if (!shadow) {
+                    bool fetched;
+                    const float3 em = lookup_emission<MT>(a, at, seed, fetched);
+                    if (fetched) {
+                        cnt.emis();
+                        const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                        L = L + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant;
+                    }
+                    if (rng(seed) * majorant < d) {          // real collision: the segment ends here (common.glsl:490-496)
+                        thr = thr * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                        if (TF) thr = thr * tf_rgb;
+                        stage = SG_NEE;
+                        parked = true;
+                    }
+                } else {
+                    if (rng(seed) * majorant < d) {          // common.glsl:442-450
+                        Tr *= fmaxf(0.f, 1.f - MT::div(a.p.vol_majorant, majorant));
+                        if (Tr < .1f) {
+                            const float prob = 1 - Tr;
+                            if (rng(seed) < prob) { Tr = 0.f; t = INFINITY; parked = true; }
+                            else Tr = MT::div(Tr, 1 - prob);
+                        }
+                    }
+                }
+                if (!parked) {
+                    tau = -MT::log(1.f - rng(seed));
+                    mip = fmaxf(0.f, mip - 2.f);
+                }
+            }
+            if (stage == SG_STEP && !(t < tfar)) {   // the ray left the volume (or the shadow ray was absorbed)
+                if (shadow) {
+                    if (Tr != 0.f) L = L + pend * Tr;     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
+                    stage = SG_SCATTER;
+                } else {
+                    escaped = true;
+                    stage = SG_FINISH;
+                }
+            }
+        }
+
+        // ================= scheduler =================
+        const unsigned m_step = __ballot_sync(FULL, stage == SG_STEP);
+        const unsigned m_nee = __ballot_sync(FULL, stage == SG_NEE);
+        const unsigned m_scat = __ballot_sync(FULL, stage == SG_SCATTER);
+        const unsigned m_fin = __ballot_sync(FULL, stage == SG_FINISH);
+        if ((m_step | m_nee | m_scat | m_fin) == 0u) break;     // every lane idle
+        const int n_step = __popc(m_step), n_nee = __popc(m_nee), n_scat = __popc(m_scat), n_fin = __popc(m_fin);
+        bool run_nee = n_nee >= VR_K_NEE, run_scat = n_scat >= VR_K_SCATTER, run_fin = n_fin >= VR_K_FINISH;
+        if (!(run_nee | run_scat | run_fin)) {
+            if (n_step >= VR_MIN_STEP) continue;               // keep stepping
+            // too few lanes can step: drain the fullest queue
+            if (n_nee >= n_scat && n_nee >= n_fin) run_nee = n_nee > 0;
+            else if (n_scat >= n_fin) run_scat = n_scat > 0;
+            else run_fin = n_fin > 0;
+        }
+
+        bool start = false;     // this lane starts a new ray from (pos, rd) below
+        float3 rd = dir;
+
+        // ================= NEE: real collision -> next-event estimation (common.glsl:611-626) =================
+        if (run_nee && stage == SG_NEE) {
+            cnt.real();
+            pos = pos + t * dir;
+            float3 w_i;
+            const float r0 = rng(seed), r1 = rng(seed);
+            cnt.nee();
+            const float4 Le_pdf = sample_environment<MT>(a, r0, r1, w_i);
+            if (Le_pdf.w > 0) {
+                f_p = phase_hg<MT>(dot(-dir, w_i), a.p.vol_phase_g);
+                const float mis_weight = a.p.show_environment > 0 ? MT::div(sqr(Le_pdf.w), sqr(Le_pdf.w) + sqr(f_p)) : 1.f;
+                // L += throughput * mis_weight * f_p * Tr * Le / pdf, with Tr applied when the shadow ray is done
+                const float3 c = thr * mis_weight * f_p * f3(Le_pdf.x, Le_pdf.y, Le_pdf.z);
+                pend = f3(MT::div(c.x, Le_pdf.w), MT::div(c.y, Le_pdf.w), MT::div(c.z, Le_pdf.w));
+                Tr = 1.f;
+                shadow = true;
+                rd = w_i; start = true;
+                stage = SG_STEP;
+            } else {
+                stage = SG_SCATTER;
+            }
+        }
+
+        // ================= SCATTER: bounce limit, Russian roulette, phase sampling (common.glsl:628-641) =================
+        if (run_scat && stage == SG_SCATTER) {
+            bool end = false;
+            if (++n_paths >= uint32_t(a.p.bounces)) end = true;
+            else {
+                const float rr_val = luma(thr);
+                if (rr_val < .1f) {
+                    const float prob = 1 - rr_val;
+                    if (rng(seed) < prob) end = true;
+                    else { const float k = 1 - prob; thr = f3(MT::div(thr.x, k), MT::div(thr.y, k), MT::div(thr.z, k)); }
+                }
+            }
+            if (end) {
+                escaped = false;
+                stage = SG_FINISH;
+            } else {
+                const float s0 = rng(seed), s1 = rng(seed);
+                const float3 scatter_dir = sample_phase_hg<MT>(dir, a.p.vol_phase_g, s0, s1);
+                f_p = phase_hg<MT>(dot(-dir, scatter_dir), a.p.vol_phase_g);
+                dir = scatter_dir;
+                shadow = false;
+                rd = dir; start = true;
+                stage = SG_STEP;
+            }
+        }
+
+        // ================= FINISH: environment on escape, fold the sample, next sample / next pixel =================
+        if (run_fin) {     // warp-uniform: the ticket loop below uses warp collectives
+            const bool mine = stage == SG_FINISH;
+            if (mine && have_pixel) {
+                if (escaped && a.p.show_environment > 0) {      // common.glsl:644-649
+                    cnt.env();
+                    const float3 Le = lookup_environment(a, dir);
+                    const float pe = pdf_environment<MT>(a, Le);
+                    const float mis_weight = n_paths > 0 ? MT::div(sqr(f_p), sqr(f_p) + sqr(pe)) : 1.f;
+                    L = L + thr * mis_weight * Le;
+                }
+                cnt.samp();                                     // pathtracer_brick.glsl:36
+                const float Lx = sanitize(L.x), Ly = sanitize(L.y), Lz = sanitize(L.z), Lw = sanitize(fminf(float(n_paths), 1.f));
+                if (a.accum_mode == VRB_ACCUM_MEAN) {
+                    const float w = 1.f / float(s);
+                    acc.x = mix_rn(acc.x, Lx, w); acc.y = mix_rn(acc.y, Ly, w); acc.z = mix_rn(acc.z, Lz, w); acc.w = mix_rn(acc.w, Lw, w);
+                } else {
+                    acc.x += Lx; acc.y += Ly; acc.z += Lz; acc.w += Lw;
+                }
+                if (++s == s_end) {
+                    a.color[size_t(py) * W + px] = acc;
+                    have_pixel = false;
+                }
+            }
+            // pixel tickets (tile-major order: 32 consecutive tickets = one 8x4 pixel tile)
+            bool want = mine && !have_pixel;
+            while (true) {
+                const unsigned m_fetch = __ballot_sync(FULL, want);
+                if (m_fetch == 0u) break;
+                unsigned base = 0;
+                const int leader = __ffs(m_fetch) - 1;
+                if (lane == leader) base = atomicAdd(a.job_counter, unsigned(__popc(m_fetch)));
+                base = __shfl_sync(FULL, base, leader);
+                if (want) {
+                    const unsigned job = base + __popc(m_fetch & ((1u << lane) - 1u));
+                    if (job >= unsigned(a.n_jobs)) { want = false; stage = SG_IDLE; }
+                    else {
+                        const unsigned tile = job >> 5, within = job & 31u;
+                        px = a.x0 + int(tile % unsigned(a.tiles_x)) * 8 + int(within & 7u);
+                        py = a.y0 + int(tile / unsigned(a.tiles_x)) * 4 + int(within >> 3);
+                        if (px < a.x1 && py < a.y1) {
+                            acc = a.color[size_t(py) * W + px];
+                            s = a.first_sample;
+                            have_pixel = true;
+                            want = false;
+                        }
+                    }
+                }
+            }
+            // new sample: TEA seed, jittered camera ray (pathtracer_brick.glsl:28-30)
+            if (mine && stage == SG_FINISH) {
+                seed = tea32(uint32_t(a.p.seed) * uint32_t(py * W + px), uint32_t(s));
+                const float jx = rng(seed), jy = rng(seed);
+                dir = view_dir<MT>(a, px, py, jx, jy);
+                pos = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
+                thr = f3(1.f); L = f3(0.f); n_paths = 0; f_p = 0.f;
+                shadow = false; escaped = false;
+                rd = dir; start = true;
+                stage = SG_STEP;
+            }
+        }
+
+        // ================= start the new rays: clip + world->index + first free-flight draw (common.glsl:459-468 / 413-421) =================
+        if (start) {
+            float tn, tf;
+            steps = 0;
+            if (intersect_box<MT>(pos, rd, a.p.vol_bb_min, a.p.vol_bb_max, tn, tf)) {
+                const Mat4& M = *reinterpret_cast<const Mat4*>(a.p.vol_density_inv_transform);
+                ipos = mul_point(M, pos);
+                idir = mul_dir(M, rd);
+                ri = f3(MT::rcp(idir.x), MT::rcp(idir.y), MT::rcp(idir.z));
+                t = tn + 1e-6f;
+                tfar = tf;
+                tau = -MT::log(1.f - rng(seed));
+                mip = 3.f;
+            } else {
+                t = 0.f; tfar = -1.f;   // missed the box: the ray "ends" at once (Tr = 1 / escape)
+            }
+        }
+    }
+    flush_counters(a, cnt);
+}
+
+}  // namespace vr

@@ -6,6 +6,7 @@
 #include "vr_brick.cuh"
 #include "vr_env.cuh"
 #include "vr_trace.cuh"
+#include "vr_trace2.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -36,6 +37,9 @@ struct DeviceGrid {
     uint2* rec = nullptr;
     uint8_t* atlas_lin = nullptr;
     size_t n_slots = 0;
+    // majorant tables of the persistent kernel, valid for maj_key
+    float* maj[4] = { nullptr, nullptr, nullptr, nullptr };
+    uint64_t maj_key = 0;
 };
 
 struct Frame {
@@ -61,7 +65,11 @@ struct vrb_ctx {
     float4* lut = nullptr;
     uint32_t tf_size = 0;
     unsigned long long* counters = nullptr;
+    unsigned int* job_counter = nullptr;
     bool counting = false;
+    int kernel = 0;            // 0 = persistent FastMath (production), 1 = simple strict cross-check, 2 = persistent StrictMath
+    int trace_blocks[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    uint64_t lut_version = 0;
     std::string err;
 };
 
@@ -97,6 +105,7 @@ void free_grid(DeviceGrid& g) {
     cudaFree(g.indirection); cudaFree(g.range); cudaFree(g.atlas);
     for (auto& m : g.mips) cudaFree(m);
     cudaFree(g.rec); cudaFree(g.atlas_lin);
+    for (auto& m : g.maj) cudaFree(m);
     g = DeviceGrid();
 }
 
@@ -247,6 +256,7 @@ int fill_trace_args(vrb_ctx* ctx, const vrb_params* p, TraceArgs& a) {
     a.tf_size = ctx->tf_size;
     a.color = ctx->color;
     a.counters = ctx->counters;
+    a.cam_z = -.5f / std::tan(.5f * PI_F * p->cam_fov / 180.f);   // common.glsl:78, fp32 like the shader
     return VRB_OK;
 }
 
@@ -291,7 +301,8 @@ int vrb_create(int device, vrb_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     DeviceGuard guard(device);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->counters, 7 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMalloc(&ctx->counters, 7 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->job_counter, sizeof(unsigned int)) != cudaSuccess) {
         delete ctx;
         return VRB_ERR_CUDA;
     }
@@ -307,7 +318,7 @@ void vrb_destroy(vrb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& f : ctx->frames) { free_grid(f.second.slot[0]); free_grid(f.second.slot[1]); }
     if (!ctx->color_external) cudaFree(ctx->color);
-    cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->lut); cudaFree(ctx->counters);
+    cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -532,6 +543,7 @@ int vrb_tf_upload(vrb_ctx* ctx, const float* rgba, uint32_t n) {
     CK(cudaMemcpyAsync(ctx->lut, rgba, size_t(n) * 16, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->tf_size = n;
+    ctx->lut_version++;
     return VRB_OK;
 }
 
@@ -547,16 +559,77 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     if (a.x0 < 0 || a.y0 < 0 || a.x1 > ctx->w || a.y1 > ctx->h || a.x0 >= a.x1 || a.y0 >= a.y1) return fail(ctx, VRB_ERR_INVALID, "bad tile");
     a.first_sample = first_sample; a.n_samples = n_samples; a.accum_mode = accum_mode;
     DeviceGuard guard(ctx->device);
-    const dim3 grid((a.x1 - a.x0 + 15) / 16, (a.y1 - a.y0 + 15) / 16);
     const bool tf = params->use_transferfunc != 0;
-    if (ctx->counting) {
-        if (tf) k_trace_pixels<true, true><<<grid, 256, 0, ctx->stream>>>(a);
-        else k_trace_pixels<false, true><<<grid, 256, 0, ctx->stream>>>(a);
-    } else {
-        if (tf) k_trace_pixels<true, false><<<grid, 256, 0, ctx->stream>>>(a);
-        else k_trace_pixels<false, false><<<grid, 256, 0, ctx->stream>>>(a);
+    if (ctx->kernel == 1) {   // cross-check kernel: one thread per pixel, no regeneration
+        const dim3 grid((a.x1 - a.x0 + 15) / 16, (a.y1 - a.y0 + 15) / 16);
+        if (ctx->counting) {
+            if (tf) k_trace_pixels<true, true><<<grid, 256, 0, ctx->stream>>>(a);
+            else k_trace_pixels<false, true><<<grid, 256, 0, ctx->stream>>>(a);
+        } else {
+            if (tf) k_trace_pixels<true, false><<<grid, 256, 0, ctx->stream>>>(a);
+            else k_trace_pixels<false, false><<<grid, 256, 0, ctx->stream>>>(a);
+        }
+        CK_LAUNCH();
+        return VRB_OK;
     }
-    CK_LAUNCH();
+    // ---- production path: persistent kernel ----
+    DeviceGrid& g = ctx->frames[params->frame].slot[VRB_SLOT_DENSITY];
+    // majorant tables depend on (grid, density_scale, global majorant, TF + window + LUT): rebuild when the key changes
+    uint64_t key = 1469598103934665603ull;
+    auto mix_key = [&key](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); for (size_t i = 0; i < n; ++i) { key ^= b[i]; key *= 1099511628211ull; } };
+    mix_key(&params->vol_density_scale, 4); mix_key(&params->vol_majorant, 4); mix_key(&params->vol_inv_majorant, 4);
+    mix_key(&params->use_transferfunc, 4);
+    if (tf) { mix_key(&params->tf_window_left, 4); mix_key(&params->tf_window_width, 4); mix_key(&ctx->lut_version, 8); }
+    const size_t n0 = size_t(g.nb.x) * g.nb.y * g.nb.z;
+    if (!g.maj[0]) {
+        CK(cudaMalloc(&g.maj[0], (n0 + 1) * 4));   // + 1: the out-of-bounds majorant
+        for (int l = 1; l < 4; ++l) CK(cudaMalloc(&g.maj[l], mip_words(g.nb, l - 1) * 4));
+        g.maj_key = 0;
+    }
+    for (int l = 0; l < 4; ++l) a.maj[l] = g.maj[l];
+    a.maj_oob = g.maj[0] + n0;
+    if (g.maj_key != key) {
+        for (int l = 0; l < 4; ++l) {
+            const size_t n = l == 0 ? n0 : mip_words(g.nb, l - 1);
+            const int blocks = grid_for(n, 256, ctx->sm_count);
+            if (tf) k_majorant_table<true><<<blocks, 256, 0, ctx->stream>>>(a, l, g.maj[l], n);
+            else k_majorant_table<false><<<blocks, 256, 0, ctx->stream>>>(a, l, g.maj[l], n);
+            CK_LAUNCH();
+        }
+        g.maj_key = key;
+    }
+    a.tiles_x = (a.x1 - a.x0 + 7) / 8;
+    a.n_jobs = a.tiles_x * ((a.y1 - a.y0 + 3) / 4) * 32;
+    a.job_counter = ctx->job_counter;
+    CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
+    const int variant = (tf ? 1 : 0) | (ctx->counting ? 2 : 0) | (ctx->kernel == 2 ? 4 : 0);
+    const void* fn = nullptr;
+    switch (variant) {
+        case 0: fn = (const void*)k_trace_persistent<false, false, FastMath>; break;
+        case 1: fn = (const void*)k_trace_persistent<true, false, FastMath>; break;
+        case 2: fn = (const void*)k_trace_persistent<false, true, FastMath>; break;
+        case 3: fn = (const void*)k_trace_persistent<true, true, FastMath>; break;
+        case 4: fn = (const void*)k_trace_persistent<false, false, StrictMath>; break;
+        case 5: fn = (const void*)k_trace_persistent<true, false, StrictMath>; break;
+        case 6: fn = (const void*)k_trace_persistent<false, true, StrictMath>; break;
+        default: fn = (const void*)k_trace_persistent<true, true, StrictMath>; break;
+    }
+    if (!ctx->trace_blocks[variant]) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, VR_TRACE_BLOCK, 0));
+        ctx->trace_blocks[variant] = ctx->sm_count * (per_sm > 0 ? per_sm : 1);   // one resident wave: grid = 148 x blocks/SM
+    }
+    const int needed = (a.n_jobs / 32 + (VR_TRACE_BLOCK / 32) - 1) / (VR_TRACE_BLOCK / 32);
+    const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
+    void* kargs[] = { (void*)&a };
+    CK(cudaLaunchKernel(fn, dim3(blocks), dim3(VR_TRACE_BLOCK), kargs, 0, ctx->stream));
+    return VRB_OK;
+}
+
+int vrb_set_kernel(vrb_ctx* ctx, int kind) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (kind < 0 || kind > 2) return fail(ctx, VRB_ERR_INVALID, "kernel kind must be 0 (persistent, fast math), 1 (simple, strict math) or 2 (persistent, strict math)");
+    ctx->kernel = kind;
     return VRB_OK;
 }
 
