@@ -52,17 +52,26 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #ifndef VR_TRACE_MIN_BLOCKS
 #define VR_TRACE_MIN_BLOCKS 6
 #endif
-#ifndef VR_K_NEE
-#define VR_K_NEE 12       // lanes that must wait for next-event estimation before the stage runs
+// Queue thresholds, tuned on B200 (tools/sweep.py, profiles/r01_sweep.txt): the TF variant has cheap events and an
+// expensive 8-tap collision -> drain queues early (4); the non-TF variant prefers fuller queues (8) and keeps
+// stepping only while at least 16 lanes can.
+#ifndef VR_K_EVENT_TF
+#define VR_K_EVENT_TF 4
 #endif
-#ifndef VR_K_SCATTER
-#define VR_K_SCATTER 12
+#ifndef VR_K_EVENT
+#define VR_K_EVENT 8
 #endif
-#ifndef VR_K_FINISH
-#define VR_K_FINISH 12
+#ifndef VR_MIN_STEP_TF
+#define VR_MIN_STEP_TF 4
+#endif
+#ifndef VR_SUBSTEPS
+#define VR_SUBSTEPS 1     // DDA rounds per scheduler iteration (lanes with a pending collision sit out the extra rounds)
+#endif
+#ifndef VR_SUBSTEP_MIN
+#define VR_SUBSTEP_MIN 12 // an extra round needs at least this many lanes able to step
 #endif
 #ifndef VR_MIN_STEP
-#define VR_MIN_STEP 10    // fewer stepping lanes than this: drain the fullest queue even below its threshold
+#define VR_MIN_STEP 16    // fewer stepping lanes than this: drain the fullest queue even below its threshold
 #endif
 constexpr int MAX_RAY_STEPS = 1 << 20;  // hang guard only: no finite ray takes this many DDA steps
 
@@ -88,10 +97,15 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
 
     while (true) {
         // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) + tentative collision =================
-        if (stage == SG_STEP) {
-            bool collide = false;
-            float majorant = 0.f;
-            if (t < tfar) {
+        // Lanes that found a tentative collision wait (at most VR_SUBSTEPS - 1 extra rounds) while the others keep
+        // stepping, so that the expensive collision code below runs with more active lanes.
+        bool collide = false;
+        float majorant = 0.f;
+#pragma unroll 1
+        for (int sub = 0; sub < VR_SUBSTEPS; ++sub) {
+            const bool can = stage == SG_STEP && !collide && t < tfar;
+            if (sub > 0 && __popc(__ballot_sync(FULL, can)) < VR_SUBSTEP_MIN) break;
+            if (can) {
                 const float3 curr = ipos + t * idir;
                 const int m = round_mip(mip);
                 cnt.maj();
@@ -106,6 +120,8 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 }
                 if (++steps > MAX_RAY_STEPS) { t = INFINITY; collide = false; }
             }
+        }
+        if (stage == SG_STEP) {
             if (collide) {   // common.glsl:436-452 / 483-498
                 cnt.dens();
                 const float3 at = ipos + t * idir;
@@ -167,9 +183,10 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         const unsigned m_fin = __ballot_sync(FULL, stage == SG_FINISH);
         if ((m_step | m_nee | m_scat | m_fin) == 0u) break;     // every lane idle
         const int n_step = __popc(m_step), n_nee = __popc(m_nee), n_scat = __popc(m_scat), n_fin = __popc(m_fin);
-        bool run_nee = n_nee >= VR_K_NEE, run_scat = n_scat >= VR_K_SCATTER, run_fin = n_fin >= VR_K_FINISH;
+        constexpr int K = TF ? VR_K_EVENT_TF : VR_K_EVENT, MIN_STEP = TF ? VR_MIN_STEP_TF : VR_MIN_STEP;
+        bool run_nee = n_nee >= K, run_scat = n_scat >= K, run_fin = n_fin >= K;
         if (!(run_nee | run_scat | run_fin)) {
-            if (n_step >= VR_MIN_STEP) continue;               // keep stepping
+            if (n_step >= MIN_STEP) continue;                  // keep stepping
             // too few lanes can step: drain the fullest queue
             if (n_nee >= n_scat && n_nee >= n_fin) run_nee = n_nee > 0;
             else if (n_scat >= n_fin) run_scat = n_scat > 0;
