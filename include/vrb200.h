@@ -116,8 +116,9 @@ void vrb_destroy(vrb_ctx* ctx);
 const char* vrb_last_error(vrb_ctx* ctx);
 const char* vrb_status_string(int status);
 int vrb_abi_version(void);
-/* run all work of this context on an existing cudaStream_t (e.g. torch's current stream); NULL = own stream */
-int vrb_set_stream(vrb_ctx* ctx, void* cuda_stream);
+/* external != 0: run all work of this context on the given cudaStream_t (NULL = the legacy default stream, which is
+ * what torch.cuda.current_stream() is unless changed); external == 0: back to the context's own non-blocking stream */
+int vrb_set_stream(vrb_ctx* ctx, void* cuda_stream, int external);
 int vrb_sync(vrb_ctx* ctx);
 /* replaces RendererOpenGL::resize / the RGBA32F `color` texture (src/renderer.cpp:46-54); zero-fills */
 int vrb_resize(vrb_ctx* ctx, int w, int h);

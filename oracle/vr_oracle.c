@@ -63,6 +63,15 @@ static inline float luma(v3 c) { return dot3(c, V3(0.212671f, 0.715160f, 0.07216
 static inline float sanitize1(float x) { return (isnan(x) || isinf(x)) ? 0.f : x; }     /* :17-19 */
 static inline float saturate(float x) { return gl_clamp(x, 0.f, 1.f); }                 /* :23 */
 static inline float power_heuristic(float a, float b) { return sqr(a) / (sqr(a) + sqr(b)); } /* :35 */
+/* float -> int as the GPU does it (saturating, NaN -> 0). GLSL leaves out-of-range conversions undefined and the
+ * reference reaches them: rng() == 0 with a zero majorant gives t = 0/0 (common.glsl:434/481), after which lookups
+ * run on NaN positions; robust texel/buffer access makes that harmless on a GPU, a plain C cast would index wildly. */
+static inline int f2i(float x) {
+    if (isnan(x)) return 0;
+    if (x >= 2147483648.f) return 2147483647;
+    if (x <= -2147483648.f) return -2147483647 - 1;
+    return (int)x;
+}
 
 /* column-major mat3 * vec3, mat4 * vec4 */
 static inline v3 m3mul(const float* m, v3 v) {
@@ -319,8 +328,8 @@ static v3 env_texture(const float* rgb, int w, int h, float u, float v) { /* tex
     const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
     const float fx = floorf(x), fy = floorf(y);
     const float ax = x - fx, ay = y - fy;
-    const int x0 = wrap_repeat((int)fx, w), y0 = wrap_repeat((int)fy, h);
-    const int x1 = wrap_repeat((int)fx + 1, w), y1 = wrap_repeat((int)fy + 1, h);
+    const int x0 = wrap_repeat(f2i(fx), w), y0 = wrap_repeat(f2i(fy), h);
+    const int x1 = wrap_repeat(x0 + 1, w), y1 = wrap_repeat(y0 + 1, h);
     const float* t00 = rgb + ((size_t)y0 * w + x0) * 3;
     const float* t10 = rgb + ((size_t)y0 * w + x1) * 3;
     const float* t01 = rgb + ((size_t)y1 * w + x0) * 3;
@@ -458,7 +467,7 @@ static v4 tf_lookup(const tctx* c, float d) {
     const float tc = gl_clamp((d - c->p->tf_window_left) / c->p->tf_window_width, 0.0f, 1.0f - 1e-6f);
     const uint32_t n = c->sc->tf_size;
     const float s = tc * (float)n;
-    const int idx = (int)floorf(s);
+    const int idx = f2i(floorf(s));
     const float f = gl_fract(s);
     uint32_t idx1 = (uint32_t)(idx + 1);
     if (idx1 > n - 1) idx1 = n - 1;
@@ -471,7 +480,7 @@ static v4 tf_lookup(const tctx* c, float d) {
 /* common.glsl:221-244 */
 static i3 stochastic_tricubic_filter(v3 ipos, uint32_t* seed) {
     const v3 q = V3(ipos.x - 0.5f, ipos.y - 0.5f, ipos.z - 0.5f);
-    const i3 ii = { (int)floorf(q.x), (int)floorf(q.y), (int)floorf(q.z) };
+    const i3 ii = { f2i(floorf(q.x)), f2i(floorf(q.y)), f2i(floorf(q.z)) };
     const float t[3] = { q.x - (float)ii.x, q.y - (float)ii.y, q.z - (float)ii.z };
     int idx[3] = { 0, 0, 0 };
     float sum[3], w[3], t2[3];
@@ -524,14 +533,14 @@ static float lookup_brick_value(const vro_grid* g, i3 ii) {
 static float lookup_majorant(tctx* c, v3 ipos, int mip) {
     c->n_maj++;
     const vro_grid* g = &c->sc->density;
-    const int bx = (int)floorf(ipos.x) >> (3 + mip), by = (int)floorf(ipos.y) >> (3 + mip), bz = (int)floorf(ipos.z) >> (3 + mip);
+    const int bx = f2i(floorf(ipos.x)) >> (3 + mip), by = f2i(floorf(ipos.y)) >> (3 + mip), bz = f2i(floorf(ipos.z)) >> (3 + mip);
     size_t bi;
     if (!brick_index(g, bx, by, bz, mip, &bi)) return c->p->vol_density_scale * 0.f;
     const uint32_t rw = mip == 0 ? g->range[bi] : g->range_mips[mip - 1][bi];
     return c->p->vol_density_scale * vro_from_half((uint16_t)(rw >> 16));
 }
 
-static inline i3 floor3(v3 p) { i3 r = { (int)floorf(p.x), (int)floorf(p.y), (int)floorf(p.z) }; return r; }
+static inline i3 floor3(v3 p) { i3 r = { f2i(floorf(p.x)), f2i(floorf(p.y)), f2i(floorf(p.z)) }; return r; }
 
 /* common.glsl:289-297 */
 static float lookup_density_trilinear(tctx* c, v3 ipos) {

@@ -96,7 +96,7 @@ def load_library(path: str = LIB_PATH):
     L.vrb_last_error.restype = C.c_char_p
     L.vrb_status_string.argtypes = [ci]
     L.vrb_status_string.restype = C.c_char_p
-    L.vrb_set_stream.argtypes = [vp, vp]
+    L.vrb_set_stream.argtypes = [vp, vp, ci]
     L.vrb_sync.argtypes = [vp]
     L.vrb_resize.argtypes = [vp, ci, ci]
     L.vrb_grid_clear.argtypes = [vp]
@@ -158,8 +158,8 @@ class Context:
             raise VrbError(st, self.lib.vrb_last_error(self.handle).decode())
 
     # --- plumbing ---
-    def set_stream(self, cuda_stream_ptr):
-        self._ck(self.lib.vrb_set_stream(self.handle, cuda_stream_ptr))
+    def set_stream(self, cuda_stream_ptr, external=True):
+        self._ck(self.lib.vrb_set_stream(self.handle, cuda_stream_ptr, int(external)))
 
     def sync(self):
         self._ck(self.lib.vrb_sync(self.handle))

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 mip = fminf(mip + 0.25f, 3.f);
                 if (!(tau > 0.f)) {
                     t += MT::div(tau, majorant);
-                    collide = t < tfar;
+                    collide = !(t >= tfar);   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
                 }
                 if (++steps > MAX_RAY_STEPS) { t = INFINITY; collide = false; }
             }

@@ -325,11 +325,11 @@ void vrb_destroy(vrb_ctx* ctx) {
 
 const char* vrb_last_error(vrb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-int vrb_set_stream(vrb_ctx* ctx, void* cuda_stream) {
+int vrb_set_stream(vrb_ctx* ctx, void* cuda_stream, int external) {
     if (!ctx) return VRB_ERR_INVALID;
     DeviceGuard guard(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stream = cuda_stream ? cudaStream_t(cuda_stream) : ctx->own_stream;
+    ctx->stream = external ? cudaStream_t(cuda_stream) : ctx->own_stream;   // external + NULL = the legacy default stream
     return VRB_OK;
 }
 
