@@ -126,6 +126,8 @@ int vrb_resize(vrb_ctx* ctx, int w, int h);
 /* ---- volume data (src/renderer.cpp:56-76 commit, :159-225 brick_grid_to_textures) --------------- */
 /* commit() starts with density_grids.clear(); emission_grids.clear() (renderer.cpp:57-58) */
 int vrb_grid_clear(vrb_ctx* ctx);
+/* release one grid (frees its device memory); no-op if absent */
+int vrb_grid_free(vrb_ctx* ctx, int slot, int frame);
 /* upload an existing BrickGrid verbatim (a loaded .brick file) */
 int vrb_grid_upload_brick(vrb_ctx* ctx, int slot, int frame, const vrb_brick_view* grid);
 /* voldata::BrickGrid::BrickGrid(const Grid&) for a DenseGrid source (voldata/src/grid_brick.cpp:60-142,
@@ -199,6 +201,9 @@ int vrb_bind_color(vrb_ctx* ctx, void* device_rgba32f);
  * over peer-to-peer NVLink copies + an add kernel. One-process-per-GPU runs use NCCL on
  * vrb_color_device_ptr instead (bench.py). */
 int vrb_reduce(vrb_ctx* const* ctxs, int n, int root);
+/* tile-partitioned rendering: copy image rows [y0, y1) of src's colour buffer into dst's (peer-to-peer when the
+ * contexts live on different devices); both must have the same resolution */
+int vrb_copy_rows(vrb_ctx* dst, vrb_ctx* src, int y0, int y1);
 
 #ifdef __cplusplus
 }

@@ -18,11 +18,11 @@ ACCUM_MEAN, ACCUM_SUM = 0, 1
 # every symbol include/vrb200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "vrb_create", "vrb_destroy", "vrb_last_error", "vrb_status_string", "vrb_abi_version", "vrb_set_stream", "vrb_sync",
-    "vrb_resize", "vrb_grid_clear", "vrb_grid_upload_brick", "vrb_grid_build_from_dense",
+    "vrb_resize", "vrb_grid_clear", "vrb_grid_free", "vrb_grid_upload_brick", "vrb_grid_build_from_dense",
     "vrb_grid_build_from_dense_device", "vrb_grid_info", "vrb_grid_download", "vrb_dense_from_float",
     "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_scale",
     "vrb_clear", "vrb_set_counting", "vrb_get_counters", "vrb_tonemap", "vrb_download_color", "vrb_download_color_ldr",
-    "vrb_download_framebuffer", "vrb_upload_color", "vrb_color_device_ptr", "vrb_bind_color", "vrb_reduce",
+    "vrb_download_framebuffer", "vrb_upload_color", "vrb_color_device_ptr", "vrb_bind_color", "vrb_reduce", "vrb_copy_rows",
 ]
 
 
@@ -100,6 +100,7 @@ def load_library(path: str = LIB_PATH):
     L.vrb_sync.argtypes = [vp]
     L.vrb_resize.argtypes = [vp, ci, ci]
     L.vrb_grid_clear.argtypes = [vp]
+    L.vrb_grid_free.argtypes = [vp, ci, ci]
     L.vrb_grid_upload_brick.argtypes = [vp, ci, ci, C.POINTER(BrickView)]
     L.vrb_grid_build_from_dense.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3, cf, cf]
     L.vrb_grid_build_from_dense_device.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3, cf, cf]
@@ -125,6 +126,7 @@ def load_library(path: str = LIB_PATH):
     L.vrb_color_device_ptr.restype = vp
     L.vrb_bind_color.argtypes = [vp, vp]
     L.vrb_reduce.argtypes = [C.POINTER(vp), ci, ci]
+    L.vrb_copy_rows.argtypes = [vp, vp, ci, ci]
     _lib = L
     return L
 
@@ -171,6 +173,9 @@ class Context:
     # --- volume ---
     def grid_clear(self):
         self._ck(self.lib.vrb_grid_clear(self.handle))
+
+    def grid_free(self, slot=SLOT_DENSITY, frame=0):
+        self._ck(self.lib.vrb_grid_free(self.handle, slot, frame))
 
     def grid_upload_brick(self, grid, slot=SLOT_DENSITY, frame=0):
         """grid: any object with n_bricks, atlas_dim, brick_count, indirection, range, atlas, mips (numpy)."""

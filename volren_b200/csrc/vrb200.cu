@@ -378,6 +378,18 @@ int vrb_grid_clear(vrb_ctx* ctx) {
     return VRB_OK;
 }
 
+int vrb_grid_free(vrb_ctx* ctx, int slot, int frame) {
+    int st = check_slot_frame(ctx, slot, frame);
+    if (st) return st;
+    auto it = ctx->frames.find(frame);
+    if (it == ctx->frames.end()) return VRB_OK;
+    DeviceGuard guard(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_grid(it->second.slot[slot]);
+    if (!it->second.slot[0].valid && !it->second.slot[1].valid) ctx->frames.erase(it);
+    return VRB_OK;
+}
+
 int vrb_grid_upload_brick(vrb_ctx* ctx, int slot, int frame, const vrb_brick_view* v) {
     int st = check_slot_frame(ctx, slot, frame);
     if (st) return st;
@@ -763,6 +775,20 @@ int vrb_reduce(vrb_ctx* const* ctxs, int n, int root) {
     }
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(staging);
+    return VRB_OK;
+}
+
+int vrb_copy_rows(vrb_ctx* dst, vrb_ctx* src, int y0, int y1) {
+    if (!dst || !src) return VRB_ERR_INVALID;
+    vrb_ctx* ctx = dst;
+    if (!dst->color || !src->color || dst->w != src->w || dst->h != src->h) return fail(ctx, VRB_ERR_INVALID, "contexts do not share a resolution");
+    if (y0 < 0 || y1 > dst->h || y0 >= y1) return fail(ctx, VRB_ERR_INVALID, "bad row range [%d, %d)", y0, y1);
+    { DeviceGuard g2(src->device); cudaStreamSynchronize(src->stream); }
+    DeviceGuard guard(dst->device);
+    const size_t off = size_t(y0) * dst->w, bytes = size_t(y1 - y0) * dst->w * sizeof(float4);
+    if (dst->device == src->device) CK(cudaMemcpyAsync(dst->color + off, src->color + off, bytes, cudaMemcpyDeviceToDevice, dst->stream));
+    else CK(cudaMemcpyPeerAsync(dst->color + off, dst->device, src->color + off, src->device, bytes, dst->stream));
+    CK(cudaStreamSynchronize(dst->stream));
     return VRB_OK;
 }
 
