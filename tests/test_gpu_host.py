@@ -67,6 +67,8 @@ def test_uniform_marshalling_matches_python_scene(volpy, smoke_grid):
     r = _readme_renderer(volpy, W, H)
     got, want = _params_of(r), readme_scene(smoke_grid, W, H)
     for name, ctype in got._fields_:
+        if name.startswith("tf_window") and not got.use_transferfunc:
+            continue                      # unset GL uniforms without a transfer function (renderer.cpp:125)
         a, b = getattr(got, name), getattr(want, name)
         if isinstance(a, ctypes.Array):
             a, b = np.array(a[:], np.float64), np.array(b[:], np.float64)
