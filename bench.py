@@ -37,15 +37,19 @@ METRIC = "path samples/sec (1080p, 128 bounces)"
 UNIT = "samples/s"
 
 
-def load_workload():
+def load_workload(w=W, h=H):
     from volren_b200 import formats
     from helpers import default_scene
     grid = formats.load_brick(os.path.join(ASSETS, "smoke.brick"))
     env = formats.load_hdr(os.path.join(ASSETS, "table_mountain_2_puresky_1k.hdr"))
     lut = formats.lut_for_upload(formats.load_lut_txt(os.path.join(ASSETS, "lut.txt")))
     # `./volren data/smoke.brick <hdr> data/lut.txt -w 1920 -h 1080 --render --bounces 128`
-    params = default_scene(grid, W, H, bounces=BOUNCES, use_tf=True)
+    params = default_scene(grid, w, h, bounces=BOUNCES, use_tf=True)
     return grid, env, lut, params
+
+
+# CPU legs: the SAME frame (camera, fov, aspect -> the same mix of empty and dense pixels) at 1/4 resolution per axis
+CPU_W, CPU_H = W // 4, H // 4
 
 
 def algorithmic_bytes(c: dict, use_tf: bool) -> float:
@@ -116,28 +120,26 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle.binding import Oracle
-    grid, env, lut, params = load_workload()
+    grid, env, lut, params = load_workload(CPU_W, CPU_H)
     o = Oracle()
     pyr = o.env_build(env)
     sc = o.make_scene(grid, env, pyr, lut=lut)
     cores = o.max_threads()
-    # bounded sample: a centred crop of the 1080p image at 1 spp per step, sized for ~3 s per step
-    cw, ch = 480, 270
-    tile = ((W - cw) // 2, (H - ch) // 2, (W + cw) // 2, (H + ch) // 2)
-    color = np.zeros((H, W, 4), np.float32)
+    # bounded sample: the whole frame at 480x270, spp per step sized for ~3 s per step
+    color = np.zeros((CPU_H, CPU_W, 4), np.float32)
     t0 = time.perf_counter()
-    o.trace(sc, params, 1, 1, color=color, tile=tile)
+    o.trace(sc, params, 1, 1, color=color)
     probe = time.perf_counter() - t0
     spp = max(1, int(3.0 / max(probe, 1e-3)))
     for i in range(args.warmup):
-        o.trace(sc, params, 1 + i, 1, color=color, tile=tile)
+        o.trace(sc, params, 1 + i, 1, color=color)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        o.trace(sc, params, 1 + k * spp, spp, color=color, tile=tile)
+        o.trace(sc, params, 1 + k * spp, spp, color=color)
     dt = time.perf_counter() - t0
-    samples = cw * ch * spp * args.steps
+    samples = CPU_W * CPU_H * spp * args.steps
     v = samples / dt
-    sample = f"{cw}x{ch} centre crop of the 1080p frame, {spp} spp per step, {args.steps} steps"
+    sample = f"the 1080p frame rendered at {CPU_W}x{CPU_H} (same camera), {spp} spp per step, {args.steps} steps"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -151,22 +153,20 @@ def run_reference(args, rank, world):
 def cpu_baseline_worker():
     """cpu_baseline leg: the oracle (port of the reference shaders) on a bounded sample of the bench workload."""
     from oracle.binding import Oracle
-    grid, env, lut, params = load_workload()
+    grid, env, lut, params = load_workload(CPU_W, CPU_H)
     o = Oracle()
     pyr = o.env_build(env)
     sc = o.make_scene(grid, env, pyr, lut=lut)
-    cw, ch = 480, 270
-    tile = ((W - cw) // 2, (H - ch) // 2, (W + cw) // 2, (H + ch) // 2)
-    img = np.zeros((H, W, 4), np.float32)
+    img = np.zeros((CPU_H, CPU_W, 4), np.float32)
     t0 = time.perf_counter()
-    o.trace(sc, params, 1, 1, color=img, tile=tile)
+    o.trace(sc, params, 1, 1, color=img)
     probe = time.perf_counter() - t0
     spp = max(1, int(12.0 / max(probe, 1e-3)))
     t0 = time.perf_counter()
-    o.trace(sc, params, 2, spp, color=img, tile=tile)
+    o.trace(sc, params, 2, spp, color=img)
     dt = time.perf_counter() - t0
-    print(json.dumps({"value": cw * ch * spp / dt, "unit": UNIT, "cores": o.max_threads(), "kind": "port",
-                      "sample": f"{cw}x{ch} centre crop of the 1080p frame, {spp} spp (oracle/vr_oracle.c, OpenMP)"}))
+    print(json.dumps({"value": CPU_W * CPU_H * spp / dt, "unit": UNIT, "cores": o.max_threads(), "kind": "port",
+                      "sample": f"the 1080p frame rendered at {CPU_W}x{CPU_H} (same camera), {spp} spp (oracle/vr_oracle.c, OpenMP)"}))
 
 
 def main():
@@ -219,14 +219,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(k):
-        """one step: this rank's spp slice for all pixels, then the accumulation-buffer reduce"""
-        first = 1 + (k * world + rank) * S
-        if world > 1:
-            ctx.trace(params, first, S, accum_mode=vr._capi.ACCUM_SUM)
-            dist.reduce(color, dst=0, op=dist.ReduceOp.SUM)
-        else:
-            ctx.trace(params, first, S)
+    from volren_b200.multigpu import PartitionedRenderer
+    kev_cur = [None]
+
+    def trace_fn(first, n, tile, accum):
+        if kev_cur[0] is not None:
+            kev_cur[0][0].record()
+        ctx.trace(params, first, n, tile=tile, accum_mode=accum)
+        if kev_cur[0] is not None:
+            kev_cur[0][1].record()
+
+    # spp slices: rank r traces S of the S*world samples of a step into a SUM buffer, one NCCL reduce(SUM) to rank 0
+    pr = PartitionedRenderer(color, trace_fn, partition="spp")
+
+    def step():
+        """one step: S samples per pixel on every rank (weak scaling), then the accumulation-buffer reduce"""
+        pr.render(S * world)
 
     # ---- counting pass (defines the algorithmic bytes of one launch) ----
     ctx.set_counting(True)
@@ -236,9 +244,9 @@ def main():
     alg_bytes = algorithmic_bytes(counters, use_tf=True)
 
     # ---- device-resident throughput ----
-    color.zero_()
+    pr.reset()
     for i in range(args.warmup):
-        step(i)
+        step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -248,14 +256,11 @@ def main():
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                   # L2 flush between timed iterations (not timed)
         barrier()
+        kev_cur[0] = kev[k]
         ev[k][0].record()
-        first = 1 + ((args.warmup + k) * world + rank) * S
-        kev[k][0].record()
-        ctx.trace(params, first, S, accum_mode=vr._capi.ACCUM_SUM if world > 1 else vr._capi.ACCUM_MEAN)
-        kev[k][1].record()
-        if world > 1:
-            dist.reduce(color, dst=0, op=dist.ReduceOp.SUM)
+        step()
         ev[k][1].record()
+        kev_cur[0] = None
         barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -276,12 +281,7 @@ def main():
         ctx.grid_upload_brick(grid)             # host -> device: indirection, range, atlas, mips
         ctx.env_upload(env)                     # host -> device + importance pyramid rebuild
         ctx.tf_upload(lut)
-        first = 1 + (k * world + rank) * S
-        if world > 1:
-            ctx.trace(params, first, S, accum_mode=vr._capi.ACCUM_SUM)
-            dist.reduce(color, dst=0, op=dist.ReduceOp.SUM)
-        else:
-            ctx.trace(params, first, S)
+        step()
         if rank == 0:
             ctx.lib.vrb_download_color(ctx.handle, host_img.ctypes.data, 4)   # device -> host (blocks)
         else:

@@ -1,0 +1,95 @@
+"""Multi-GPU rendering, one process per GPU (torch.distributed): the scene is replicated on every rank, the work is
+split by spp slice or by image tile and the RGBA32F accumulation buffers are combined with ONE
+collective per batch -- `reduce(SUM)` over NCCL/NVLink on GPUs, gloo in the CPU tests. Every (pixel, sample) depends only
+on (seed, pixel, W, sample index, scene) (reference shader/pathtracer_brick.glsl:28), so no other exchange exists.
+
+The tracer is injected (`trace_fn`): on a GPU box it is `Context.trace` rendering into the bound colour tensor; the
+CPU tests inject the oracle so that the partition / reduction logic is exercised without a device.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+ACCUM_MEAN, ACCUM_SUM = 0, 1
+
+
+def spp_slices(first_sample: int, n_samples: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous slices of the 1-based sample range [first, first + n) for each rank: (first_r, n_r), sum n_r == n."""
+    if first_sample < 1 or n_samples < 0 or world < 1:
+        raise ValueError("bad sample range / world size")
+    out, s = [], first_sample
+    for r in range(world):
+        n = n_samples * (r + 1) // world - n_samples * r // world
+        out.append((s, n))
+        s += n
+    return out
+
+
+def row_bands(height: int, world: int, align: int = 4) -> List[Tuple[int, int]]:
+    """`align`-row-aligned bands [y0, y1) per rank (the tracer walks 8x4 pixel tiles); bands tile [0, height) exactly."""
+    if height < 1 or world < 1:
+        raise ValueError("bad height / world size")
+    units = (height + align - 1) // align
+    return [(min(height, units * r // world * align), min(height, units * (r + 1) // world * align)) for r in range(world)]
+
+
+class PartitionedRenderer:
+    """Renders batches of samples across the ranks of a process group into `color` (a (H, W, 4) float32 torch tensor on
+    this rank's device). After `render`, rank `dst` holds the finished MEAN image of all samples rendered since `reset`.
+
+    trace_fn(first_sample, n_samples, tile, accum_mode) must fold the samples into `color` in place:
+      accum_mode == ACCUM_SUM : color[tile] += sum of L;  ACCUM_MEAN: reference running mean over sample indices.
+    """
+
+    def __init__(self, color, trace_fn: Callable[[int, int, Optional[Sequence[int]], int], None], partition: str = "spp", group=None, dst: int = 0):
+        import torch.distributed as dist
+        if partition not in ("spp", "tile"):
+            raise ValueError("partition must be 'spp' or 'tile'")
+        self.color, self.trace_fn, self.partition, self.group, self.dst = color, trace_fn, partition, group, dst
+        self.dist = dist
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.samples = 0
+
+    def reset(self):
+        self.samples = 0
+        self.color.zero_()
+
+    def render(self, n_samples: int):
+        """n more samples per pixel (job-wide). Returns the work this rank did: (first, n) or (y0, y1)."""
+        H, W = int(self.color.shape[0]), int(self.color.shape[1])
+        first = self.samples + 1
+        if self.world == 1:
+            self.trace_fn(first, n_samples, None, ACCUM_MEAN)
+            self.samples += n_samples
+            return (first, n_samples)
+        if self.partition == "spp":
+            # every rank keeps a running SUM of its own slices; rank dst's buffer doubles as the reduction target, so its
+            # mean of the previous batches is turned back into a sum first
+            if self.rank == self.dst and self.samples > 0:
+                self.color.mul_(float(self.samples))
+            elif self.rank != self.dst:
+                self.color.zero_()
+            mine = spp_slices(first, n_samples, self.world)[self.rank]
+            if mine[1] > 0:
+                self.trace_fn(mine[0], mine[1], None, ACCUM_SUM)
+            self.dist.reduce(self.color, dst=self.dst, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.samples += n_samples
+            if self.rank == self.dst:
+                self.color.mul_(1.0 / float(self.samples))
+            return mine
+        # tiles: every rank owns a band of rows and keeps the reference running mean there; rows outside the band are
+        # zero, so the SUM reduction assembles the image exactly (x + 0 == x)
+        y0, y1 = row_bands(H, self.world)[self.rank]
+        if self.samples > 0:     # rows that are not this rank's own (gathered or scratch) must not enter the next sum
+            self.color[:y0].zero_()
+            self.color[y1:].zero_()
+        if y0 < y1:
+            self.trace_fn(first, n_samples, (0, y0, W, y1), ACCUM_MEAN)
+        keep = self.color[y0:y1].clone() if self.rank != self.dst else None
+        self.dist.reduce(self.color, dst=self.dst, op=self.dist.ReduceOp.SUM, group=self.group)
+        if keep is not None:     # reduce() may scribble partial sums into non-destination buffers (gloo does)
+            self.color.zero_()
+            self.color[y0:y1] = keep
+        self.samples += n_samples
+        return (y0, y1)
