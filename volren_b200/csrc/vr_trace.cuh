@@ -41,7 +41,9 @@ struct GridView {
     uint3 nb;                  // n_bricks (level 0)
     const uint2* rec;          // {atlas slot, range word} per brick
     const uint32_t* mips[3];   // range words of levels 1..3 (dims nb >> level)
-    const uint8_t* atlas_lin;  // slot * 512 + z*64 + y*8 + x
+    const uint8_t* atlas_lin;  // slot * 512 + z*64 + y*8 + x  (+ one all-zero brick behind the last slot)
+    const uint2* recp;         // records padded by one brick per side: ((bz+1) * (nby+2) + (by+1)) * (nbx+2) + (bx+1)
+    uint32_t psx, psxy;        // strides of recp: nbx + 2, (nbx + 2) * (nby + 2)
 };
 
 struct TraceArgs {
@@ -165,43 +167,39 @@ VR_DEV float tf_lookup_alpha(const TraceArgs& a, float d) {
     return mixf(__ldg(&a.lut[idx].w), __ldg(&a.lut[idx1].w), f);
 }
 
-// lookup_density_trilinear (common.glsl:289-297) without density_scale. When the 2x2x2 footprint lies inside one
-// brick (67 % of the positions) the eight taps share one record and come from four 8-byte rows of the
-// brick-linear atlas; otherwise the four x-pairs are fetched in a rolled loop (code size).
+// lookup_density_trilinear (common.glsl:289-297) without density_scale: eight nearest decodes at ipos - 0.5.
+// Branch-free: the footprint touches at most two bricks per axis; every tap reads its record from the padded record
+// array (border / out-of-atlas entries point at an all-zero brick with range 0, i.e. texelFetch out of bounds -> 0)
+// and its byte from the brick-linear atlas. All lanes of a warp run the same ~170 instructions whether or not the
+// footprint straddles bricks (the previous in-brick fast path + rolled slow path cost ~600 issue slots per collision
+// event because almost every warp had lanes in both, profiles/r01_v3_trace_tf_lines.txt).
 VR_DEV float density_trilinear(const GridView& g, float3 ipos) {
     const float qx = ipos.x - 0.5f, qy = ipos.y - 0.5f, qz = ipos.z - 0.5f;
     const float flx = floorf(qx), fly = floorf(qy), flz = floorf(qz);
     const float fx = qx - flx, fy = qy - fly, fz = qz - flz;
     const int x = int(flx), y = int(fly), z = int(flz);
-    const int lx = x & 7, ly = y & 7, lz = z & 7;
     const int bx = x >> 3, by = y >> 3, bz = z >> 3;
-    if (lx < 7 && ly < 7 && lz < 7 && unsigned(bx) < g.nb.x && unsigned(by) < g.nb.y && unsigned(bz) < g.nb.z) {
-        const uint2 r = __ldg(g.rec + (size_t(bz) * g.nb.y + by) * g.nb.x + bx);
-        const float lo = range_lo(r.y), span = range_hi(r.y) - lo;
-        uint32_t b00 = 0, b10 = 0, b01 = 0, b11 = 0;
-        if (r.x != 0xffffffffu) {
-            const uint2* rows = reinterpret_cast<const uint2*>(g.atlas_lin + size_t(r.x) * 512u) + (lz * 8 + ly);
-            const uint2 r00 = __ldg(rows), r10 = __ldg(rows + 1), r01 = __ldg(rows + 8), r11 = __ldg(rows + 9);
-            const int sh = lx * 8;
-            b00 = uint32_t((((unsigned long long)r00.y << 32) | r00.x) >> sh); b10 = uint32_t((((unsigned long long)r10.y << 32) | r10.x) >> sh);
-            b01 = uint32_t((((unsigned long long)r01.y << 32) | r01.x) >> sh); b11 = uint32_t((((unsigned long long)r11.y << 32) | r11.x) >> sh);
-        }
-        const float lx0 = mixf(lo + unorm8_to_float(b00 & 255u) * span, lo + unorm8_to_float((b00 >> 8) & 255u) * span, fx);
-        const float lx1 = mixf(lo + unorm8_to_float(b10 & 255u) * span, lo + unorm8_to_float((b10 >> 8) & 255u) * span, fx);
-        const float hx0 = mixf(lo + unorm8_to_float(b01 & 255u) * span, lo + unorm8_to_float((b01 >> 8) & 255u) * span, fx);
-        const float hx1 = mixf(lo + unorm8_to_float(b11 & 255u) * span, lo + unorm8_to_float((b11 >> 8) & 255u) * span, fx);
-        return mixf(mixf(lx0, lx1, fy), mixf(hx0, hx1, fy), fz);
-    }
-    float lo_z = 0.f, prev = 0.f, out = 0.f;
-#pragma unroll 1
+    // base brick in [-1, nb - 1]: otherwise all eight taps are outside the grid
+    if (unsigned(bx + 1) > g.nb.x || unsigned(by + 1) > g.nb.y || unsigned(bz + 1) > g.nb.z) return 0.f;
+    const uint32_t lx = x & 7, ly = y & 7, lz = z & 7;
+    const uint32_t sx = lx == 7u, sy = ly == 7u ? g.psx : 0u, sz = lz == 7u ? g.psxy : 0u;   // record strides taken by the +1 taps
+    const uint32_t base = uint32_t(bz + 1) * g.psxy + uint32_t(by + 1) * g.psx + uint32_t(bx + 1);
+    const uint32_t lx1 = (lx + 1u) & 7u;
+    float row[4];
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int yy = y + (k & 1), zz = z + (k >> 1);
-        const float row = mixf(brick_value(g, x, yy, zz), brick_value(g, x + 1, yy, zz), fx);
-        if (k == 1) lo_z = mixf(prev, row, fy);
-        if (k == 3) out = mixf(lo_z, mixf(prev, row, fy), fz);
-        prev = row;
+        const uint32_t dy = k & 1, dz = k >> 1;
+        const uint32_t ridx = base + (dy ? sy : 0u) + (dz ? sz : 0u);
+        const uint2 ra = __ldg(g.recp + ridx), rb = __ldg(g.recp + ridx + sx);
+        const uint32_t voff = (((lz + dz) & 7u) << 6) | (((ly + dy) & 7u) << 3);
+        const uint32_t a = __ldg(g.atlas_lin + size_t(ra.x) * 512u + (voff | lx));
+        const uint32_t b = __ldg(g.atlas_lin + size_t(rb.x) * 512u + (voff | lx1));
+        const float loa = range_lo(ra.y), lob = range_lo(rb.y);
+        const float va = loa + unorm8_to_float(a) * (range_hi(ra.y) - loa);
+        const float vb = lob + unorm8_to_float(b) * (range_hi(rb.y) - lob);
+        row[k] = mixf(va, vb, fx);
     }
-    return out;
+    return mixf(mixf(row[0], row[1], fy), mixf(row[2], row[3], fy), fz);
 }
 
 // lookup_emission (common.glsl:324-328). Without an emission grid the samplers are unbound (value 0) but the
@@ -271,8 +269,7 @@ VR_DEV float3 sample_phase_hg(float3 dir, float g, float s0, float s1) {  // com
 // bilinear REPEAT fetch with a cheap wrap (uv in [-1, 2] never needs the integer modulo)
 VR_DEV int wrap_fast(int i, int n) {
     if (i < 0) i += n; else if (i >= n) i -= n;
-    while (i < 0) i += n;        // only for |uv| > 2: never taken by the tracer's own lookups
-    while (i >= n) i -= n;
+    if (unsigned(i) >= unsigned(n)) { i %= n; if (i < 0) i += n; }   // only for |uv| > 2: never taken by the tracer's own lookups
     return i;
 }
 VR_DEV float3 env_texture_fw(const EnvView& e, float u, float v) {

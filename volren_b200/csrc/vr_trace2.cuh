@@ -7,11 +7,11 @@
 //     a global ticket when it is done -> no tail of idle SMs behind the few long pixels;
 //   * camera segments and shadow rays share ONE brick-DDA loop body (common.glsl:412-501 differ only in what
 //     happens at a collision), so a warp's lanes step convergently whatever kind of ray they are on;
-//   * path events are scheduled wavefront-style INSIDE the warp: a lane whose ray ended parks in one of three
-//     queues (NEE / SCATTER / FINISH); a queue's stage runs when enough lanes wait in it (or nothing else can
-//     make progress), so the heavy, rare stages (importance-pyramid warp, phase sampling, escape lookup + TEA
-//     reseed) execute with many active lanes instead of one or two; every new ray (camera, shadow, scattered)
-//     is started at ONE shared site after the stages;
+//   * path events are scheduled wavefront-style INSIDE the warp: a lane whose ray hit a tentative collision or ended
+//     parks in one of four queues (COLLIDE / NEE / SCATTER / FINISH); a queue's stage runs when enough lanes wait
+//     in it (or nothing else can make progress), so the heavy stages (8-tap trilinear + LUT collision test,
+//     importance-pyramid warp, phase sampling, escape lookup + TEA reseed) execute with many active lanes
+//     instead of a few; every new ray (camera, shadow, scattered) is started at ONE shared site after the stages;
 //   * per-level majorants are read from float tables precomputed per (grid, params) with the identical
 //     expression (the TF variant otherwise evaluates a LUT lerp and a divide on every DDA step);
 //   * MT = FastMath in production (MUFU rcp/rsqrt/lg2/sin/cos): 3x less SASS than the IEEE sequences, which
@@ -23,7 +23,7 @@
 namespace vr {
 
 // lane stages
-enum : int { SG_STEP = 0, SG_NEE = 1, SG_SCATTER = 2, SG_FINISH = 3, SG_IDLE = 4 };
+enum : int { SG_STEP = 0, SG_COLLIDE = 1, SG_NEE = 2, SG_SCATTER = 3, SG_FINISH = 4, SG_IDLE = 5 };
 
 // fills one level of the majorant table: exactly majorant_at() of vr_trace.cuh, hoisted out of the DDA loop
 template <bool TF>
@@ -52,23 +52,23 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #ifndef VR_TRACE_MIN_BLOCKS
 #define VR_TRACE_MIN_BLOCKS 6
 #endif
-// Queue thresholds, tuned on B200 (tools/sweep.py, profiles/r01_sweep.txt): the TF variant has cheap events and an
-// expensive 8-tap collision -> drain queues early (4); the non-TF variant prefers fuller queues (8) and keeps
-// stepping only while at least 16 lanes can.
+// Queue thresholds, tuned on B200 (tools/sweep.py, profiles/r01_sweep*.txt): a queue's stage runs once this many lanes
+// wait in it. The TF variant has cheap events and an expensive 8-tap collision; the non-TF variant a cheap 1-tap
+// collision and relatively expensive events.
 #ifndef VR_K_EVENT_TF
 #define VR_K_EVENT_TF 4
 #endif
 #ifndef VR_K_EVENT
 #define VR_K_EVENT 8
 #endif
+#ifndef VR_K_COLLIDE_TF
+#define VR_K_COLLIDE_TF 8
+#endif
+#ifndef VR_K_COLLIDE
+#define VR_K_COLLIDE 4
+#endif
 #ifndef VR_MIN_STEP_TF
 #define VR_MIN_STEP_TF 4
-#endif
-#ifndef VR_SUBSTEPS
-#define VR_SUBSTEPS 1     // DDA rounds per scheduler iteration (lanes with a pending collision sit out the extra rounds)
-#endif
-#ifndef VR_SUBSTEP_MIN
-#define VR_SUBSTEP_MIN 12 // an extra round needs at least this many lanes able to step
 #endif
 #ifndef VR_MIN_STEP
 #define VR_MIN_STEP 16    // fewer stepping lanes than this: drain the fullest queue even below its threshold
@@ -93,19 +93,12 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
     uint32_t seed = 0, n_paths = 0;
     float3 pos = f3(0.f), dir = f3(0.f, 0.f, -1.f), thr = f3(1.f), L = f3(0.f), pend = f3(0.f);
     float3 ipos = f3(0.f), idir = f3(1.f), ri = f3(1.f);
-    float t = 0.f, tfar = -1.f, tau = 0.f, mip = 3.f, f_p = 0.f, Tr = 1.f;
+    float t = 0.f, tfar = -1.f, tau = 0.f, mip = 3.f, f_p = 0.f, Tr = 1.f, majorant = 0.f;
 
     while (true) {
-        // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) + tentative collision =================
-        // Lanes that found a tentative collision wait (at most VR_SUBSTEPS - 1 extra rounds) while the others keep
-        // stepping, so that the expensive collision code below runs with more active lanes.
-        bool collide = false;
-        float majorant = 0.f;
-#pragma unroll 1
-        for (int sub = 0; sub < VR_SUBSTEPS; ++sub) {
-            const bool can = stage == SG_STEP && !collide && t < tfar;
-            if (sub > 0 && __popc(__ballot_sync(FULL, can)) < VR_SUBSTEP_MIN) break;
-            if (can) {
+        // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) =================
+        if (stage == SG_STEP) {
+            if (t < tfar) {
                 const float3 curr = ipos + t * idir;
                 const int m = round_mip(mip);
                 cnt.maj();
@@ -116,56 +109,11 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 mip = fminf(mip + 0.25f, 3.f);
                 if (!(tau > 0.f)) {
                     t += MT::div(tau, majorant);
-                    collide = !(t >= tfar);   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
+                    if (!(t >= tfar)) stage = SG_COLLIDE;   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
                 }
-                if (++steps > MAX_RAY_STEPS) { t = INFINITY; collide = false; }
+                if (++steps > MAX_RAY_STEPS) { t = INFINITY; stage = SG_STEP; }
             }
-        }
-        if (stage == SG_STEP) {
-            if (collide) {   // common.glsl:436-452 / 483-498
-                cnt.dens();
-                const float3 at = ipos + t * idir;
-                float d;
-                float3 tf_rgb = f3(1.f);
-                if (TF) {
-                    const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * density_trilinear(a.density, at) * a.p.vol_inv_majorant);
-                    d = a.p.vol_majorant * rgba.w;
-                    tf_rgb = f3(rgba.x, rgba.y, rgba.z);
-                } else {
-                    const int3 tap = stochastic_tricubic_filter<MT>(at, seed);
-                    d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
-                }
-                bool parked = false;
-                if (!shadow) {
-                    bool fetched;
-                    const float3 em = lookup_emission<MT>(a, at, seed, fetched);
-                    if (fetched) {
-                        cnt.emis();
-                        const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-                        L = L + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant;
-                    }
-                    if (rng(seed) * majorant < d) {          // real collision: the segment ends here (common.glsl:490-496)
-                        thr = thr * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-                        if (TF) thr = thr * tf_rgb;
-                        stage = SG_NEE;
-                        parked = true;
-                    }
-                } else {
-                    if (rng(seed) * majorant < d) {          // common.glsl:442-450
-                        Tr *= fmaxf(0.f, 1.f - MT::div(a.p.vol_majorant, majorant));
-                        if (Tr < .1f) {
-                            const float prob = 1 - Tr;
-                            if (rng(seed) < prob) { Tr = 0.f; t = INFINITY; parked = true; }
-                            else Tr = MT::div(Tr, 1 - prob);
-                        }
-                    }
-                }
-                if (!parked) {
-                    tau = -MT::log(1.f - rng(seed));
-                    mip = fmaxf(0.f, mip - 2.f);
-                }
-            }
-            if (stage == SG_STEP && !(t < tfar)) {   // the ray left the volume (or the shadow ray was absorbed)
+            if (stage == SG_STEP && !(t < tfar)) {   // the ray left the volume
                 if (shadow) {
                     if (Tr != 0.f) L = L + pend * Tr;     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
                     stage = SG_SCATTER;
@@ -178,19 +126,67 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
 
         // ================= scheduler =================
         const unsigned m_step = __ballot_sync(FULL, stage == SG_STEP);
+        const unsigned m_col = __ballot_sync(FULL, stage == SG_COLLIDE);
         const unsigned m_nee = __ballot_sync(FULL, stage == SG_NEE);
         const unsigned m_scat = __ballot_sync(FULL, stage == SG_SCATTER);
         const unsigned m_fin = __ballot_sync(FULL, stage == SG_FINISH);
-        if ((m_step | m_nee | m_scat | m_fin) == 0u) break;     // every lane idle
-        const int n_step = __popc(m_step), n_nee = __popc(m_nee), n_scat = __popc(m_scat), n_fin = __popc(m_fin);
-        constexpr int K = TF ? VR_K_EVENT_TF : VR_K_EVENT, MIN_STEP = TF ? VR_MIN_STEP_TF : VR_MIN_STEP;
-        bool run_nee = n_nee >= K, run_scat = n_scat >= K, run_fin = n_fin >= K;
-        if (!(run_nee | run_scat | run_fin)) {
+        if ((m_step | m_col | m_nee | m_scat | m_fin) == 0u) break;     // every lane idle
+        const int n_step = __popc(m_step), n_col = __popc(m_col), n_nee = __popc(m_nee), n_scat = __popc(m_scat), n_fin = __popc(m_fin);
+        constexpr int K = TF ? VR_K_EVENT_TF : VR_K_EVENT, KC = TF ? VR_K_COLLIDE_TF : VR_K_COLLIDE, MIN_STEP = TF ? VR_MIN_STEP_TF : VR_MIN_STEP;
+        bool run_col = n_col >= KC, run_nee = n_nee >= K, run_scat = n_scat >= K, run_fin = n_fin >= K;
+        if (!(run_col | run_nee | run_scat | run_fin)) {
             if (n_step >= MIN_STEP) continue;                  // keep stepping
             // too few lanes can step: drain the fullest queue
-            if (n_nee >= n_scat && n_nee >= n_fin) run_nee = n_nee > 0;
+            if (n_col >= n_nee && n_col >= n_scat && n_col >= n_fin) run_col = n_col > 0;
+            else if (n_nee >= n_scat && n_nee >= n_fin) run_nee = n_nee > 0;
             else if (n_scat >= n_fin) run_scat = n_scat > 0;
             else run_fin = n_fin > 0;
+        }
+
+        // ================= COLLIDE: tentative collision (common.glsl:436-452 / 483-498) =================
+        if (run_col && stage == SG_COLLIDE) {
+            cnt.dens();
+            stage = SG_STEP;
+            const float3 at = ipos + t * idir;
+            float d;
+            float3 tf_rgb = f3(1.f);
+            if (TF) {
+                const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * density_trilinear(a.density, at) * a.p.vol_inv_majorant);
+                d = a.p.vol_majorant * rgba.w;
+                tf_rgb = f3(rgba.x, rgba.y, rgba.z);
+            } else {
+                const int3 tap = stochastic_tricubic_filter<MT>(at, seed);
+                d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
+            }
+            bool parked = false;
+            if (!shadow) {
+                bool fetched;
+                const float3 em = lookup_emission<MT>(a, at, seed, fetched);
+                if (fetched) {
+                    cnt.emis();
+                    const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                    L = L + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant;
+                }
+                if (rng(seed) * majorant < d) {          // real collision: the segment ends here (common.glsl:490-496)
+                    thr = thr * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                    if (TF) thr = thr * tf_rgb;
+                    stage = SG_NEE;
+                    parked = true;
+                }
+            } else {
+                if (rng(seed) * majorant < d) {          // common.glsl:442-450
+                    Tr *= fmaxf(0.f, 1.f - MT::div(a.p.vol_majorant, majorant));
+                    if (Tr < .1f) {
+                        const float prob = 1 - Tr;
+                        if (rng(seed) < prob) { Tr = 0.f; stage = SG_SCATTER; parked = true; }   // absorbed: `return 0.f`, nothing is added to L
+                        else Tr = MT::div(Tr, 1 - prob);
+                    }
+                }
+            }
+            if (!parked) {
+                tau = -MT::log(1.f - rng(seed));
+                mip = fmaxf(0.f, mip - 2.f);
+            }
         }
 
         bool start = false;     // this lane starts a new ray from (pos, rd) below

@@ -35,7 +35,8 @@ struct DeviceGrid {
     uint32_t* mips[3] = { nullptr, nullptr, nullptr };
     // tracer layout
     uint2* rec = nullptr;
-    uint8_t* atlas_lin = nullptr;
+    uint2* recp = nullptr;       // padded (nb + 2)^3 records for the trilinear fetch
+    uint8_t* atlas_lin = nullptr;   // n_slots bricks + one all-zero brick
     size_t n_slots = 0;
     // majorant tables of the persistent kernel, valid for maj_key
     float* maj[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -104,7 +105,7 @@ struct DeviceGuard {
 void free_grid(DeviceGrid& g) {
     cudaFree(g.indirection); cudaFree(g.range); cudaFree(g.atlas);
     for (auto& m : g.mips) cudaFree(m);
-    cudaFree(g.rec); cudaFree(g.atlas_lin);
+    cudaFree(g.rec); cudaFree(g.recp); cudaFree(g.atlas_lin);
     for (auto& m : g.maj) cudaFree(m);
     g = DeviceGrid();
 }
@@ -123,8 +124,14 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g) {
     const uint3 ab = make_uint3(g.atlas_dim.x >> 3, g.atlas_dim.y >> 3, g.atlas_dim.z >> 3);
     g.n_slots = size_t(ab.x) * ab.y * ab.z;
     CK(cudaMalloc(&g.rec, n * sizeof(uint2)));
-    CK(cudaMalloc(&g.atlas_lin, (g.n_slots ? g.n_slots : 1) * 512));
+    if (g.n_slots >= 0xffffffffull) return fail(ctx, VRB_ERR_INVALID, "atlas too large");
+    CK(cudaMalloc(&g.atlas_lin, (g.n_slots + 1) * 512));
+    CK(cudaMemsetAsync(g.atlas_lin + g.n_slots * 512, 0, 512, ctx->stream));   // the all-zero brick
     k_make_records<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.indirection, g.range, n, ab, g.rec);
+    CK_LAUNCH();
+    const size_t np = size_t(g.nb.x + 2) * (g.nb.y + 2) * (g.nb.z + 2);
+    CK(cudaMalloc(&g.recp, np * sizeof(uint2)));
+    k_make_records_padded<<<grid_for(np, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.rec, g.nb, uint32_t(g.n_slots), g.recp);
     CK_LAUNCH();
     if (g.n_slots) {
         k_linearize_atlas<<<grid_for(g.n_slots * 64, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.atlas, g.atlas_dim, g.atlas_lin, g.n_slots);
@@ -221,6 +228,9 @@ GridView make_view(const DeviceGrid& g) {
     v.rec = g.rec;
     for (int i = 0; i < 3; ++i) v.mips[i] = g.mips[i];
     v.atlas_lin = g.atlas_lin;
+    v.recp = g.recp;
+    v.psx = g.nb.x + 2;
+    v.psxy = (g.nb.x + 2) * (g.nb.y + 2);
     return v;
 }
 
