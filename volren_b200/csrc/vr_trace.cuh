@@ -63,6 +63,10 @@ struct TraceArgs {
     const float* maj_oob;          // majorant of an out-of-bounds fetch (one float)
     unsigned int* job_counter;     // pixel ticket
     int tiles_x, n_jobs;
+    // heaviest-tiles-first scheduling: ticket block k is tile tile_order[k] (nullptr: natural order); every finished
+    // pixel adds the cycles it occupied its lane to tile_cost[tile] for the next launch of the same view
+    const uint32_t* tile_order;
+    unsigned int* tile_cost;
 };
 
 template <bool COUNT> struct Cnt;

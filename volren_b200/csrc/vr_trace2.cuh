@@ -12,6 +12,11 @@
 //     in it (or nothing else can make progress), so the heavy stages (8-tap trilinear + LUT collision test,
 //     importance-pyramid warp, phase sampling, escape lookup + TEA reseed) execute with many active lanes
 //     instead of a few; every new ray (camera, shadow, scattered) is started at ONE shared site after the stages;
+//   * tickets are issued HEAVIEST TILE FIRST when the previous launch of the same view left per-tile costs (cycles a
+//     pixel occupied its lane): with whole-pixel tickets the last heavy pixels otherwise run alone for a third of the
+//     launch (profiles/r01_v4_*: SMs active 55-95 % of the kernel time). Splitting a pixel's samples into chunks
+//     handed to different lanes was tried and rejected: the release/acquire (or fence) per hand-off costs more than
+//     the tail it removes (profiles/r01_v4_chunk_sweep_*.txt);
 //   * per-level majorants are read from float tables precomputed per (grid, params) with the identical
 //     expression (the TF variant otherwise evaluates a LUT lerp and a divide on every DDA step);
 //   * MT = FastMath in production (MUFU rcp/rsqrt/lg2/sin/cos): 3x less SASS than the IEEE sequences, which
@@ -89,6 +94,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
     bool escaped = false;          // FINISH entered because the camera segment left the volume (-> environment)
     bool have_pixel = false;
     int px = 0, py = 0, s = 0, steps = 0;
+    unsigned t_ticket = 0;         // clock at which this lane took its pixel
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t seed = 0, n_paths = 0;
     float3 pos = f3(0.f), dir = f3(0.f, 0.f, -1.f), thr = f3(1.f), L = f3(0.f), pend = f3(0.f);
@@ -263,6 +269,11 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 if (++s == s_end) {
                     a.color[size_t(py) * W + px] = acc;
                     have_pixel = false;
+                    if (a.tile_cost) {
+                        unsigned now;
+                        asm volatile("mov.u32 %0, %%clock;" : "=r"(now));
+                        atomicAdd(a.tile_cost + ((py - a.y0) >> 2) * a.tiles_x + ((px - a.x0) >> 3), (now - t_ticket) >> 8);
+                    }
                 }
             }
             // pixel tickets (tile-major order: 32 consecutive tickets = one 8x4 pixel tile)
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                     const unsigned job = base + __popc(m_fetch & ((1u << lane) - 1u));
                     if (job >= unsigned(a.n_jobs)) { want = false; stage = SG_IDLE; }
                     else {
-                        const unsigned tile = job >> 5, within = job & 31u;
+                        const unsigned tile = a.tile_order ? __ldg(a.tile_order + (job >> 5)) : job >> 5, within = job & 31u;
                         px = a.x0 + int(tile % unsigned(a.tiles_x)) * 8 + int(within & 7u);
                         py = a.y0 + int(tile / unsigned(a.tiles_x)) * 4 + int(within >> 3);
                         if (px < a.x1 && py < a.y1) {
@@ -286,6 +297,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                             s = a.first_sample;
                             have_pixel = true;
                             want = false;
+                            asm volatile("mov.u32 %0, %%clock;" : "=r"(t_ticket));
                         }
                     }
                 }

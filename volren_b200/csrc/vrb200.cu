@@ -8,7 +8,11 @@
 #include "vr_trace.cuh"
 #include "vr_trace2.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -67,6 +71,16 @@ struct vrb_ctx {
     uint32_t tf_size = 0;
     unsigned long long* counters = nullptr;
     unsigned int* job_counter = nullptr;
+    // heaviest-tiles-first scheduling (vr_trace2.cuh): per-tile cost of the last launch, its view key, the sorted order
+    unsigned int* tile_cost = nullptr;
+    unsigned int* tile_cost_sorted = nullptr;
+    uint32_t* tile_iota = nullptr;
+    uint32_t* tile_order = nullptr;
+    void* sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    int tile_capacity = 0;
+    uint64_t cost_key = 0;       // view the costs in tile_cost belong to (0 = none)
+    bool lpt = true;             // VRB200_LPT=0 disables
     bool counting = false;
     int kernel = 0;            // 0 = persistent FastMath (production), 1 = simple strict cross-check, 2 = persistent StrictMath
     int trace_blocks[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -317,6 +331,7 @@ int vrb_create(int device, vrb_ctx** out) {
         return VRB_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char* e = getenv("VRB200_LPT")) ctx->lpt = atoi(e) != 0;
     cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream);
     *out = ctx;
     return VRB_OK;
@@ -328,6 +343,7 @@ void vrb_destroy(vrb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& f : ctx->frames) { free_grid(f.second.slot[0]); free_grid(f.second.slot[1]); }
     if (!ctx->color_external) cudaFree(ctx->color);
+    cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
     cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -621,9 +637,54 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         g.maj_key = key;
     }
     a.tiles_x = (a.x1 - a.x0 + 7) / 8;
-    a.n_jobs = a.tiles_x * ((a.y1 - a.y0 + 3) / 4) * 32;
+    const int n_tiles = a.tiles_x * ((a.y1 - a.y0 + 3) / 4);
+    a.n_jobs = n_tiles * 32;
     a.job_counter = ctx->job_counter;
     CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
+    // ---- heaviest tiles first: order the tickets by the per-tile cost the previous launch of this view measured ----
+    if (ctx->lpt && !ctx->counting && ctx->kernel == 0) {
+        // the cost landscape depends on everything but the seed and the sample range
+        uint64_t vkey = key;
+        auto mix2 = [&vkey](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); for (size_t i = 0; i < n; ++i) { vkey ^= b[i]; vkey *= 1099511628211ull; } };
+        vrb_params pk = *params;
+        pk.seed = 0;
+        mix2(&pk, sizeof pk);
+        mix2(&a.x0, 4 * sizeof(int));
+        mix2(&ctx->env_w, sizeof(int));
+        if (vkey == 0) vkey = 1;
+        if (n_tiles > ctx->tile_capacity) {
+            cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
+            ctx->tile_cost = ctx->tile_cost_sorted = nullptr; ctx->tile_iota = ctx->tile_order = nullptr; ctx->sort_tmp = nullptr;
+            ctx->tile_capacity = 0; ctx->cost_key = 0;
+            CK(cudaMalloc(&ctx->tile_cost, size_t(n_tiles) * 4));
+            CK(cudaMalloc(&ctx->tile_cost_sorted, size_t(n_tiles) * 4));
+            CK(cudaMalloc(&ctx->tile_iota, size_t(n_tiles) * 4));
+            CK(cudaMalloc(&ctx->tile_order, size_t(n_tiles) * 4));
+            ctx->sort_tmp_bytes = 0;
+            CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, ctx->sort_tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
+            CK(cudaMalloc(&ctx->sort_tmp, ctx->sort_tmp_bytes ? ctx->sort_tmp_bytes : 16));
+            k_iota<<<grid_for(size_t(n_tiles), 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->tile_iota, size_t(n_tiles));
+            CK_LAUNCH();
+            ctx->tile_capacity = n_tiles;
+        }
+        if (ctx->cost_key != vkey && n_samples >= 4) {
+            // no history for this view: a one-sample pilot launch measures the tiles (same image: launches fold in order)
+            ctx->cost_key = vkey;
+            CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, ctx->stream));
+            int st2 = vrb_trace(ctx, params, first_sample, 1, tile, accum_mode);
+            if (st2) return st2;
+            return vrb_trace(ctx, params, first_sample + 1, n_samples - 1, tile, accum_mode);
+        }
+        if (ctx->cost_key == vkey) {
+            size_t tmp_bytes = ctx->sort_tmp_bytes;
+            CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
+            a.tile_order = ctx->tile_order;
+        } else {
+            ctx->cost_key = vkey;     // first (short) launch of a new view: natural order, but measure
+        }
+        CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, ctx->stream));
+        a.tile_cost = ctx->tile_cost;
+    }
     const int variant = (tf ? 1 : 0) | (ctx->counting ? 2 : 0) | (ctx->kernel == 2 ? 4 : 0);
     const void* fn = nullptr;
     switch (variant) {
