@@ -2,25 +2,30 @@
 //
 // Same per-path algorithm and random-number order as the straightforward kernel in vr_trace.cuh
 // (kept as the in-library cross-check, vrb_set_kernel(ctx, 1)), restructured for the SIMT machine:
-//   * one lane owns one PIXEL for all samples of the launch (running mean stays in registers, in sample
-//     order, exactly like n successive dispatches of pathtracer_brick.glsl) and fetches the next pixel from
-//     a global ticket when it is done -> no tail of idle SMs behind the few long pixels;
+//   * the unit of work is ONE PATH SAMPLE (pixel, sample index). Warps draw blocks of 32 samples = (8x4 pixel tile,
+//     sample index) from a global counter (the next block is prefetched one switch ahead, so the atomic's round trip is
+//     never on the critical path) and hand them to whichever lane is free. A sample's radiance goes to a per-launch
+//     buffer lbuf[sample][pixel]; k_fold then folds the samples of each pixel into `color` IN SAMPLE ORDER, so the image
+//     is bit-identical to successive dispatches of pathtracer_brick.glsl (:36 running mean). History: with whole-pixel
+//     tickets (v3-v5) the heaviest pixel's samples ran back to back on one lane and a third of the SM time was tail
+//     (profiles/r01_v4_*, r01_v5_*); handing chunks of a pixel to different lanes needed a release/acquire per hand-off
+//     that cost more than the tail (profiles/r01_v4_chunk_sweep_*.txt). The buffer costs 32 B of traffic per sample;
+//   * when a warp switches to a new block ALL 32 lanes prepare it together -- TEA seed (32 rounds, the largest single
+//     cost of a short path), pixel jitter and view direction of the block's 32 samples go to shared memory -- instead of
+//     each lane seeding its own sample whenever it happens to become free (17 of 32 lanes active before);
+//   * blocks are issued HEAVIEST TILE FIRST when the previous launch of the same view left per-tile costs (cycles a
+//     sample occupied its lane), so the last blocks of a launch are the cheap ones;
 //   * camera segments and shadow rays share ONE brick-DDA loop body (common.glsl:412-501 differ only in what
 //     happens at a collision), so a warp's lanes step convergently whatever kind of ray they are on;
 //   * path events are scheduled wavefront-style INSIDE the warp: a lane whose ray hit a tentative collision or ended
 //     parks in one of four queues (COLLIDE / NEE / SCATTER / FINISH); a queue's stage runs when enough lanes wait
 //     in it (or nothing else can make progress), so the heavy stages (8-tap trilinear + LUT collision test,
-//     importance-pyramid warp, phase sampling, escape lookup + TEA reseed) execute with many active lanes
+//     importance-pyramid warp, phase sampling, escape lookup) execute with many active lanes
 //     instead of a few; every new ray (camera, shadow, scattered) is started at ONE shared site after the stages;
-//   * tickets are issued HEAVIEST TILE FIRST when the previous launch of the same view left per-tile costs (cycles a
-//     pixel occupied its lane): with whole-pixel tickets the last heavy pixels otherwise run alone for a third of the
-//     launch (profiles/r01_v4_*: SMs active 55-95 % of the kernel time). Splitting a pixel's samples into chunks
-//     handed to different lanes was tried and rejected: the release/acquire (or fence) per hand-off costs more than
-//     the tail it removes (profiles/r01_v4_chunk_sweep_*.txt);
 //   * per-level majorants are read from float tables precomputed per (grid, params) with the identical
 //     expression (the TF variant otherwise evaluates a LUT lerp and a divide on every DDA step);
 //   * MT = FastMath in production (MUFU rcp/rsqrt/lg2/sin/cos): 3x less SASS than the IEEE sequences, which
-//     matters because the kernel was instruction-fetch bound (profiles/r01_v3_*: stall_no_instruction 50 %).
+//     matters because the kernel was instruction-fetch bound (profiles/r01_v1_*: stall_no_instruction 50 %).
 #pragma once
 
 #include "vr_trace.cuh"
@@ -85,21 +90,27 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int W = a.p.resolution[0];
-    const int s_end = a.first_sample + a.n_samples;
     Cnt<COUNT> cnt;
 
     // ---- lane state ----
-    int stage = SG_FINISH;         // everybody starts by fetching a pixel
+    int stage = SG_FINISH;         // everybody starts by asking for a sample
     bool shadow = false;           // kind of the ray being stepped
     bool escaped = false;          // FINISH entered because the camera segment left the volume (-> environment)
-    bool have_pixel = false;
-    int px = 0, py = 0, s = 0, steps = 0;
-    unsigned t_ticket = 0;         // clock at which this lane took its pixel
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool have_item = false;
+    int px = 0, py = 0, sj = 0, steps = 0;   // the lane's sample: pixel and sample index relative to first_sample
+    unsigned t_item = 0;           // clock at which this lane took its sample
     uint32_t seed = 0, n_paths = 0;
     float3 pos = f3(0.f), dir = f3(0.f, 0.f, -1.f), thr = f3(1.f), L = f3(0.f), pend = f3(0.f);
     float3 ipos = f3(0.f), idir = f3(1.f), ri = f3(1.f);
     float t = 0.f, tfar = -1.f, tau = 0.f, mip = 3.f, f_p = 0.f, Tr = 1.f, majorant = 0.f;
+    // ---- warp state: the current block of 32 samples (one tile, one sample index), prepared in shared memory ----
+    __shared__ float4 s_prep[VR_TRACE_BLOCK / 32][32];     // {view dir, seed after the two jitter draws}
+    float4* prep = s_prep[threadIdx.x >> 5];
+    int blk_x0 = 0, blk_y0 = 0, blk_sj = 0;
+    unsigned blk_mask = 0u;        // samples of the block not handed out yet (bit i = pixel i of the tile)
+    bool blk_done = false;         // the counter is exhausted
+    unsigned nxt_block = 0;        // lane 0: id of the prefetched next block
+    if (lane == 0) nxt_block = atomicAdd(a.job_counter, 1u);
 
     while (true) {
         // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) =================
@@ -247,10 +258,10 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
             }
         }
 
-        // ================= FINISH: environment on escape, fold the sample, next sample / next pixel =================
-        if (run_fin) {     // warp-uniform: the ticket loop below uses warp collectives
+        // ================= FINISH: environment on escape, store the sample, take the next one =================
+        if (run_fin) {     // warp-uniform: the block switch below is a warp-wide cooperative step
             const bool mine = stage == SG_FINISH;
-            if (mine && have_pixel) {
+            if (mine && have_item) {
                 if (escaped && a.p.show_environment > 0) {      // common.glsl:644-649
                     cnt.env();
                     const float3 Le = lookup_environment(a, dir);
@@ -258,55 +269,70 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                     const float mis_weight = n_paths > 0 ? MT::div(sqr(f_p), sqr(f_p) + sqr(pe)) : 1.f;
                     L = L + thr * mis_weight * Le;
                 }
-                cnt.samp();                                     // pathtracer_brick.glsl:36
-                const float Lx = sanitize(L.x), Ly = sanitize(L.y), Lz = sanitize(L.z), Lw = sanitize(fminf(float(n_paths), 1.f));
-                if (a.accum_mode == VRB_ACCUM_MEAN) {
-                    const float w = 1.f / float(s);
-                    acc.x = mix_rn(acc.x, Lx, w); acc.y = mix_rn(acc.y, Ly, w); acc.z = mix_rn(acc.z, Lz, w); acc.w = mix_rn(acc.w, Lw, w);
-                } else {
-                    acc.x += Lx; acc.y += Ly; acc.z += Lz; acc.w += Lw;
-                }
-                if (++s == s_end) {
-                    a.color[size_t(py) * W + px] = acc;
-                    have_pixel = false;
-                    if (a.tile_cost) {
-                        unsigned now;
-                        asm volatile("mov.u32 %0, %%clock;" : "=r"(now));
-                        atomicAdd(a.tile_cost + ((py - a.y0) >> 2) * a.tiles_x + ((px - a.x0) >> 3), (now - t_ticket) >> 8);
-                    }
+                cnt.samp();                                     // pathtracer_brick.glsl:36: sanitize(L), folded by k_fold
+                a.lbuf[size_t(sj) * a.lbuf_stride + size_t(py) * W + px] =
+                    make_float4(sanitize(L.x), sanitize(L.y), sanitize(L.z), sanitize(fminf(float(n_paths), 1.f)));
+                have_item = false;
+                if (a.tile_cost) {
+                    unsigned now;
+                    asm volatile("mov.u32 %0, %%clock;" : "=r"(now));
+                    atomicAdd(a.tile_cost + ((py - a.y0) >> 2) * a.tiles_x + ((px - a.x0) >> 3), (now - t_item) >> 8);
                 }
             }
-            // pixel tickets (tile-major order: 32 consecutive tickets = one 8x4 pixel tile)
-            bool want = mine && !have_pixel;
+            bool want = mine;
             while (true) {
-                const unsigned m_fetch = __ballot_sync(FULL, want);
-                if (m_fetch == 0u) break;
-                unsigned base = 0;
-                const int leader = __ffs(m_fetch) - 1;
-                if (lane == leader) base = atomicAdd(a.job_counter, unsigned(__popc(m_fetch)));
-                base = __shfl_sync(FULL, base, leader);
-                if (want) {
-                    const unsigned job = base + __popc(m_fetch & ((1u << lane) - 1u));
-                    if (job >= unsigned(a.n_jobs)) { want = false; stage = SG_IDLE; }
-                    else {
-                        const unsigned tile = a.tile_order ? __ldg(a.tile_order + (job >> 5)) : job >> 5, within = job & 31u;
-                        px = a.x0 + int(tile % unsigned(a.tiles_x)) * 8 + int(within & 7u);
-                        py = a.y0 + int(tile / unsigned(a.tiles_x)) * 4 + int(within >> 3);
-                        if (px < a.x1 && py < a.y1) {
-                            acc = a.color[size_t(py) * W + px];
-                            s = a.first_sample;
-                            have_pixel = true;
-                            want = false;
-                            asm volatile("mov.u32 %0, %%clock;" : "=r"(t_ticket));
-                        }
+                const unsigned m_want = __ballot_sync(FULL, want);
+                if (m_want == 0u) break;
+                if (blk_mask == 0u) {                              // warp-uniform: switch to the prefetched block
+                    unsigned b = 0xffffffffu;
+                    if (!blk_done) {
+                        b = __shfl_sync(FULL, nxt_block, 0);
+                        if (lane == 0) nxt_block = atomicAdd(a.job_counter, 1u);
                     }
+                    if (b >= unsigned(a.n_jobs)) {                 // no blocks left
+                        blk_done = true;
+                        if (want) { want = false; stage = SG_IDLE; }
+                        break;
+                    }
+                    // tile-major: the n_samples blocks of a tile are consecutive; tiles in cost order
+                    const unsigned slot = b / unsigned(a.n_samples);
+                    blk_sj = int(b - slot * unsigned(a.n_samples));
+                    const unsigned tile = a.tile_order ? __ldg(a.tile_order + slot) : slot;
+                    blk_x0 = a.x0 + int(tile % unsigned(a.tiles_x)) * 8;
+                    blk_y0 = a.y0 + int(tile / unsigned(a.tiles_x)) * 4;
+                    // all 32 lanes prepare the block: lane i seeds sample (pixel i of the tile, sample blk_sj)
+                    // (pathtracer_brick.glsl:28-30: TEA seed, two jitter draws, view direction)
+                    const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
+                    const bool inside = ix < a.x1 && iy < a.y1;
+                    uint32_t sd = tea32(uint32_t(a.p.seed) * uint32_t(iy * W + ix), uint32_t(a.first_sample + blk_sj));
+                    const float jx = rng(sd), jy = rng(sd);
+                    const float3 vd = view_dir<MT>(a, ix, iy, jx, jy);
+                    __syncwarp();
+                    prep[lane] = make_float4(vd.x, vd.y, vd.z, __uint_as_float(sd));
+                    __syncwarp();
+                    blk_mask = __ballot_sync(FULL, inside);
+                    continue;
                 }
+                // the r-th wanting lane takes the r-th remaining sample of the block
+                const int rank = __popc(m_want & ((1u << lane) - 1u));
+                unsigned took = 0u;
+                if (want && rank < __popc(blk_mask)) {
+                    const int i = int(__fns(blk_mask, 0, rank + 1));
+                    took = 1u << i;
+                    const float4 pr = prep[i];
+                    px = blk_x0 + (i & 7);
+                    py = blk_y0 + (i >> 3);
+                    sj = blk_sj;
+                    seed = __float_as_uint(pr.w);
+                    dir = f3(pr.x, pr.y, pr.z);
+                    have_item = true;
+                    want = false;
+                }
+                blk_mask &= ~__reduce_or_sync(FULL, took);
             }
-            // new sample: TEA seed, jittered camera ray (pathtracer_brick.glsl:28-30)
-            if (mine && stage == SG_FINISH) {
-                seed = tea32(uint32_t(a.p.seed) * uint32_t(py * W + px), uint32_t(s));
-                const float jx = rng(seed), jy = rng(seed);
-                dir = view_dir<MT>(a, px, py, jx, jy);
+            // new sample: camera ray of the prepared sample
+            if (mine && have_item) {
+                asm volatile("mov.u32 %0, %%clock;" : "=r"(t_item));
                 pos = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
                 thr = f3(1.f); L = f3(0.f); n_paths = 0; f_p = 0.f;
                 shadow = false; escaped = false;
@@ -334,6 +360,28 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         }
     }
     flush_counters(a, cnt);
+}
+
+// Folds the samples of one launch into the colour buffer in sample order (pathtracer_brick.glsl:36):
+// color = mix(color, L_s, 1 / s) for s = first_sample ... (VRB_ACCUM_MEAN) or color += L_s (VRB_ACCUM_SUM).
+__global__ void __launch_bounds__(256) k_fold(float4* __restrict__ color, const float4* __restrict__ lbuf, size_t lbuf_stride, int W, int x0, int y0, int x1, int y1,
+                                              int first_sample, int n_samples, int accum_mode) {
+    const int rw = x1 - x0;
+    const size_t n = size_t(rw) * (y1 - y0);
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t p = size_t(y0 + int(i / rw)) * W + (x0 + int(i % rw));
+        float4 acc = color[p];
+        for (int j = 0; j < n_samples; ++j) {
+            const float4 L = __ldcs(lbuf + size_t(j) * lbuf_stride + p);
+            if (accum_mode == VRB_ACCUM_MEAN) {
+                const float w = 1.f / float(first_sample + j);
+                acc.x = mix_rn(acc.x, L.x, w); acc.y = mix_rn(acc.y, L.y, w); acc.z = mix_rn(acc.z, L.z, w); acc.w = mix_rn(acc.w, L.w, w);
+            } else {
+                acc.x += L.x; acc.y += L.y; acc.z += L.z; acc.w += L.w;
+            }
+        }
+        color[p] = acc;
+    }
 }
 
 }  // namespace vr

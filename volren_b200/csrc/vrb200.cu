@@ -71,6 +71,9 @@ struct vrb_ctx {
     uint32_t tf_size = 0;
     unsigned long long* counters = nullptr;
     unsigned int* job_counter = nullptr;
+    float4* lbuf = nullptr;      // per-launch sample buffer of the persistent kernel: lbuf_samples x (w * h) float4
+    int lbuf_samples = 0;
+    int pass_samples = 16;       // samples per pixel and pass (VRB200_PASS); bounds lbuf (also capped at 1 GiB)
     // heaviest-tiles-first scheduling (vr_trace2.cuh): per-tile cost of the last launch, its view key, the sorted order
     unsigned int* tile_cost = nullptr;
     unsigned int* tile_cost_sorted = nullptr;
@@ -332,6 +335,7 @@ int vrb_create(int device, vrb_ctx** out) {
     }
     ctx->stream = ctx->own_stream;
     if (const char* e = getenv("VRB200_LPT")) ctx->lpt = atoi(e) != 0;
+    if (const char* e = getenv("VRB200_PASS")) ctx->pass_samples = std::max(1, atoi(e));
     cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream);
     *out = ctx;
     return VRB_OK;
@@ -344,6 +348,7 @@ void vrb_destroy(vrb_ctx* ctx) {
     for (auto& f : ctx->frames) { free_grid(f.second.slot[0]); free_grid(f.second.slot[1]); }
     if (!ctx->color_external) cudaFree(ctx->color);
     cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
+    cudaFree(ctx->lbuf);
     cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -372,8 +377,8 @@ int vrb_resize(vrb_ctx* ctx, int w, int h) {
     DeviceGuard guard(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
     if (!ctx->color_external) cudaFree(ctx->color);
-    cudaFree(ctx->fb); cudaFree(ctx->ldr);
-    ctx->color = nullptr; ctx->fb = nullptr; ctx->ldr = nullptr; ctx->color_external = false;
+    cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->lbuf);
+    ctx->color = nullptr; ctx->fb = nullptr; ctx->ldr = nullptr; ctx->lbuf = nullptr; ctx->lbuf_samples = 0; ctx->color_external = false;
     ctx->w = w; ctx->h = h;
     const size_t n = size_t(w) * h;
     CK(cudaMalloc(&ctx->color, n * sizeof(float4)));
@@ -638,13 +643,25 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     }
     a.tiles_x = (a.x1 - a.x0 + 7) / 8;
     const int n_tiles = a.tiles_x * ((a.y1 - a.y0 + 3) / 4);
-    a.n_jobs = n_tiles * 32;
     a.job_counter = ctx->job_counter;
-    CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
-    // ---- heaviest tiles first: order the tickets by the per-tile cost the previous launch of this view measured ----
-    if (ctx->lpt && !ctx->counting && ctx->kernel == 0) {
+    // ---- per-launch sample buffer: passes of at most `pass` samples per pixel (16 B per sample and pixel) ----
+    const size_t n_px = size_t(ctx->w) * ctx->h;
+    const int pass = int(std::max<size_t>(1, std::min<size_t>(size_t(ctx->pass_samples), (size_t(1) << 30) / (n_px * sizeof(float4)))));
+    const int want_pass = std::min(pass, n_samples);
+    if (ctx->lbuf_samples < want_pass) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->lbuf);
+        ctx->lbuf = nullptr; ctx->lbuf_samples = 0;
+        CK(cudaMalloc(&ctx->lbuf, n_px * sizeof(float4) * size_t(want_pass)));
+        ctx->lbuf_samples = want_pass;
+    }
+    a.lbuf = ctx->lbuf;
+    a.lbuf_stride = n_px;
+    // ---- heaviest tiles first: order the blocks by the per-tile cost the previous launch of this view measured ----
+    const bool lpt = ctx->lpt && !ctx->counting && ctx->kernel == 0;
+    uint64_t vkey = key;
+    if (lpt) {
         // the cost landscape depends on everything but the seed and the sample range
-        uint64_t vkey = key;
         auto mix2 = [&vkey](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); for (size_t i = 0; i < n; ++i) { vkey ^= b[i]; vkey *= 1099511628211ull; } };
         vrb_params pk = *params;
         pk.seed = 0;
@@ -667,23 +684,6 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             CK_LAUNCH();
             ctx->tile_capacity = n_tiles;
         }
-        if (ctx->cost_key != vkey && n_samples >= 4) {
-            // no history for this view: a one-sample pilot launch measures the tiles (same image: launches fold in order)
-            ctx->cost_key = vkey;
-            CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, ctx->stream));
-            int st2 = vrb_trace(ctx, params, first_sample, 1, tile, accum_mode);
-            if (st2) return st2;
-            return vrb_trace(ctx, params, first_sample + 1, n_samples - 1, tile, accum_mode);
-        }
-        if (ctx->cost_key == vkey) {
-            size_t tmp_bytes = ctx->sort_tmp_bytes;
-            CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
-            a.tile_order = ctx->tile_order;
-        } else {
-            ctx->cost_key = vkey;     // first (short) launch of a new view: natural order, but measure
-        }
-        CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, ctx->stream));
-        a.tile_cost = ctx->tile_cost;
     }
     const int variant = (tf ? 1 : 0) | (ctx->counting ? 2 : 0) | (ctx->kernel == 2 ? 4 : 0);
     const void* fn = nullptr;
@@ -702,10 +702,33 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, VR_TRACE_BLOCK, 0));
         ctx->trace_blocks[variant] = ctx->sm_count * (per_sm > 0 ? per_sm : 1);   // one resident wave: grid = 148 x blocks/SM
     }
-    const int needed = (a.n_jobs / 32 + (VR_TRACE_BLOCK / 32) - 1) / (VR_TRACE_BLOCK / 32);
-    const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
-    void* kargs[] = { (void*)&a };
-    CK(cudaLaunchKernel(fn, dim3(blocks), dim3(VR_TRACE_BLOCK), kargs, 0, ctx->stream));
+    const int first_end = first_sample + n_samples;
+    for (int s0 = first_sample; s0 < first_end; s0 += pass) {
+        a.first_sample = s0;
+        a.n_samples = std::min(pass, first_end - s0);
+        // 32-bit block counter: tiles * samples blocks per pass (a pass holds at most 2^30 / 16 sample-pixels)
+        a.n_jobs = n_tiles * a.n_samples;
+        CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
+        a.tile_order = nullptr;
+        a.tile_cost = nullptr;
+        if (lpt) {
+            if (ctx->cost_key == vkey) {      // the previous pass / launch measured this view
+                size_t tmp_bytes = ctx->sort_tmp_bytes;
+                CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
+                a.tile_order = ctx->tile_order;
+            }
+            ctx->cost_key = vkey;
+            CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, ctx->stream));
+            a.tile_cost = ctx->tile_cost;
+        }
+        const int needed = (a.n_jobs + (VR_TRACE_BLOCK / 32) - 1) / (VR_TRACE_BLOCK / 32);
+        const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
+        void* kargs[] = { (void*)&a };
+        CK(cudaLaunchKernel(fn, dim3(blocks), dim3(VR_TRACE_BLOCK), kargs, 0, ctx->stream));
+        const size_t n_region = size_t(a.x1 - a.x0) * (a.y1 - a.y0);
+        k_fold<<<grid_for(n_region, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(ctx->color, ctx->lbuf, n_px, ctx->w, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode);
+        CK_LAUNCH();
+    }
     return VRB_OK;
 }
 
