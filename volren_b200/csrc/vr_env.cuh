@@ -110,8 +110,10 @@ __global__ void k_color_to_ldr(const float4* __restrict__ color, uchar4* __restr
         out[i] = make_uchar4((unsigned char)to_unorm8(c.x), (unsigned char)to_unorm8(c.y), (unsigned char)to_unorm8(c.z), (unsigned char)to_unorm8(c.w));
     }
 }
-__global__ void k_iota(uint32_t* __restrict__ out, size_t n) {
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) out[i] = uint32_t(i);
+// packed tile coordinates (ty << 16 | tx) in raster order
+__global__ void k_tile_coords(uint32_t* __restrict__ out, size_t n, uint32_t tiles_x) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        out[i] = (uint32_t(i / tiles_x) << 16) | uint32_t(i % tiles_x);
 }
 __global__ void k_scale(float4* __restrict__ color, size_t n, float s) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {

@@ -61,12 +61,14 @@ struct TraceArgs {
     // persistent kernel only
     const float* maj[4];           // per-level majorant tables (final value used by the tracking loop)
     const float* maj_oob;          // majorant of an out-of-bounds fetch (one float)
-    unsigned int* job_counter;     // block ticket: block b = (tile slot b / n_samples, sample b % n_samples), 32 samples each
-    int tiles_x, n_jobs;           // n_jobs = number of blocks = tiles * n_samples
+    unsigned int* job_counter;     // block ticket: block b = (tile slot b >> sample_bits, sample b & mask), 32 samples each
+    int tiles_x, n_jobs;           // n_jobs = number of block ids = tiles << sample_bits (ids with sample >= n_samples are padding)
+    int sample_bits;               // ceil(log2(n_samples))
     float4* lbuf;                  // per-launch sample buffer: lbuf[(s - first_sample) * lbuf_stride + y * W + x]
     size_t lbuf_stride;
-    // heaviest-tiles-first scheduling: tile slot k is tile tile_order[k] (nullptr: natural order); every finished
-    // sample adds the cycles it occupied its lane to tile_cost[tile] for the next launch of the same view
+    // tile slot k is the tile with packed coordinates tile_order[k] = (ty << 16 | tx): natural order, or heaviest first
+    // when the previous launch of the same view left costs; finished samples add the cycles they occupied their lane to
+    // tile_cost[ty * tiles_x + tx] (nullptr: not measured)
     const uint32_t* tile_order;
     unsigned int* tile_cost;
 };

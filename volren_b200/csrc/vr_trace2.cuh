@@ -71,6 +71,12 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #ifndef VR_K_EVENT
 #define VR_K_EVENT 8
 #endif
+#ifndef VR_K_FINISH_TF
+#define VR_K_FINISH_TF VR_K_EVENT_TF
+#endif
+#ifndef VR_K_FINISH
+#define VR_K_FINISH VR_K_EVENT
+#endif
 #ifndef VR_K_COLLIDE_TF
 #define VR_K_COLLIDE_TF 8
 #endif
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
     __shared__ float4 s_prep[VR_TRACE_BLOCK / 32][32];     // {view dir, seed after the two jitter draws}
     float4* prep = s_prep[threadIdx.x >> 5];
     int blk_x0 = 0, blk_y0 = 0, blk_sj = 0;
-    unsigned blk_mask = 0u;        // samples of the block not handed out yet (bit i = pixel i of the tile)
+    int blk_next = 32;             // next sample of the block to hand out (>= 32: block used up)
     bool blk_done = false;         // the counter is exhausted
     unsigned nxt_block = 0;        // lane 0: id of the prefetched next block
     if (lane == 0) nxt_block = atomicAdd(a.job_counter, 1u);
@@ -149,8 +155,9 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         const unsigned m_fin = __ballot_sync(FULL, stage == SG_FINISH);
         if ((m_step | m_col | m_nee | m_scat | m_fin) == 0u) break;     // every lane idle
         const int n_step = __popc(m_step), n_col = __popc(m_col), n_nee = __popc(m_nee), n_scat = __popc(m_scat), n_fin = __popc(m_fin);
+        constexpr int KF = TF ? VR_K_FINISH_TF : VR_K_FINISH;
         constexpr int K = TF ? VR_K_EVENT_TF : VR_K_EVENT, KC = TF ? VR_K_COLLIDE_TF : VR_K_COLLIDE, MIN_STEP = TF ? VR_MIN_STEP_TF : VR_MIN_STEP;
-        bool run_col = n_col >= KC, run_nee = n_nee >= K, run_scat = n_scat >= K, run_fin = n_fin >= K;
+        bool run_col = n_col >= KC, run_nee = n_nee >= K, run_scat = n_scat >= K, run_fin = n_fin >= KF;
         if (!(run_col | run_nee | run_scat | run_fin)) {
             if (n_step >= MIN_STEP) continue;                  // keep stepping
             // too few lanes can step: drain the fullest queue
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 a.lbuf[size_t(sj) * a.lbuf_stride + size_t(py) * W + px] =
                     make_float4(sanitize(L.x), sanitize(L.y), sanitize(L.z), sanitize(fminf(float(n_paths), 1.f)));
                 have_item = false;
-                if (a.tile_cost) {
+                if (a.tile_cost && ((px ^ py ^ sj) & 3) == 0) {   // a dithered quarter of the samples is enough to rank tiles
                     unsigned now;
                     asm volatile("mov.u32 %0, %%clock;" : "=r"(now));
                     atomicAdd(a.tile_cost + ((py - a.y0) >> 2) * a.tiles_x + ((px - a.x0) >> 3), (now - t_item) >> 8);
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
             while (true) {
                 const unsigned m_want = __ballot_sync(FULL, want);
                 if (m_want == 0u) break;
-                if (blk_mask == 0u) {                              // warp-uniform: switch to the prefetched block
+                if (blk_next >= 32) {                              // warp-uniform: switch to the prefetched block
                     unsigned b = 0xffffffffu;
                     if (!blk_done) {
                         b = __shfl_sync(FULL, nxt_block, 0);
@@ -294,41 +301,40 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                         if (want) { want = false; stage = SG_IDLE; }
                         break;
                     }
-                    // tile-major: the n_samples blocks of a tile are consecutive; tiles in cost order
-                    const unsigned slot = b / unsigned(a.n_samples);
-                    blk_sj = int(b - slot * unsigned(a.n_samples));
-                    const unsigned tile = a.tile_order ? __ldg(a.tile_order + slot) : slot;
-                    blk_x0 = a.x0 + int(tile % unsigned(a.tiles_x)) * 8;
-                    blk_y0 = a.y0 + int(tile / unsigned(a.tiles_x)) * 4;
+                    // tile-major: the blocks of a tile slot are consecutive (sample index in the low bits); the slot's tile
+                    // comes from the order array (natural or heaviest-first), packed as (tile y << 16 | tile x)
+                    blk_sj = int(b & ((1u << a.sample_bits) - 1u));
+                    if (blk_sj >= a.n_samples) continue;           // padding of a non-power-of-two sample count
+                    const unsigned txy = __ldg(a.tile_order + (b >> a.sample_bits));
+                    blk_x0 = a.x0 + int(txy & 0xffffu) * 8;
+                    blk_y0 = a.y0 + int(txy >> 16) * 4;
                     // all 32 lanes prepare the block: lane i seeds sample (pixel i of the tile, sample blk_sj)
                     // (pathtracer_brick.glsl:28-30: TEA seed, two jitter draws, view direction)
                     const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
-                    const bool inside = ix < a.x1 && iy < a.y1;
                     uint32_t sd = tea32(uint32_t(a.p.seed) * uint32_t(iy * W + ix), uint32_t(a.first_sample + blk_sj));
                     const float jx = rng(sd), jy = rng(sd);
                     const float3 vd = view_dir<MT>(a, ix, iy, jx, jy);
                     __syncwarp();
                     prep[lane] = make_float4(vd.x, vd.y, vd.z, __uint_as_float(sd));
                     __syncwarp();
-                    blk_mask = __ballot_sync(FULL, inside);
-                    continue;
+                    blk_next = 0;
                 }
-                // the r-th wanting lane takes the r-th remaining sample of the block
-                const int rank = __popc(m_want & ((1u << lane) - 1u));
-                unsigned took = 0u;
-                if (want && rank < __popc(blk_mask)) {
-                    const int i = int(__fns(blk_mask, 0, rank + 1));
-                    took = 1u << i;
-                    const float4 pr = prep[i];
+                // the r-th wanting lane takes the r-th remaining sample of the block (samples of a border tile that fall
+                // outside the image are dropped and the lane asks again)
+                const int i = blk_next + __popc(m_want & ((1u << lane) - 1u));
+                if (want && i < 32) {
                     px = blk_x0 + (i & 7);
                     py = blk_y0 + (i >> 3);
-                    sj = blk_sj;
-                    seed = __float_as_uint(pr.w);
-                    dir = f3(pr.x, pr.y, pr.z);
-                    have_item = true;
-                    want = false;
+                    if (px < a.x1 && py < a.y1) {
+                        const float4 pr = prep[i];
+                        sj = blk_sj;
+                        seed = __float_as_uint(pr.w);
+                        dir = f3(pr.x, pr.y, pr.z);
+                        have_item = true;
+                        want = false;
+                    }
                 }
-                blk_mask &= ~__reduce_or_sync(FULL, took);
+                blk_next += __popc(m_want);
             }
             // new sample: camera ray of the prepared sample
             if (mine && have_item) {

@@ -84,6 +84,7 @@ struct vrb_ctx {
     int tile_capacity = 0;
     uint64_t cost_key = 0;       // view the costs in tile_cost belong to (0 = none)
     bool lpt = true;             // VRB200_LPT=0 disables
+    int tile_coords_tx = 0;      // tiles_x the packed coordinates in tile_iota were made for
     bool counting = false;
     int kernel = 0;            // 0 = persistent FastMath (production), 1 = simple strict cross-check, 2 = persistent StrictMath
     int trace_blocks[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -660,7 +661,8 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     // ---- heaviest tiles first: order the blocks by the per-tile cost the previous launch of this view measured ----
     const bool lpt = ctx->lpt && !ctx->counting && ctx->kernel == 0;
     uint64_t vkey = key;
-    if (lpt) {
+    if (a.tiles_x >= 65536 || n_tiles / a.tiles_x >= 65536) return fail(ctx, VRB_ERR_INVALID, "image too large");
+    {
         // the cost landscape depends on everything but the seed and the sample range
         auto mix2 = [&vkey](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); for (size_t i = 0; i < n; ++i) { vkey ^= b[i]; vkey *= 1099511628211ull; } };
         vrb_params pk = *params;
@@ -669,7 +671,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         mix2(&a.x0, 4 * sizeof(int));
         mix2(&ctx->env_w, sizeof(int));
         if (vkey == 0) vkey = 1;
-        if (n_tiles > ctx->tile_capacity) {
+        if (n_tiles > ctx->tile_capacity || a.tiles_x != ctx->tile_coords_tx) {
             cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
             ctx->tile_cost = ctx->tile_cost_sorted = nullptr; ctx->tile_iota = ctx->tile_order = nullptr; ctx->sort_tmp = nullptr;
             ctx->tile_capacity = 0; ctx->cost_key = 0;
@@ -680,9 +682,10 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             ctx->sort_tmp_bytes = 0;
             CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, ctx->sort_tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
             CK(cudaMalloc(&ctx->sort_tmp, ctx->sort_tmp_bytes ? ctx->sort_tmp_bytes : 16));
-            k_iota<<<grid_for(size_t(n_tiles), 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->tile_iota, size_t(n_tiles));
+            k_tile_coords<<<grid_for(size_t(n_tiles), 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->tile_iota, size_t(n_tiles), uint32_t(a.tiles_x));
             CK_LAUNCH();
             ctx->tile_capacity = n_tiles;
+            ctx->tile_coords_tx = a.tiles_x;
         }
     }
     const int variant = (tf ? 1 : 0) | (ctx->counting ? 2 : 0) | (ctx->kernel == 2 ? 4 : 0);
@@ -707,9 +710,11 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         a.first_sample = s0;
         a.n_samples = std::min(pass, first_end - s0);
         // 32-bit block counter: tiles * samples blocks per pass (a pass holds at most 2^30 / 16 sample-pixels)
-        a.n_jobs = n_tiles * a.n_samples;
+        a.sample_bits = 0;
+        while ((1 << a.sample_bits) < a.n_samples) ++a.sample_bits;
+        a.n_jobs = n_tiles << a.sample_bits;
         CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
-        a.tile_order = nullptr;
+        a.tile_order = ctx->tile_iota;       // natural order
         a.tile_cost = nullptr;
         if (lpt) {
             if (ctx->cost_key == vkey) {      // the previous pass / launch measured this view
@@ -721,7 +726,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, ctx->stream));
             a.tile_cost = ctx->tile_cost;
         }
-        const int needed = (a.n_jobs + (VR_TRACE_BLOCK / 32) - 1) / (VR_TRACE_BLOCK / 32);
+        const int needed = (n_tiles * a.n_samples + (VR_TRACE_BLOCK / 32) - 1) / (VR_TRACE_BLOCK / 32);
         const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
         void* kargs[] = { (void*)&a };
         CK(cudaLaunchKernel(fn, dim3(blocks), dim3(VR_TRACE_BLOCK), kargs, 0, ctx->stream));
