@@ -70,47 +70,64 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons DURING the timed region, polled through NVML every few ms from a thread (the timed
+    region of a short run is shorter than one `nvidia-smi -lms` period); falls back to nvidia-smi when NVML is missing."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index=0):
-        self.index, self.samples, self.proc = index, [], None
+    def __init__(self, index=0, period_s=0.002):
+        self.index, self.period, self.sm, self.mask, self.max_mhz = index, period_s, [], 0, None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: match by PCI bus id of the torch device when possible
+            import torch
+            try:
+                bus = torch.cuda.get_device_properties(index).pci_bus_id
+                dom = getattr(torch.cuda.get_device_properties(index), "pci_domain_id", 0)
+                dev = getattr(torch.cuda.get_device_properties(index), "pci_device_id", 0)
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                try:
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                except Exception:
+                    pass
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.samples.append(ln.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 6:
-                continue
+        if self.nvml is None:
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                f = [x.strip() for x in subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                                       capture_output=True, text=True, timeout=10).stdout.strip().split(",")]
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "reasons": [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")],
+                        "samples": 1, "how": "nvidia-smi once after the timed region (NVML unavailable)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        self.stop_flag.set()
+        self.thread.join(timeout=1)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(k for k, bit in self.REASONS.items() if self.mask & bit), "samples": len(self.sm), "how": "NVML poll every 2 ms during the timed region"}
 
 
 def run_reference(args, rank, world):
@@ -273,7 +290,19 @@ def main():
     value = samples_per_step * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ----
-    host_img = np.empty((H, W, 4), np.float32)
+    # pinned host buffers for everything that crosses PCIe inside the timed region
+    pinned = []
+
+    def pin(arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        pinned.append(t)
+        return t.numpy()
+
+    import copy
+    grid = copy.copy(grid)
+    grid.indirection, grid.range, grid.atlas, grid.mips = pin(grid.indirection), pin(grid.range), pin(grid.atlas), [pin(m) for m in grid.mips]
+    env, lut = pin(env), pin(lut)
+    host_img = pin(np.empty((H, W, 4), np.float32))
     h2d = grid.indirection.nbytes + grid.range.nbytes + grid.atlas.nbytes + sum(m.nbytes for m in grid.mips) + env.nbytes + lut.nbytes
     d2h = host_img.nbytes if rank == 0 else 0
 
@@ -318,7 +347,7 @@ def main():
                 "note": "latency-bound gather workload on an L2-resident volume: see DESIGN.md for the L2 roofline",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": args.steps * 1,
+            "gpu_launches": args.steps * 2,     # per step: k_trace_persistent + k_fold (the tile sort is cub, memsets are not kernels of ours)
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

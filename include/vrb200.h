@@ -169,6 +169,10 @@ int vrb_trace_deterministic(vrb_ctx* ctx, const vrb_params* params);
  * 1 = the straightforward one-thread-per-pixel kernel with IEEE math; 2 = the persistent kernel with IEEE math.
  * 1 and 2 are cross-checks: 2 must reproduce 1 (same paths, same counters), 0 is compared statistically */
 int vrb_set_kernel(vrb_ctx* ctx, int kind);
+/* scheduling options of the production kernel (none changes the image): "lpt" (heaviest tiles first, default 1),
+ * "cull" (screen-space culling of the volume's box when the environment is hidden, default 1), "pass" (samples per
+ * pixel and internal pass, default 16). Environment variables VRB200_LPT / VRB200_CULL / VRB200_PASS set the defaults. */
+int vrb_set_option(vrb_ctx* ctx, const char* name, int value);
 /* color *= s (finalise VRB_ACCUM_SUM buffers) */
 int vrb_scale(vrb_ctx* ctx, float s);
 /* zero the colour buffer */

@@ -244,3 +244,28 @@ def test_persistent_kernel_equals_simple_kernel(smoke_ctx, oracle, smoke_grid, l
     print(f"bit-identical pixels persistent vs simple (tf={use_tf}): {same:.5f}")
     assert same > (0.99 if use_tf else 0.999)     # TF: the in-brick trilinear fast path contracts its FMAs differently
     assert np.allclose(out[0], out[1], rtol=1e-5, atol=1e-6)
+
+
+def test_scheduling_options_do_not_change_the_image(smoke_ctx, oracle, smoke_grid, lut_raw):
+    """Heaviest-tiles-first order, screen-space box culling and the pass size are pure scheduling: bit-identical images."""
+    W, H = 200, 120                               # not a multiple of the 8x4 tile: border tiles
+    lut, _ = oracle.lut_upload(lut_raw)
+    smoke_ctx.tf_upload(lut)
+    smoke_ctx.resize(W, H)
+    for p in (default_scene(smoke_grid, W, H, bounces=8, use_tf=True),                  # environment hidden: culling is active
+              readme_scene(smoke_grid, W, H, bounces=8)):
+        images = []
+        for lpt, cull, npass in ((1, 1, 16), (0, 0, 16), (1, 1, 3), (0, 1, 1)):
+            smoke_ctx.set_option("lpt", lpt); smoke_ctx.set_option("cull", cull); smoke_ctx.set_option("pass", npass)
+            smoke_ctx.clear()
+            smoke_ctx.trace(p, 1, 5)
+            smoke_ctx.trace(p, 6, 5)              # the second launch of the same view uses the measured tile costs
+            images.append(smoke_ctx.download_color())
+        for img in images[1:]:
+            assert np.array_equal(images[0], img)
+        # a pixel row far from the volume is exactly zero with the environment hidden
+        if not p.show_environment:
+            assert np.all(images[0][0] == 0)
+    smoke_ctx.set_option("lpt", 1); smoke_ctx.set_option("cull", 1); smoke_ctx.set_option("pass", 16)
+    with pytest.raises(Exception):
+        smoke_ctx.set_option("nonsense", 1)

@@ -13,6 +13,8 @@
 //   * when a warp switches to a new block ALL 32 lanes prepare it together -- TEA seed (32 rounds, the largest single
 //     cost of a short path), pixel jitter and view direction of the block's 32 samples go to shared memory -- instead of
 //     each lane seeding its own sample whenever it happens to become free (17 of 32 lanes active before);
+//   * with a hidden environment, tiles whose pixels cannot see the volume's bounding box (host-side conservative
+//     projection of the box, one pixel of margin) are written as zeros without seeding or tracing anything;
 //   * blocks are issued HEAVIEST TILE FIRST when the previous launch of the same view left per-tile costs (cycles a
 //     sample occupied its lane), so the last blocks of a launch are the cheap ones;
 //   * camera segments and shadow rays share ONE brick-DDA loop body (common.glsl:412-501 differ only in what
@@ -308,9 +310,15 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                     const unsigned txy = __ldg(a.tile_order + (b >> a.sample_bits));
                     blk_x0 = a.x0 + int(txy & 0xffffu) * 8;
                     blk_y0 = a.y0 + int(txy >> 16) * 4;
+                    const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
+                    if (a.cull && (blk_x0 > a.cull_x1 || blk_x0 + 7 < a.cull_x0 || blk_y0 > a.cull_y1 || blk_y0 + 3 < a.cull_y0)) {
+                        // no ray of this tile can reach the volume's box and the environment is hidden: every sample of the
+                        // block is (0, 0, 0, 0) (trace_path returns L = 0, n_paths = 0) -- no seed, no ray
+                        if (ix < a.x1 && iy < a.y1) a.lbuf[size_t(blk_sj) * a.lbuf_stride + size_t(iy) * W + ix] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        continue;
+                    }
                     // all 32 lanes prepare the block: lane i seeds sample (pixel i of the tile, sample blk_sj)
                     // (pathtracer_brick.glsl:28-30: TEA seed, two jitter draws, view direction)
-                    const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
                     uint32_t sd = tea32(uint32_t(a.p.seed) * uint32_t(iy * W + ix), uint32_t(a.first_sample + blk_sj));
                     const float jx = rng(sd), jy = rng(sd);
                     const float3 vd = view_dir<MT>(a, ix, iy, jx, jy);

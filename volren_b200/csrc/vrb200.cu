@@ -65,6 +65,7 @@ struct vrb_ctx {
     uchar4* ldr = nullptr;
     std::map<int, Frame> frames;
     float4* env_rgb = nullptr;
+    float* env_stage = nullptr;      // RGB staging of vrb_env_upload (kept while the size stays the same)
     int env_w = 0, env_h = 0;
     float* impmap = nullptr;
     float4* lut = nullptr;
@@ -84,6 +85,7 @@ struct vrb_ctx {
     int tile_capacity = 0;
     uint64_t cost_key = 0;       // view the costs in tile_cost belong to (0 = none)
     bool lpt = true;             // VRB200_LPT=0 disables
+    bool cull = true;            // VRB200_CULL=0 disables the screen-space box culling
     int tile_coords_tx = 0;      // tiles_x the packed coordinates in tile_iota were made for
     bool counting = false;
     int kernel = 0;            // 0 = persistent FastMath (production), 1 = simple strict cross-check, 2 = persistent StrictMath
@@ -137,18 +139,21 @@ inline int grid_for(size_t n, int block, int sm_count, int per_sm = 16) {
 size_t mip_words(const uint3& nb, int level) { return size_t(nb.x >> (level + 1)) * (nb.y >> (level + 1)) * (nb.z >> (level + 1)); }
 
 // builds the tracer layout (records + brick-linear atlas) from the canonical buffers
-int finalize_grid(vrb_ctx* ctx, DeviceGrid& g) {
+int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
     const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
     const uint3 ab = make_uint3(g.atlas_dim.x >> 3, g.atlas_dim.y >> 3, g.atlas_dim.z >> 3);
     g.n_slots = size_t(ab.x) * ab.y * ab.z;
-    CK(cudaMalloc(&g.rec, n * sizeof(uint2)));
     if (g.n_slots >= 0xffffffffull) return fail(ctx, VRB_ERR_INVALID, "atlas too large");
-    CK(cudaMalloc(&g.atlas_lin, (g.n_slots + 1) * 512));
+    if (!reuse) {
+        CK(cudaMalloc(&g.rec, n * sizeof(uint2)));
+        CK(cudaMalloc(&g.atlas_lin, (g.n_slots + 1) * 512));
+        CK(cudaMalloc(&g.recp, size_t(g.nb.x + 2) * (g.nb.y + 2) * (g.nb.z + 2) * sizeof(uint2)));
+    }
+    g.maj_key = 0;   // the majorant tables (if any) belong to the previous contents
     CK(cudaMemsetAsync(g.atlas_lin + g.n_slots * 512, 0, 512, ctx->stream));   // the all-zero brick
     k_make_records<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.indirection, g.range, n, ab, g.rec);
     CK_LAUNCH();
     const size_t np = size_t(g.nb.x + 2) * (g.nb.y + 2) * (g.nb.z + 2);
-    CK(cudaMalloc(&g.recp, np * sizeof(uint2)));
     k_make_records_padded<<<grid_for(np, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.rec, g.nb, uint32_t(g.n_slots), g.recp);
     CK_LAUNCH();
     if (g.n_slots) {
@@ -336,6 +341,7 @@ int vrb_create(int device, vrb_ctx** out) {
     }
     ctx->stream = ctx->own_stream;
     if (const char* e = getenv("VRB200_LPT")) ctx->lpt = atoi(e) != 0;
+    if (const char* e = getenv("VRB200_CULL")) ctx->cull = atoi(e) != 0;
     if (const char* e = getenv("VRB200_PASS")) ctx->pass_samples = std::max(1, atoi(e));
     cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream);
     *out = ctx;
@@ -349,7 +355,7 @@ void vrb_destroy(vrb_ctx* ctx) {
     for (auto& f : ctx->frames) { free_grid(f.second.slot[0]); free_grid(f.second.slot[1]); }
     if (!ctx->color_external) cudaFree(ctx->color);
     cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
-    cudaFree(ctx->lbuf);
+    cudaFree(ctx->lbuf); cudaFree(ctx->env_stage);
     cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -435,25 +441,29 @@ int vrb_grid_upload_brick(vrb_ctx* ctx, int slot, int frame, const vrb_brick_vie
     if (atlas_bytes && !v->atlas) return fail(ctx, VRB_ERR_INVALID, "atlas is NULL");
     DeviceGuard guard(ctx->device);
     DeviceGrid& g = ctx->frames[frame].slot[slot];
-    CK(cudaStreamSynchronize(ctx->stream));
-    free_grid(g);
+    // same shape as what the slot already holds (re-upload of an animation frame, progressive edits): keep the allocations
+    const bool reuse = g.valid && g.nb.x == v->n_bricks[0] && g.nb.y == v->n_bricks[1] && g.nb.z == v->n_bricks[2] &&
+                       g.atlas_dim.x == v->atlas_dim[0] && g.atlas_dim.y == v->atlas_dim[1] && g.atlas_dim.z == v->atlas_dim[2];
+    if (!reuse) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        free_grid(g);
+    }
     g.nb = make_uint3(v->n_bricks[0], v->n_bricks[1], v->n_bricks[2]);
     g.atlas_dim = make_uint3(v->atlas_dim[0], v->atlas_dim[1], v->atlas_dim[2]);
     g.brick_count = v->brick_count;
     const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
-    CK(cudaMalloc(&g.indirection, n * 4));
-    CK(cudaMalloc(&g.range, n * 4));
-    CK(cudaMalloc(&g.atlas, atlas_bytes ? atlas_bytes : 8));
+    if (!reuse) {
+        CK(cudaMalloc(&g.indirection, n * 4));
+        CK(cudaMalloc(&g.range, n * 4));
+        CK(cudaMalloc(&g.atlas, atlas_bytes ? atlas_bytes : 8));
+        for (int i = 0; i < 3; ++i) CK(cudaMalloc(&g.mips[i], mip_words(g.nb, i) * 4));
+    }
     CK(cudaMemcpyAsync(g.indirection, v->indirection, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(g.range, v->range, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (atlas_bytes) CK(cudaMemcpyAsync(g.atlas, v->atlas, atlas_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    for (int i = 0; i < 3; ++i) {
-        const size_t words = mip_words(g.nb, i);
-        CK(cudaMalloc(&g.mips[i], words * 4));
-        CK(cudaMemcpyAsync(g.mips[i], v->range_mips[i], words * 4, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    st = finalize_grid(ctx, g);
-    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) CK(cudaMemcpyAsync(g.mips[i], v->range_mips[i], mip_words(g.nb, i) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    st = finalize_grid(ctx, g, reuse);
+    CK(cudaStreamSynchronize(ctx->stream));   // host buffers are only borrowed for the duration of the call
     return st;
 }
 
@@ -541,13 +551,16 @@ int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h) {
     if (!ctx) return VRB_ERR_INVALID;
     if (!rgb || w <= 0 || h <= 0) return fail(ctx, VRB_ERR_INVALID, "bad environment map");
     DeviceGuard guard(ctx->device);
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->env_rgb); ctx->env_rgb = nullptr;
     if (!ctx->impmap) CK(cudaMalloc(&ctx->impmap, size_t(imp_offset(IMP_LEVELS)) * 4));
     const size_t n = size_t(w) * h;
-    float* d_rgb = nullptr;
-    CK(cudaMalloc(&d_rgb, n * 12));
-    CK(cudaMalloc(&ctx->env_rgb, n * sizeof(float4)));
+    if (!ctx->env_rgb || ctx->env_w != w || ctx->env_h != h) {     // same size as before: keep the allocations
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->env_rgb); cudaFree(ctx->env_stage);
+        ctx->env_rgb = nullptr; ctx->env_stage = nullptr;
+        CK(cudaMalloc(&ctx->env_stage, n * 12));
+        CK(cudaMalloc(&ctx->env_rgb, n * sizeof(float4)));
+    }
+    float* d_rgb = ctx->env_stage;
     CK(cudaMemcpyAsync(d_rgb, rgb, n * 12, cudaMemcpyHostToDevice, ctx->stream));
     k_env_pad<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(d_rgb, ctx->env_rgb, n);
     CK_LAUNCH();
@@ -561,8 +574,7 @@ int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h) {
         k_env_mip<<<grid, block, 0, ctx->stream>>>(ctx->impmap + imp_offset(l - 1), d * 2, ctx->impmap + imp_offset(l), d);
         CK_LAUNCH();
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_rgb);
+    CK(cudaStreamSynchronize(ctx->stream));   // host buffer is only borrowed for the duration of the call
     return VRB_OK;
 }
 
@@ -581,9 +593,11 @@ int vrb_tf_upload(vrb_ctx* ctx, const float* rgba, uint32_t n) {
     if (!ctx) return VRB_ERR_INVALID;
     if (!rgba || n == 0) return fail(ctx, VRB_ERR_INVALID, "empty LUT");
     DeviceGuard guard(ctx->device);
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->lut); ctx->lut = nullptr;
-    CK(cudaMalloc(&ctx->lut, size_t(n) * 16));
+    if (!ctx->lut || ctx->tf_size != n) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->lut); ctx->lut = nullptr;
+        CK(cudaMalloc(&ctx->lut, size_t(n) * 16));
+    }
     CK(cudaMemcpyAsync(ctx->lut, rgba, size_t(n) * 16, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->tf_size = n;
@@ -658,6 +672,34 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     }
     a.lbuf = ctx->lbuf;
     a.lbuf_stride = n_px;
+    // ---- screen-space culling of the volume's box (hidden environment only; never in the counting build) ----
+    a.cull = 0;
+    if (!params->show_environment && !ctx->counting && ctx->cull) {
+        // view_dir (common.glsl:76-80): dir ~ cam_transform * (px, py, z), px = (x + jitter - w/2) / h, z = -0.5 / tan(fov/2).
+        // A box corner c maps to v = cam_transform^-1 (c - cam_pos); in front of the camera (v.z < 0) it projects to
+        // px = v.x * z / v.z. The bounding rectangle of the 8 projections (+ 1 pixel) contains every pixel that can hit.
+        const float* T = params->cam_transform;   // column-major, orthonormal up to rounding: inverse = transpose
+        const double z = -0.5 / std::tan(0.5 * M_PI * double(params->cam_fov) / 180.0), w = ctx->w, h = ctx->h;
+        double xmin = 1e30, xmax = -1e30, ymin = 1e30, ymax = -1e30;
+        bool ok = std::isfinite(z);
+        for (int k = 0; k < 8 && ok; ++k) {
+            const double c[3] = { double(k & 1 ? params->vol_bb_max[0] : params->vol_bb_min[0]) - params->cam_pos[0],
+                                  double(k & 2 ? params->vol_bb_max[1] : params->vol_bb_min[1]) - params->cam_pos[1],
+                                  double(k & 4 ? params->vol_bb_max[2] : params->vol_bb_min[2]) - params->cam_pos[2] };
+            const double vx = T[0] * c[0] + T[1] * c[1] + T[2] * c[2], vy = T[3] * c[0] + T[4] * c[1] + T[5] * c[2], vz = T[6] * c[0] + T[7] * c[1] + T[8] * c[2];
+            if (!(vz < -1e-4)) { ok = false; break; }       // a corner beside / behind the camera: no culling
+            const double sx = vx * z / vz * h + 0.5 * w, sy = vy * z / vz * h + 0.5 * h;
+            xmin = std::min(xmin, sx); xmax = std::max(xmax, sx); ymin = std::min(ymin, sy); ymax = std::max(ymax, sy);
+        }
+        // orthonormality check of cam_transform (the transpose is only its inverse then)
+        const double d01 = T[0] * T[3] + T[1] * T[4] + T[2] * T[5], d00 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2], d22 = T[6] * T[6] + T[7] * T[7] + T[8] * T[8];
+        if (std::fabs(d01) > 1e-4 || std::fabs(d00 - 1) > 1e-4 || std::fabs(d22 - 1) > 1e-4) ok = false;
+        if (ok && std::isfinite(xmin + xmax + ymin + ymax)) {
+            a.cull = 1;
+            a.cull_x0 = int(std::floor(std::max(-1e9, xmin))) - 2; a.cull_x1 = int(std::ceil(std::min(1e9, xmax))) + 1;
+            a.cull_y0 = int(std::floor(std::max(-1e9, ymin))) - 2; a.cull_y1 = int(std::ceil(std::min(1e9, ymax))) + 1;
+        }
+    }
     // ---- heaviest tiles first: order the blocks by the per-tile cost the previous launch of this view measured ----
     const bool lpt = ctx->lpt && !ctx->counting && ctx->kernel == 0;
     uint64_t vkey = key;
@@ -734,6 +776,16 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         k_fold<<<grid_for(n_region, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(ctx->color, ctx->lbuf, n_px, ctx->w, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode);
         CK_LAUNCH();
     }
+    return VRB_OK;
+}
+
+int vrb_set_option(vrb_ctx* ctx, const char* name, int value) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!name) return fail(ctx, VRB_ERR_INVALID, "NULL option name");
+    if (!strcmp(name, "lpt")) ctx->lpt = value != 0;
+    else if (!strcmp(name, "cull")) ctx->cull = value != 0;
+    else if (!strcmp(name, "pass")) { if (value < 1) return fail(ctx, VRB_ERR_INVALID, "pass must be >= 1"); ctx->pass_samples = value; }
+    else return fail(ctx, VRB_ERR_INVALID, "unknown option '%s'", name);
     return VRB_OK;
 }
 
