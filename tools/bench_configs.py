@@ -1,0 +1,173 @@
+"""The other BASELINE.json configs on one GPU, as measurements next to bench.py's headline (configs[1]):
+
+  C1  smoke.brick + hdr, 1024x1024, README command (non-TF kernel, environment visible)
+  C3  synthetic 1024^3 fBm cloud -> GPU brick build -> 1920x1080, density 100, albedo .8 (atlas ~ 1 GiB: HBM-resident)
+  C4  synthetic 512x512x1800 CT-like grid + 256-entry RGBA LUT (TF kernel), 1920x1080
+
+    python tools/bench_configs.py [--configs C1,C3,C4] [--scale 1.0] [--spp 16] [--launches 4]
+
+Per config one JSON line: brick-build time and GB/s (algorithmic bytes: 1 B/voxel read + 1 B/allocated voxel written +
+8 B/brick), samples/s of the tracking kernel, event counters per sample and the algorithmic GB/s they imply.
+Synthetic volumes are generated on the device with torch (no host copy of a 1 GiB grid).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+import volren_b200 as vr  # noqa: E402
+from volren_b200 import formats, scene  # noqa: E402
+from helpers import readme_scene  # noqa: E402
+
+A = os.path.join(ROOT, "tests", "golden", "assets")
+
+
+def fbm_cloud(n, seed=42, octaves=5, base=4, threshold=0.30):
+    """5-octave value-noise fBm (lacunarity 2, gain .5, base frequency 4) x smoothstep radial falloff, max(0, f - 0.45) -> u8 [z][y][x]."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    acc = torch.zeros((1, 1, n, n, n), device="cuda", dtype=torch.float16)
+    amp, norm = 0.5, 0.0
+    for o in range(octaves):
+        f = base * 2 ** o
+        lattice = torch.rand((1, 1, f + 1, f + 1, f + 1), device="cuda", generator=g, dtype=torch.float32).half()
+        acc += amp * F.interpolate(lattice, size=(n, n, n), mode="trilinear", align_corners=True)
+        norm += amp
+        amp *= 0.5
+    acc /= norm
+    ax = torch.linspace(-1, 1, n, device="cuda", dtype=torch.float16)
+    r = torch.sqrt(ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2)
+    t = ((1.0 - r) / 0.6).clamp(0, 1)
+    fall = t * t * (3 - 2 * t)
+    d = (acc[0, 0] * fall - threshold).clamp_(min=0)
+    d /= d.max()
+    return (d * 255).round().to(torch.uint8).contiguous()
+
+
+def ct_phantom(w, h, d, seed=42):
+    """Nested ellipsoid body (.25), cylinder bones (.8), sphere organs (.45), + U(-.02, .02) noise, air 0 -> u8 [z][y][x]."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    z = torch.linspace(-1, 1, d, device="cuda", dtype=torch.float16)[:, None, None]
+    y = torch.linspace(-1, 1, h, device="cuda", dtype=torch.float16)[None, :, None]
+    x = torch.linspace(-1, 1, w, device="cuda", dtype=torch.float16)[None, None, :]
+    v = torch.zeros((d, h, w), device="cuda", dtype=torch.float16)
+    body = (x / 0.8) ** 2 + (y / 0.6) ** 2 + (z / 0.95) ** 2 < 1
+    v[body] = 0.25
+    for cx, cy in ((-0.3, 0.0), (0.3, 0.0), (0.0, 0.35)):
+        v[((x - cx) ** 2 + (y - cy) ** 2 < 0.006).expand_as(v) & body] = 0.8
+    for cx, cy, cz, rr in ((0.25, -0.2, 0.3, 0.2), (-0.3, 0.15, -0.2, 0.25), (0.0, -0.1, -0.6, 0.18)):
+        v[((x - cx) ** 2 + (y - cy) ** 2 + (z - cz) ** 2 < rr * rr)] = 0.45
+    noise = (torch.rand((d, h, w), device="cuda", generator=g, dtype=torch.float32).half() - 0.5) * 0.04
+    v = torch.where(v > 0, (v + noise).clamp(0, 1), v)
+    return (v * 255).round().to(torch.uint8).contiguous()
+
+
+def turbo_like_lut(n=256):
+    """RGBA LUT with alpha = i / n (transferfunc.cpp:69-77 shape); colours from a simple blue-green-red ramp."""
+    f = np.arange(n, dtype=np.float32) / n
+    rgb = np.stack([np.clip(1.5 - np.abs(4 * f - 3), 0, 1), np.clip(1.5 - np.abs(4 * f - 2), 0, 1), np.clip(1.5 - np.abs(4 * f - 1), 0, 1)], -1)
+    return np.concatenate([rgb, f[:, None]], -1).astype(np.float32)
+
+
+class DenseInfo:
+    def __init__(self, dims_whd):
+        self.dims, self.min_maj = dims_whd, (0.0, 1.0)
+
+    def matrix(self):
+        return np.eye(4, dtype=np.float32)
+
+    def index_extent(self):
+        return self.dims
+
+
+def timed(fn):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b)
+
+
+def alg_bytes(c, tf):
+    per_maj, per_dens = (36, 104) if tf else (4, 9)
+    return per_maj * c["n_maj"] + per_dens * c["n_dens"] + 9 * c["n_emis"] + 200 * c["n_nee"] + 100 * c["n_env"] + 32 * c["n_samples"]
+
+
+def run(name, ctx, params, W, H, tf, spp, launches, extra):
+    ctx.resize(W, H)
+    ctx.set_counting(True)
+    ctx.trace(params, 1, 2)
+    c = ctx.get_counters().as_dict()
+    ctx.set_counting(False)
+    n = c["n_samples"]
+    per = {k: v / n for k, v in c.items()}
+    ctx.clear()
+    ms = [timed(lambda i=i: ctx.trace(params, 1 + i * spp, spp)) for i in range(launches)]
+    best = min(ms[1:]) if launches > 1 else ms[0]
+    sps = W * H * spp / (best * 1e-3)
+    out = dict(config=name, resolution=[W, H], spp_per_launch=spp, ms_per_launch=best, samples_per_s=sps, counters_per_sample=per,
+               algorithmic_bytes_per_sample=alg_bytes(c, tf) / n, algorithmic_GBps=alg_bytes(c, tf) / n * sps / 1e9, **extra)
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="C1,C3,C4")
+    ap.add_argument("--scale", type=float, default=1.0, help="scales the synthetic grid edge (1.0 = the named sizes)")
+    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--launches", type=int, default=4)
+    a = ap.parse_args()
+    ctx = vr.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    env = formats.load_hdr(os.path.join(A, "table_mountain_2_puresky_1k.hdr"))
+    ctx.env_upload(env)
+    for name in a.configs.split(","):
+        ctx.grid_clear()
+        if name == "C1":
+            grid = formats.load_brick(os.path.join(A, "smoke.brick"))
+            ctx.grid_upload_brick(grid)
+            run("C1 smoke.brick + hdr, README command", ctx, readme_scene(grid, 1024, 1024), 1024, 1024, False, a.spp, a.launches, {})
+            continue
+        if name == "C3":
+            n = int(1024 * a.scale) // 8 * 8
+            vox = fbm_cloud(n)
+            dims, tf, label = (n, n, n), False, f"C3 synthetic {n}^3 fBm cloud"
+        else:
+            w, d = int(512 * a.scale) // 8 * 8, int(1800 * a.scale) // 8 * 8
+            vox = ct_phantom(w, w, d)
+            dims, tf, label = (w, w, d), True, f"C4 synthetic {w}x{w}x{d} CT phantom + 256-entry LUT"
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()          # the generator's temporaries go back to the driver before the pool grows
+        build_first_ms = timed(lambda: ctx.grid_build_from_dense_device(vox.data_ptr(), dims, 0.0, 1.0))
+        build_ms = min(timed(lambda: ctx.grid_build_from_dense_device(vox.data_ptr(), dims, 0.0, 1.0)) for _ in range(3))
+        nb, _, count = ctx.grid_info()
+        n_vox = dims[0] * dims[1] * dims[2]
+        n_bricks = nb[0] * nb[1] * nb[2]
+        build_bytes = n_vox + count * 512 + 8 * n_bricks
+        extra = dict(grid=list(dims), n_bricks=list(nb), bricks_allocated=count, atlas_MiB=count * 512 / 2 ** 20,
+                     build_first_ms=build_first_ms, build_ms=build_ms, build_algorithmic_GBps=build_bytes / (build_ms * 1e-3) / 1e9)
+        del vox
+        torch.cuda.empty_cache()
+        s = scene.RenderSettings(bounces=128, albedo=(.8, .8, .8), use_transferfunc=tf, show_environment=not tf)
+        g = DenseInfo(dims)
+        scene.scale_and_move_to_unit_cube(g.matrix(), g.index_extent(), s)
+        if not tf:
+            s.density_scale = 100.0
+        else:
+            ctx.tf_upload(turbo_like_lut())
+        p = scene.make_params(1920, 1080, scene.Camera(), s, g.matrix(), g.index_extent(), g.min_maj)
+        run(label, ctx, p, 1920, 1080, tf, a.spp, a.launches, extra)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -122,11 +122,17 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-void free_grid(DeviceGrid& g) {
-    cudaFree(g.indirection); cudaFree(g.range); cudaFree(g.atlas);
-    for (auto& m : g.mips) cudaFree(m);
-    cudaFree(g.rec); cudaFree(g.recp); cudaFree(g.atlas_lin);
-    for (auto& m : g.maj) cudaFree(m);
+// Grid storage and build scratch come from the device's stream-ordered pool (release threshold raised in vrb_create):
+// after the first build of a given size an allocation or free costs microseconds instead of the 0.1-1 ms of a
+// cudaMalloc / cudaFree of hundreds of MiB (the brick build of a 1024^3 grid spent 26 of its 29 ms there).
+template <typename T> cudaError_t pool_alloc(T** p, size_t bytes, cudaStream_t s) { return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, s); }
+inline void pool_free(void* p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
+
+void free_grid(DeviceGrid& g, cudaStream_t s) {
+    pool_free(g.indirection, s); pool_free(g.range, s); pool_free(g.atlas, s);
+    for (auto& m : g.mips) pool_free(m, s);
+    pool_free(g.rec, s); pool_free(g.recp, s); pool_free(g.atlas_lin, s);
+    for (auto& m : g.maj) pool_free(m, s);
     g = DeviceGrid();
 }
 
@@ -145,9 +151,9 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
     g.n_slots = size_t(ab.x) * ab.y * ab.z;
     if (g.n_slots >= 0xffffffffull) return fail(ctx, VRB_ERR_INVALID, "atlas too large");
     if (!reuse) {
-        CK(cudaMalloc(&g.rec, n * sizeof(uint2)));
-        CK(cudaMalloc(&g.atlas_lin, (g.n_slots + 1) * 512));
-        CK(cudaMalloc(&g.recp, size_t(g.nb.x + 2) * (g.nb.y + 2) * (g.nb.z + 2) * sizeof(uint2)));
+        CK(pool_alloc(&g.rec, n * sizeof(uint2), ctx->stream));
+        CK(pool_alloc(&g.atlas_lin, (g.n_slots + 1) * 512, ctx->stream));
+        CK(pool_alloc(&g.recp, size_t(g.nb.x + 2) * (g.nb.y + 2) * (g.nb.z + 2) * sizeof(uint2), ctx->stream));
     }
     g.maj_key = 0;   // the majorant tables (if any) belong to the previous contents
     CK(cudaMemsetAsync(g.atlas_lin + g.n_slots * 512, 0, 512, ctx->stream));   // the all-zero brick
@@ -189,22 +195,40 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
     if (compute_n_bricks(dim, nb) != VRB_OK)
         return fail(ctx, VRB_ERR_TOO_MANY_BRICKS, "exceeded max brick count of 1024");
     DeviceGrid& g = ctx->frames[frame].slot[slot];
-    free_grid(g);
+    free_grid(g, ctx->stream);
     g.nb = nb;
     const size_t n = size_t(nb.x) * nb.y * nb.z;
     const uint3 vdim = make_uint3(dim[0], dim[1], dim[2]);
     uint32_t *flags = nullptr, *brick_id = nullptr, *block_sums = nullptr;
     unsigned long long* d_total = nullptr;
     const int n_blocks = int((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    CK(cudaMalloc(&g.indirection, n * 4));
-    CK(cudaMalloc(&g.range, n * 4));
-    CK(cudaMalloc(&flags, n * 4));
-    CK(cudaMalloc(&brick_id, n * 4));
-    CK(cudaMalloc(&block_sums, size_t(n_blocks) * 4));
-    CK(cudaMalloc(&d_total, 8));
+    CK(pool_alloc(&g.indirection, n * 4, ctx->stream));
+    CK(pool_alloc(&g.range, n * 4, ctx->stream));
+    CK(pool_alloc(&flags, n * 4, ctx->stream));
+    CK(pool_alloc(&brick_id, n * 4, ctx->stream));
+    CK(pool_alloc(&block_sums, size_t(n_blocks) * 4, ctx->stream));
+    CK(pool_alloc(&d_total, 8, ctx->stream));
     // A: ranges
-    k_brick_range<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_vox, vdim, vmin, vmax, nb, g.range, flags);
-    CK_LAUNCH();
+    if ((dim[0] & 7u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 7u) == 0) {
+        // separable, coalesced reduction over the 12^3 windows (x, then y, then z)
+        uint16_t *m1 = nullptr, *m2 = nullptr;
+        const size_t n1 = size_t(dim[2]) * dim[1] * nb.x, n2 = size_t(dim[2]) * nb.y * nb.x;
+        CK(pool_alloc(&m1, n1 * 2, ctx->stream));
+        CK(pool_alloc(&m2, n2 * 2, ctx->stream));
+        const size_t n_rows = size_t(dim[2]) * dim[1];
+        if (dim[2] > 65535u) return fail(ctx, VRB_ERR_INVALID, "grid too deep");
+        k_range_x<<<dim3(unsigned((n_rows + 7) / 8), (nb.x + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(reinterpret_cast<const uint2*>(d_vox), vdim, nb.x, n_rows, m1);
+        CK_LAUNCH();
+        k_range_y<<<dim3((nb.x + 31) / 32, (nb.y + 7) / 8, dim[2]), dim3(32, 8), 0, ctx->stream>>>(m1, vdim, nb, m2);
+        CK_LAUNCH();
+        k_range_z<<<grid_for(n, 256, ctx->sm_count, 32), 256, 0, ctx->stream>>>(m2, vdim, vmin, vmax, nb, g.range, flags);
+        CK_LAUNCH();
+        pool_free(m1, ctx->stream);
+        pool_free(m2, ctx->stream);
+    } else {
+        k_brick_range<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_vox, vdim, vmin, vmax, nb, g.range, flags);
+        CK_LAUNCH();
+    }
     // B: ordered allocation
     k_scan_block_sums<<<n_blocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, n, block_sums);
     CK_LAUNCH();
@@ -220,11 +244,12 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
     const uint32_t az = 8u * uint32_t(std::round(std::ceil(float(total) / float(nb.x * nb.y))));
     g.atlas_dim = make_uint3(nb.x * 8, nb.y * 8, az);
     const size_t atlas_bytes = size_t(g.atlas_dim.x) * g.atlas_dim.y * g.atlas_dim.z;
-    CK(cudaMalloc(&g.atlas, atlas_bytes ? atlas_bytes : 8));
+    CK(pool_alloc(&g.atlas, atlas_bytes, ctx->stream));
     if (atlas_bytes) CK(cudaMemsetAsync(g.atlas, 0, atlas_bytes, ctx->stream));
     // C: encode
     if (total) {
-        k_brick_encode<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_vox, vdim, vmin, vmax, nb, g.range, brick_id, g.atlas, g.atlas_dim);
+        k_brick_encode<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_vox, vdim, vmin, vmax, nb, g.range, brick_id, g.atlas, g.atlas_dim,
+                                                                                                 ((dim[0] & 7u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 7u) == 0) ? 1 : 0);
         CK_LAUNCH();
     }
     // D: range mips
@@ -233,7 +258,7 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
     for (int i = 0; i < 3; ++i) {
         const uint3 ddim = make_uint3(nb.x >> (i + 1), nb.y >> (i + 1), nb.z >> (i + 1));
         const size_t words = mip_words(nb, i);
-        CK(cudaMalloc(&g.mips[i], words * 4));
+        CK(pool_alloc(&g.mips[i], words * 4, ctx->stream));
         k_range_mip<<<grid_for(words, 256, ctx->sm_count), 256, 0, ctx->stream>>>(src, sdim, g.mips[i], ddim);
         CK_LAUNCH();
         src = g.mips[i];
@@ -241,7 +266,7 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
     }
     const int st = finalize_grid(ctx, g);
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(flags); cudaFree(brick_id); cudaFree(block_sums); cudaFree(d_total);
+    pool_free(flags, ctx->stream); pool_free(brick_id, ctx->stream); pool_free(block_sums, ctx->stream); pool_free(d_total, ctx->stream);
     return st;
 }
 
@@ -340,6 +365,13 @@ int vrb_create(int device, vrb_ctx** out) {
         return VRB_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    {   // keep freed blocks in the stream-ordered pool instead of returning them to the driver at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t threshold = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+    }
     if (const char* e = getenv("VRB200_LPT")) ctx->lpt = atoi(e) != 0;
     if (const char* e = getenv("VRB200_CULL")) ctx->cull = atoi(e) != 0;
     if (const char* e = getenv("VRB200_PASS")) ctx->pass_samples = std::max(1, atoi(e));
@@ -352,11 +384,16 @@ void vrb_destroy(vrb_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& f : ctx->frames) { free_grid(f.second.slot[0]); free_grid(f.second.slot[1]); }
+    for (auto& f : ctx->frames) { free_grid(f.second.slot[0], ctx->stream); free_grid(f.second.slot[1], ctx->stream); }
     if (!ctx->color_external) cudaFree(ctx->color);
     cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
     cudaFree(ctx->lbuf); cudaFree(ctx->env_stage);
     cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
+    cudaStreamSynchronize(ctx->stream);
+    {   // hand the pooled grid memory back to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -411,7 +448,7 @@ int vrb_grid_clear(vrb_ctx* ctx) {
     if (!ctx) return VRB_ERR_INVALID;
     DeviceGuard guard(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    for (auto& f : ctx->frames) { free_grid(f.second.slot[0]); free_grid(f.second.slot[1]); }
+    for (auto& f : ctx->frames) { free_grid(f.second.slot[0], ctx->stream); free_grid(f.second.slot[1], ctx->stream); }
     ctx->frames.clear();
     return VRB_OK;
 }
@@ -423,7 +460,7 @@ int vrb_grid_free(vrb_ctx* ctx, int slot, int frame) {
     if (it == ctx->frames.end()) return VRB_OK;
     DeviceGuard guard(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    free_grid(it->second.slot[slot]);
+    free_grid(it->second.slot[slot], ctx->stream);
     if (!it->second.slot[0].valid && !it->second.slot[1].valid) ctx->frames.erase(it);
     return VRB_OK;
 }
@@ -446,17 +483,17 @@ int vrb_grid_upload_brick(vrb_ctx* ctx, int slot, int frame, const vrb_brick_vie
                        g.atlas_dim.x == v->atlas_dim[0] && g.atlas_dim.y == v->atlas_dim[1] && g.atlas_dim.z == v->atlas_dim[2];
     if (!reuse) {
         CK(cudaStreamSynchronize(ctx->stream));
-        free_grid(g);
+        free_grid(g, ctx->stream);
     }
     g.nb = make_uint3(v->n_bricks[0], v->n_bricks[1], v->n_bricks[2]);
     g.atlas_dim = make_uint3(v->atlas_dim[0], v->atlas_dim[1], v->atlas_dim[2]);
     g.brick_count = v->brick_count;
     const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
     if (!reuse) {
-        CK(cudaMalloc(&g.indirection, n * 4));
-        CK(cudaMalloc(&g.range, n * 4));
-        CK(cudaMalloc(&g.atlas, atlas_bytes ? atlas_bytes : 8));
-        for (int i = 0; i < 3; ++i) CK(cudaMalloc(&g.mips[i], mip_words(g.nb, i) * 4));
+        CK(pool_alloc(&g.indirection, n * 4, ctx->stream));
+        CK(pool_alloc(&g.range, n * 4, ctx->stream));
+        CK(pool_alloc(&g.atlas, atlas_bytes, ctx->stream));
+        for (int i = 0; i < 3; ++i) CK(pool_alloc(&g.mips[i], mip_words(g.nb, i) * 4, ctx->stream));
     }
     CK(cudaMemcpyAsync(g.indirection, v->indirection, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(g.range, v->range, n * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -484,11 +521,11 @@ int vrb_grid_build_from_dense(vrb_ctx* ctx, int slot, int frame, const uint8_t* 
     DeviceGuard guard(ctx->device);
     const size_t n = size_t(dim[0]) * dim[1] * dim[2];
     uint8_t* d_vox = nullptr;
-    CK(cudaMalloc(&d_vox, n));
+    CK(pool_alloc(&d_vox, n, ctx->stream));
     cudaError_t e = cudaMemcpyAsync(d_vox, voxels_u8, n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { cudaFree(d_vox); return fail(ctx, VRB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { pool_free(d_vox, ctx->stream); return fail(ctx, VRB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
     st = build_from_device_voxels(ctx, slot, frame, d_vox, dim, vmin, vmax);
-    cudaFree(d_vox);
+    pool_free(d_vox, ctx->stream);
     return st;
 }
 
@@ -640,8 +677,8 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     if (tf) { mix_key(&params->tf_window_left, 4); mix_key(&params->tf_window_width, 4); mix_key(&ctx->lut_version, 8); }
     const size_t n0 = size_t(g.nb.x) * g.nb.y * g.nb.z;
     if (!g.maj[0]) {
-        CK(cudaMalloc(&g.maj[0], (n0 + 1) * 4));   // + 1: the out-of-bounds majorant
-        for (int l = 1; l < 4; ++l) CK(cudaMalloc(&g.maj[l], mip_words(g.nb, l - 1) * 4));
+        CK(pool_alloc(&g.maj[0], (n0 + 1) * 4, ctx->stream));   // + 1: the out-of-bounds majorant
+        for (int l = 1; l < 4; ++l) CK(pool_alloc(&g.maj[l], mip_words(g.nb, l - 1) * 4, ctx->stream));
         g.maj_key = 0;
     }
     for (int l = 0; l < 4; ++l) a.maj[l] = g.maj[l];
