@@ -153,6 +153,70 @@ def test_synthetic_dense_volume_end_to_end(ctx, oracle, env_rgb, env_pyramid):
     assert ref_a[..., 3].max() == 1.0
 
 
+def test_emission_grid_end_to_end(ctx, oracle, env_rgb, env_pyramid):
+    """a density grid plus a `temperature` emission grid with its OWN transform (half resolution, so
+    emis_from_density is a real matrix), through lookup_emission / lookup_temperature_brick (common.glsl:307-328,
+    renderer.cpp:64-74,117-124). Statistical tier against the oracle + exact n_emis accounting."""
+    from volren_b200 import scene
+    vox, lo, hi = blob_volume(48)
+    zz, yy, xx = np.mgrid[0:24, 0:24, 0:24].astype(np.float32) / 24
+    temp = np.exp(-(((xx - .45) / .2) ** 2 + ((yy - .5) / .2) ** 2 + ((zz - .5) / .25) ** 2))
+    tvox = (np.clip(temp - 0.1, 0, 1) / 0.9 * 255).astype(np.uint8)
+    ctx.grid_build_from_dense(vox, lo, hi, frame=5)
+    ctx.grid_build_from_dense(tvox, 0.0, 2.0, slot=1, frame=5)
+    ctx.env_upload(env_rgb)
+    g, ge = oracle.brick_build(vox, lo, hi), oracle.brick_build(tvox, 0.0, 2.0)
+    got_e = ctx.grid_download(slot=1, frame=5)
+    assert np.array_equal(got_e.range, ge.range) and np.array_equal(got_e.atlas, ge.atlas)
+    W, H, SPP = 64, 64, 128
+    emat = np.diag([2.0, 2.0, 2.0, 1.0]).astype(np.float32) @ np.asarray(g.matrix(), np.float32)   # 24^3 voxels of size 2 cover the 48^3 grid
+
+    def mk(seed):
+        s = scene.RenderSettings(bounces=32, seed=seed, density_scale=8.0, emission_scale=40.0, albedo=(.7, .7, .7), frame=5)
+        scene.scale_and_move_to_unit_cube(g.matrix(), (48, 48, 48), s)
+        s.density_scale = 8.0
+        return scene.make_params(W, H, scene.Camera(), s, g.matrix(), (48, 48, 48), g.min_maj,
+                                 emission_matrix=emat, majorant_emission=ge.min_maj[1])
+    sc = oracle.make_scene(g, env_rgb, env_pyramid, emission=ge)
+    ref_a, cnt_a = oracle.trace(sc, mk(42), 1, SPP)
+    ref_b, _ = oracle.trace(sc, mk(777), 1, SPP)
+    p0 = mk(42)
+    p0.has_emission = 0
+    ref_0, _ = oracle.trace(oracle.make_scene(g, env_rgb, env_pyramid), p0, 1, SPP)
+    assert ref_a[..., :3].mean() > 1.05 * ref_0[..., :3].mean()      # the emission term is visible in the image
+    ctx.resize(W, H)
+    ctx.set_counting(True)
+    ctx.trace(mk(42), 1, SPP)
+    got = ctx.download_color()
+    cnt = ctx.get_counters().as_dict()
+    ctx.set_counting(False)
+    two_run = rmse(ref_a[..., :3], ref_b[..., :3])
+    assert rmse(got[..., :3], ref_a[..., :3]) < two_run
+    ctx.clear()
+    ctx.trace(mk(4711), 1, SPP)
+    got_c = ctx.download_color()
+    assert rmse(got_c[..., :3], ref_a[..., :3]) < 1.25 * two_run
+    want = cnt_a.as_dict()
+    assert want["n_emis"] > 0
+    for k in ("n_maj", "n_dens", "n_emis", "n_nee", "n_real"):
+        assert abs(cnt[k] - want[k]) / want[k] < 0.01, (k, cnt[k], want[k])
+    # the cross-check kernels agree with the production kernel's event counts path for path
+    for kind in (1, 2):
+        ctx.set_kernel(kind)
+        ctx.clear()
+        ctx.set_counting(True)
+        ctx.trace(mk(42), 1, 4)
+        c = ctx.get_counters().as_dict()
+        ctx.set_counting(False)
+        if kind == 1:
+            c1 = c
+        else:
+            assert c == c1
+    ctx.set_kernel(0)
+    ctx.grid_free(1, 5)
+    ctx.grid_free(0, 5)
+
+
 def test_tonemap_and_readback(smoke_ctx, oracle, smoke_grid):
     W, H = 80, 56
     p = readme_scene(smoke_grid, W, H, bounces=8)

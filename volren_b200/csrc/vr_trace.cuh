@@ -64,9 +64,6 @@ struct TraceArgs {
     unsigned int* job_counter;     // block ticket: block b = (tile slot b >> sample_bits, sample b & mask), 32 samples each
     int tiles_x, n_jobs;           // n_jobs = number of block ids = tiles << sample_bits (ids with sample >= n_samples are padding)
     int sample_bits;               // ceil(log2(n_samples))
-    // screen-space culling (only with a hidden environment): pixels outside [cull_x0, cull_x1] x [cull_y0, cull_y1] cannot
-    // see the volume's box, their samples are exactly (0, 0, 0, 0) whatever the seed
-    int cull, cull_x0, cull_y0, cull_x1, cull_y1;
     float4* lbuf;                  // per-launch sample buffer: lbuf[(s - first_sample) * lbuf_stride + y * W + x]
     size_t lbuf_stride;
     // tile slot k is the tile with packed coordinates tile_order[k] = (ty << 16 | tx): natural order, or heaviest first

@@ -311,12 +311,6 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                     blk_x0 = a.x0 + int(txy & 0xffffu) * 8;
                     blk_y0 = a.y0 + int(txy >> 16) * 4;
                     const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
-                    if (a.cull && (blk_x0 > a.cull_x1 || blk_x0 + 7 < a.cull_x0 || blk_y0 > a.cull_y1 || blk_y0 + 3 < a.cull_y0)) {
-                        // no ray of this tile can reach the volume's box and the environment is hidden: every sample of the
-                        // block is (0, 0, 0, 0) (trace_path returns L = 0, n_paths = 0) -- no seed, no ray
-                        if (ix < a.x1 && iy < a.y1) a.lbuf[size_t(blk_sj) * a.lbuf_stride + size_t(iy) * W + ix] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        continue;
-                    }
                     // all 32 lanes prepare the block: lane i seeds sample (pixel i of the tile, sample blk_sj)
                     // (pathtracer_brick.glsl:28-30: TEA seed, two jitter draws, view direction)
                     uint32_t sd = tea32(uint32_t(a.p.seed) * uint32_t(iy * W + ix), uint32_t(a.first_sample + blk_sj));
@@ -378,15 +372,20 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
 
 // Folds the samples of one launch into the colour buffer in sample order (pathtracer_brick.glsl:36):
 // color = mix(color, L_s, 1 / s) for s = first_sample ... (VRB_ACCUM_MEAN) or color += L_s (VRB_ACCUM_SUM).
+// Pixels of the region [x0, x1) x [y0, y1) outside the traced rectangle [tx0, tx1) x [ty0, ty1) were culled on the host (no
+// ray of theirs can reach the volume's box and the environment is hidden): each of their samples is exactly (0, 0, 0, 0).
 __global__ void __launch_bounds__(256) k_fold(float4* __restrict__ color, const float4* __restrict__ lbuf, size_t lbuf_stride, int W, int x0, int y0, int x1, int y1,
-                                              int first_sample, int n_samples, int accum_mode) {
+                                              int tx0, int ty0, int tx1, int ty1, int first_sample, int n_samples, int accum_mode) {
     const int rw = x1 - x0;
     const size_t n = size_t(rw) * (y1 - y0);
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
-        const size_t p = size_t(y0 + int(i / rw)) * W + (x0 + int(i % rw));
+        const int x = x0 + int(i % rw), y = y0 + int(i / rw);
+        const size_t p = size_t(y) * W + x;
+        const bool traced = x >= tx0 && x < tx1 && y >= ty0 && y < ty1;
         float4 acc = color[p];
+        if (!traced && accum_mode != VRB_ACCUM_MEAN) continue;      // sum mode: + 0
         for (int j = 0; j < n_samples; ++j) {
-            const float4 L = __ldcs(lbuf + size_t(j) * lbuf_stride + p);
+            const float4 L = traced ? __ldcs(lbuf + size_t(j) * lbuf_stride + p) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (accum_mode == VRB_ACCUM_MEAN) {
                 const float w = 1.f / float(first_sample + j);
                 acc.x = mix_rn(acc.x, L.x, w); acc.y = mix_rn(acc.y, L.y, w); acc.z = mix_rn(acc.z, L.z, w); acc.w = mix_rn(acc.w, L.w, w);

@@ -693,8 +693,6 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         }
         g.maj_key = key;
     }
-    a.tiles_x = (a.x1 - a.x0 + 7) / 8;
-    const int n_tiles = a.tiles_x * ((a.y1 - a.y0 + 3) / 4);
     a.job_counter = ctx->job_counter;
     // ---- per-launch sample buffer: passes of at most `pass` samples per pixel (16 B per sample and pixel) ----
     const size_t n_px = size_t(ctx->w) * ctx->h;
@@ -710,7 +708,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     a.lbuf = ctx->lbuf;
     a.lbuf_stride = n_px;
     // ---- screen-space culling of the volume's box (hidden environment only; never in the counting build) ----
-    a.cull = 0;
+    const int fold_x0 = a.x0, fold_y0 = a.y0, fold_x1 = a.x1, fold_y1 = a.y1;       // the caller's region
     if (!params->show_environment && !ctx->counting && ctx->cull) {
         // view_dir (common.glsl:76-80): dir ~ cam_transform * (px, py, z), px = (x + jitter - w/2) / h, z = -0.5 / tan(fov/2).
         // A box corner c maps to v = cam_transform^-1 (c - cam_pos); in front of the camera (v.z < 0) it projects to
@@ -732,11 +730,18 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         const double d01 = T[0] * T[3] + T[1] * T[4] + T[2] * T[5], d00 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2], d22 = T[6] * T[6] + T[7] * T[7] + T[8] * T[8];
         if (std::fabs(d01) > 1e-4 || std::fabs(d00 - 1) > 1e-4 || std::fabs(d22 - 1) > 1e-4) ok = false;
         if (ok && std::isfinite(xmin + xmax + ymin + ymax)) {
-            a.cull = 1;
-            a.cull_x0 = int(std::floor(std::max(-1e9, xmin))) - 2; a.cull_x1 = int(std::ceil(std::min(1e9, xmax))) + 1;
-            a.cull_y0 = int(std::floor(std::max(-1e9, ymin))) - 2; a.cull_y1 = int(std::ceil(std::min(1e9, ymax))) + 1;
+            // pixels outside [cx0, cx1] x [cy0, cy1] are exactly (0, 0, 0, 0) for every sample: they get no tickets at all
+            // (the traced rectangle shrinks) and k_fold folds zeros for them without reading the sample buffer
+            const int cx0 = int(std::floor(std::max(-1e9, xmin))) - 2, cx1 = int(std::ceil(std::min(1e9, xmax))) + 1;
+            const int cy0 = int(std::floor(std::max(-1e9, ymin))) - 2, cy1 = int(std::ceil(std::min(1e9, ymax))) + 1;
+            a.x0 = std::max(a.x0, cx0); a.x1 = std::min(a.x1, cx1 + 1);
+            a.y0 = std::max(a.y0, cy0); a.y1 = std::min(a.y1, cy1 + 1);
         }
     }
+    const bool nothing_visible = a.x0 >= a.x1 || a.y0 >= a.y1;     // the whole region is culled: only the fold runs
+    if (nothing_visible) { a.x0 = a.x1 = fold_x0; a.y0 = a.y1 = fold_y0; }
+    a.tiles_x = std::max(1, (a.x1 - a.x0 + 7) / 8);
+    const int n_tiles = std::max(1, a.tiles_x * ((a.y1 - a.y0 + 3) / 4));
     // ---- heaviest tiles first: order the blocks by the per-tile cost the previous launch of this view measured ----
     const bool lpt = ctx->lpt && !ctx->counting && ctx->kernel == 0;
     uint64_t vkey = key;
@@ -792,9 +797,15 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         a.sample_bits = 0;
         while ((1 << a.sample_bits) < a.n_samples) ++a.sample_bits;
         a.n_jobs = n_tiles << a.sample_bits;
-        CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
         a.tile_order = ctx->tile_iota;       // natural order
         a.tile_cost = nullptr;
+        if (nothing_visible) {
+            k_fold<<<grid_for(size_t(fold_x1 - fold_x0) * (fold_y1 - fold_y0), 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
+                ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode);
+            CK_LAUNCH();
+            continue;
+        }
+        CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
         if (lpt) {
             if (ctx->cost_key == vkey) {      // the previous pass / launch measured this view
                 size_t tmp_bytes = ctx->sort_tmp_bytes;
@@ -809,8 +820,9 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
         void* kargs[] = { (void*)&a };
         CK(cudaLaunchKernel(fn, dim3(blocks), dim3(VR_TRACE_BLOCK), kargs, 0, ctx->stream));
-        const size_t n_region = size_t(a.x1 - a.x0) * (a.y1 - a.y0);
-        k_fold<<<grid_for(n_region, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(ctx->color, ctx->lbuf, n_px, ctx->w, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode);
+        const size_t n_region = size_t(fold_x1 - fold_x0) * (fold_y1 - fold_y0);
+        k_fold<<<grid_for(n_region, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
+            ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode);
         CK_LAUNCH();
     }
     return VRB_OK;
