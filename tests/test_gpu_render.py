@@ -333,3 +333,47 @@ def test_scheduling_options_do_not_change_the_image(smoke_ctx, oracle, smoke_gri
     smoke_ctx.set_option("lpt", 1); smoke_ctx.set_option("cull", 1); smoke_ctx.set_option("pass", 16)
     with pytest.raises(Exception):
         smoke_ctx.set_option("nonsense", 1)
+
+
+def test_screen_space_brick_mask_is_exact(smoke_ctx, oracle, smoke_grid, lut_raw):
+    """Hidden environment: tiles onto which no brick with a positive majorant projects get no tickets (k_tile_mask) and
+    pixels outside the box's screen rectangle are never traced. Both are exact: the image equals the unculled one bit for
+    bit -- off-centre views, a camera INSIDE the volume (mask unusable), a non-monotone LUT (TF majorant does not bound the
+    density: mask off), the non-TF kernel with a hidden environment, sum mode."""
+    from volren_b200 import scene
+    W, H = 232, 136
+    lut, _ = oracle.lut_upload(lut_raw)
+    bad_lut = lut.copy()
+    bad_lut[:, 3] = bad_lut[::-1, 3]                     # decreasing alpha
+    smoke_ctx.resize(W, H)
+
+    def params(cam, use_tf, seed=7):
+        st = scene.RenderSettings(bounces=6, seed=seed, use_transferfunc=use_tf, show_environment=False)
+        scene.scale_and_move_to_unit_cube(smoke_grid.matrix(), smoke_grid.index_extent(), st)
+        return scene.make_params(W, H, cam, st, smoke_grid.matrix(), smoke_grid.index_extent(), smoke_grid.min_maj)
+
+    cams = [scene.Camera(),                                                                        # default pose
+            scene.Camera(pos=np.array([.9, .5, .3], np.float32), dir=scene.normalize([-1, -.2, -.6]), fov_degree=55.0),   # volume off-centre, partly outside
+            scene.Camera(pos=np.array([.05, .1, .02], np.float32), dir=scene.normalize([.3, 1, .2])),                    # inside the volume
+            scene.Camera(pos=np.array([1, 0, 1], np.float32), dir=scene.normalize([1, 0, 1]))]                           # looking away: nothing visible
+    for table in (lut, bad_lut):
+        smoke_ctx.tf_upload(table)
+        for cam in cams:
+            for use_tf in (True, False):
+                for accum in (0, 1):
+                    p = params(cam, use_tf)
+                    images = []
+                    for cull in (1, 0):
+                        smoke_ctx.set_option("cull", cull)
+                        smoke_ctx.clear()
+                        smoke_ctx.trace(p, 1, 3, accum_mode=accum)
+                        smoke_ctx.trace(p, 4, 2, accum_mode=accum)
+                        images.append(smoke_ctx.download_color())
+                    assert np.array_equal(images[0], images[1]), (cam, use_tf, accum)
+    smoke_ctx.set_option("cull", 1)
+    smoke_ctx.tf_upload(lut)
+    assert images[0].max() == 0            # the last view looks away from the volume
+    # the default TF view is not trivially empty
+    smoke_ctx.clear()
+    smoke_ctx.trace(params(cams[0], True), 1, 4)
+    assert smoke_ctx.download_color()[..., 3].max() > 0

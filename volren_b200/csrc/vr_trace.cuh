@@ -71,6 +71,9 @@ struct TraceArgs {
     // tile_cost[ty * tiles_x + tx] (nullptr: not measured)
     const uint32_t* tile_order;
     unsigned int* tile_cost;
+    // screen-space brick mask (hidden environment only): tile slots >= *n_live hold tiles no non-empty brick projects onto;
+    // nullptr: every slot is live and n_jobs is the host's count
+    const unsigned int* n_live;
 };
 
 template <bool COUNT> struct Cnt;

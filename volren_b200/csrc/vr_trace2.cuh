@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
     bool blk_done = false;         // the counter is exhausted
     unsigned nxt_block = 0;        // lane 0: id of the prefetched next block
     if (lane == 0) nxt_block = atomicAdd(a.job_counter, 1u);
+    const unsigned n_jobs = a.n_live ? (__ldg(a.n_live) << a.sample_bits) : unsigned(a.n_jobs);
 
     while (true) {
         // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) =================
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                         b = __shfl_sync(FULL, nxt_block, 0);
                         if (lane == 0) nxt_block = atomicAdd(a.job_counter, 1u);
                     }
-                    if (b >= unsigned(a.n_jobs)) {                 // no blocks left
+                    if (b >= n_jobs) {                             // no blocks left
                         blk_done = true;
                         if (want) { want = false; stage = SG_IDLE; }
                         break;
@@ -372,16 +373,72 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
 
 // Folds the samples of one launch into the colour buffer in sample order (pathtracer_brick.glsl:36):
 // color = mix(color, L_s, 1 / s) for s = first_sample ... (VRB_ACCUM_MEAN) or color += L_s (VRB_ACCUM_SUM).
+// Screen-space brick mask (hidden environment only). With the environment hidden a sample is non-zero only if its camera
+// ray has a REAL collision, and a real collision at x needs density(x) > 0, hence a level-0 majorant > 0 in the brick
+// that contains x (the majorants are conservative: the ranges are dilated by the filter footprint, grid_brick.cpp:83-92).
+// x lies on the camera ray, so it projects into the sample's own pixel square: a tile onto which no brick with a positive
+// majorant projects yields exactly (0, 0, 0, 0) for every sample, whatever the seed. One thread per brick marks the
+// tiles under the screen bounding rectangle of its 8 corners (+ 1 pixel); a brick with a corner beside or behind the
+// camera sets `info[1]` (mask unusable: every tile is live).
+__global__ void k_tile_mask(const __grid_constant__ TraceArgs a, const float* __restrict__ maj0, unsigned int* __restrict__ tile_live,
+                            unsigned int* __restrict__ info, int tiles_y) {
+    const uint32_t nbx = a.density.nb.x, nby = a.density.nb.y, nbz = a.density.nb.z;
+    const size_t n = size_t(nbx) * nby * nbz;
+    const float w = float(a.p.resolution[0]), h = float(a.p.resolution[1]);
+    const Mat4& M = *reinterpret_cast<const Mat4*>(a.p.vol_density_transform);
+    const float* T = a.p.cam_transform;      // column-major, orthonormal (checked by the host): inverse = transpose
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        if (maj0[i] <= 0.f) continue;        // (a NaN majorant counts as live)
+        const uint32_t bx = uint32_t(i % nbx), by = uint32_t((i / nbx) % nby), bz = uint32_t(i / (size_t(nbx) * nby));
+        float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float3 c = mul_point(M, f3(float(8u * (bx + (k & 1))), float(8u * (by + ((k >> 1) & 1))), float(8u * (bz + (k >> 2))))) -
+                             f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
+            const float vx = T[0] * c.x + T[1] * c.y + T[2] * c.z, vy = T[3] * c.x + T[4] * c.y + T[5] * c.z, vz = T[6] * c.x + T[7] * c.y + T[8] * c.z;
+            if (!(vz < -1e-4f)) { ok = false; break; }
+            const float sx = vx * a.cam_z / vz * h + 0.5f * w, sy = vy * a.cam_z / vz * h + 0.5f * h;     // inverse of view_dir (common.glsl:76-80)
+            xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx); ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
+        }
+        if (!ok || !(xmin <= xmax) || !(ymin <= ymax)) { info[1] = 1u; continue; }
+        // pixel p covers [p, p + 1): pixels floor(min) - 1 ... floor(max) + 1, clipped to the traced rectangle
+        const int px0 = max(a.x0, int(floorf(fmaxf(xmin, -1e9f))) - 1), px1 = min(a.x1 - 1, int(floorf(fminf(xmax, 1e9f))) + 1);
+        const int py0 = max(a.y0, int(floorf(fmaxf(ymin, -1e9f))) - 1), py1 = min(a.y1 - 1, int(floorf(fminf(ymax, 1e9f))) + 1);
+        if (px0 > px1 || py0 > py1) continue;
+        for (int ty = (py0 - a.y0) >> 2; ty <= (py1 - a.y0) >> 2; ++ty)
+            for (int tx = (px0 - a.x0) >> 3; tx <= (px1 - a.x0) >> 3; ++tx) tile_live[ty * a.tiles_x + tx] = 1u;
+    }
+}
+
+// sort keys of the tile slots: dead tiles 0 (they sort behind every live tile), live tiles max(cost, 1) (cost = 0 everywhere
+// when the view has not been measured yet: the stable sort keeps raster order); info[0] = number of live tiles
+__global__ void k_tile_keys(const unsigned int* __restrict__ tile_live, const unsigned int* __restrict__ cost, unsigned int* __restrict__ key,
+                            unsigned int* __restrict__ info, int n_tiles) {
+    const bool all_live = info[1] != 0u;
+    unsigned int mine = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles; i += gridDim.x * blockDim.x) {
+        const bool live = all_live || tile_live[i] != 0u;
+        key[i] = live ? max(cost ? cost[i] : 0u, 1u) : 0u;
+        mine += live ? 1u : 0u;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(info, mine);
+}
+
 // Pixels of the region [x0, x1) x [y0, y1) outside the traced rectangle [tx0, tx1) x [ty0, ty1) were culled on the host (no
-// ray of theirs can reach the volume's box and the environment is hidden): each of their samples is exactly (0, 0, 0, 0).
+// ray of theirs can reach the volume's box and the environment is hidden), pixels of dead tiles by k_tile_mask: each of
+// their samples is exactly (0, 0, 0, 0).
 __global__ void __launch_bounds__(256) k_fold(float4* __restrict__ color, const float4* __restrict__ lbuf, size_t lbuf_stride, int W, int x0, int y0, int x1, int y1,
-                                              int tx0, int ty0, int tx1, int ty1, int first_sample, int n_samples, int accum_mode) {
+                                              int tx0, int ty0, int tx1, int ty1, int first_sample, int n_samples, int accum_mode,
+                                              const unsigned int* __restrict__ tile_live, const unsigned int* __restrict__ info, int tiles_x) {
     const int rw = x1 - x0;
     const size_t n = size_t(rw) * (y1 - y0);
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         const int x = x0 + int(i % rw), y = y0 + int(i / rw);
         const size_t p = size_t(y) * W + x;
-        const bool traced = x >= tx0 && x < tx1 && y >= ty0 && y < ty1;
+        bool traced = x >= tx0 && x < tx1 && y >= ty0 && y < ty1;
+        if (traced && tile_live && info[1] == 0u) traced = tile_live[((y - ty0) >> 2) * tiles_x + ((x - tx0) >> 3)] != 0u;    // k_tile_mask
         float4 acc = color[p];
         if (!traced && accum_mode != VRB_ACCUM_MEAN) continue;      // sum mode: + 0
         for (int j = 0; j < n_samples; ++j) {

@@ -80,6 +80,10 @@ struct vrb_ctx {
     unsigned int* tile_cost_sorted = nullptr;
     uint32_t* tile_iota = nullptr;
     uint32_t* tile_order = nullptr;
+    unsigned int* tile_live = nullptr;   // k_tile_mask: 1 = some non-empty brick projects onto the tile
+    unsigned int* tile_key = nullptr;    // sort keys (k_tile_keys)
+    unsigned int* live_info = nullptr;   // {number of live tiles, mask unusable}
+    bool lut_monotone = false;           // alpha of the uploaded LUT is non-decreasing (the TF majorant bounds the density then)
     void* sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     int tile_capacity = 0;
@@ -387,6 +391,7 @@ void vrb_destroy(vrb_ctx* ctx) {
     for (auto& f : ctx->frames) { free_grid(f.second.slot[0], ctx->stream); free_grid(f.second.slot[1], ctx->stream); }
     if (!ctx->color_external) cudaFree(ctx->color);
     cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
+    cudaFree(ctx->tile_live); cudaFree(ctx->tile_key); cudaFree(ctx->live_info);
     cudaFree(ctx->lbuf); cudaFree(ctx->env_stage);
     cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
     cudaStreamSynchronize(ctx->stream);
@@ -639,6 +644,11 @@ int vrb_tf_upload(vrb_ctx* ctx, const float* rgba, uint32_t n) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->tf_size = n;
     ctx->lut_version++;
+    // k_tile_mask relies on tf(hi).a bounding tf(d).a for d <= hi: true for the CDF-corrected LUTs of transferfunc.cpp:33-58,
+    // checked here because the ABI accepts any table
+    ctx->lut_monotone = true;
+    for (uint32_t i = 0; i < n; ++i)
+        if (!(rgba[4 * i + 3] >= (i ? rgba[4 * (i - 1) + 3] : 0.f))) { ctx->lut_monotone = false; break; }
     return VRB_OK;
 }
 
@@ -709,6 +719,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     a.lbuf_stride = n_px;
     // ---- screen-space culling of the volume's box (hidden environment only; never in the counting build) ----
     const int fold_x0 = a.x0, fold_y0 = a.y0, fold_x1 = a.x1, fold_y1 = a.y1;       // the caller's region
+    bool box_cull_ok = false;
     if (!params->show_environment && !ctx->counting && ctx->cull) {
         // view_dir (common.glsl:76-80): dir ~ cam_transform * (px, py, z), px = (x + jitter - w/2) / h, z = -0.5 / tan(fov/2).
         // A box corner c maps to v = cam_transform^-1 (c - cam_pos); in front of the camera (v.z < 0) it projects to
@@ -730,6 +741,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         const double d01 = T[0] * T[3] + T[1] * T[4] + T[2] * T[5], d00 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2], d22 = T[6] * T[6] + T[7] * T[7] + T[8] * T[8];
         if (std::fabs(d01) > 1e-4 || std::fabs(d00 - 1) > 1e-4 || std::fabs(d22 - 1) > 1e-4) ok = false;
         if (ok && std::isfinite(xmin + xmax + ymin + ymax)) {
+            box_cull_ok = true;
             // pixels outside [cx0, cx1] x [cy0, cy1] are exactly (0, 0, 0, 0) for every sample: they get no tickets at all
             // (the traced rectangle shrinks) and k_fold folds zeros for them without reading the sample buffer
             const int cx0 = int(std::floor(std::max(-1e9, xmin))) - 2, cx1 = int(std::ceil(std::min(1e9, xmax))) + 1;
@@ -740,6 +752,9 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     }
     const bool nothing_visible = a.x0 >= a.x1 || a.y0 >= a.y1;     // the whole region is culled: only the fold runs
     if (nothing_visible) { a.x0 = a.x1 = fold_x0; a.y0 = a.y1 = fold_y0; }
+    // brick mask (k_tile_mask): needs a usable projection and, with a transfer function, a majorant that bounds the density
+    const bool mask = box_cull_ok && !nothing_visible && params->vol_density_scale > 0.f && params->vol_majorant > 0.f &&
+                      (!tf || (ctx->lut_monotone && params->tf_window_width > 0.f));
     a.tiles_x = std::max(1, (a.x1 - a.x0 + 7) / 8);
     const int n_tiles = std::max(1, a.tiles_x * ((a.y1 - a.y0 + 3) / 4));
     // ---- heaviest tiles first: order the blocks by the per-tile cost the previous launch of this view measured ----
@@ -757,8 +772,13 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         if (vkey == 0) vkey = 1;
         if (n_tiles > ctx->tile_capacity || a.tiles_x != ctx->tile_coords_tx) {
             cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
+            cudaFree(ctx->tile_live); cudaFree(ctx->tile_key); cudaFree(ctx->live_info);
             ctx->tile_cost = ctx->tile_cost_sorted = nullptr; ctx->tile_iota = ctx->tile_order = nullptr; ctx->sort_tmp = nullptr;
+            ctx->tile_live = ctx->tile_key = ctx->live_info = nullptr;
             ctx->tile_capacity = 0; ctx->cost_key = 0;
+            CK(cudaMalloc(&ctx->tile_live, size_t(n_tiles) * 4));
+            CK(cudaMalloc(&ctx->tile_key, size_t(n_tiles) * 4));
+            CK(cudaMalloc(&ctx->live_info, 8));
             CK(cudaMalloc(&ctx->tile_cost, size_t(n_tiles) * 4));
             CK(cudaMalloc(&ctx->tile_cost_sorted, size_t(n_tiles) * 4));
             CK(cudaMalloc(&ctx->tile_iota, size_t(n_tiles) * 4));
@@ -799,19 +819,32 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         a.n_jobs = n_tiles << a.sample_bits;
         a.tile_order = ctx->tile_iota;       // natural order
         a.tile_cost = nullptr;
+        a.n_live = nullptr;
         if (nothing_visible) {
             k_fold<<<grid_for(size_t(fold_x1 - fold_x0) * (fold_y1 - fold_y0), 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
-                ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode);
+                ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode, nullptr, nullptr, 0);
             CK_LAUNCH();
             continue;
         }
         CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
+        const bool cost_valid = lpt && ctx->cost_key == vkey;      // the previous pass / launch measured this view
+        if (mask) {
+            CK(cudaMemsetAsync(ctx->tile_live, 0, size_t(n_tiles) * 4, ctx->stream));
+            CK(cudaMemsetAsync(ctx->live_info, 0, 8, ctx->stream));
+            k_tile_mask<<<grid_for(n0, 128, ctx->sm_count), 128, 0, ctx->stream>>>(a, g.maj[0], ctx->tile_live, ctx->live_info, (a.y1 - a.y0 + 3) / 4);
+            CK_LAUNCH();
+            k_tile_keys<<<grid_for(size_t(n_tiles), 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->tile_live, cost_valid ? ctx->tile_cost : nullptr, ctx->tile_key, ctx->live_info, n_tiles);
+            CK_LAUNCH();
+            size_t tmp_bytes = ctx->sort_tmp_bytes;
+            CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_key, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
+            a.tile_order = ctx->tile_order;
+            a.n_live = ctx->live_info;
+        } else if (cost_valid) {
+            size_t tmp_bytes = ctx->sort_tmp_bytes;
+            CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
+            a.tile_order = ctx->tile_order;
+        }
         if (lpt) {
-            if (ctx->cost_key == vkey) {      // the previous pass / launch measured this view
-                size_t tmp_bytes = ctx->sort_tmp_bytes;
-                CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
-                a.tile_order = ctx->tile_order;
-            }
             ctx->cost_key = vkey;
             CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, ctx->stream));
             a.tile_cost = ctx->tile_cost;
@@ -822,7 +855,8 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         CK(cudaLaunchKernel(fn, dim3(blocks), dim3(VR_TRACE_BLOCK), kargs, 0, ctx->stream));
         const size_t n_region = size_t(fold_x1 - fold_x0) * (fold_y1 - fold_y0);
         k_fold<<<grid_for(n_region, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
-            ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode);
+            ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode,
+            mask ? ctx->tile_live : nullptr, mask ? ctx->live_info : nullptr, a.tiles_x);
         CK_LAUNCH();
     }
     return VRB_OK;
