@@ -141,6 +141,11 @@ int vrb_grid_build_from_dense_device(vrb_ctx* ctx, int slot, int frame, const vo
 /* sizes of an uploaded/built grid; then a second call with buffers allocated copies it back */
 int vrb_grid_info(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* sizes_out);
 int vrb_grid_download(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out);
+/* test hook: the density the tracer itself fetches at n index-space points (x, y, z triples, host memory).
+ * mode 0 = lookup_density_trilinear (common.glsl:289-297, without density_scale) through the records + u8 atlas,
+ * mode 1 = the same through the decoded apron blocks the production kernel reads (must equal mode 0 bit for bit),
+ * mode 2 = lookup_density_brick at floor(p) (common.glsl:268-275 == BrickGrid::lookup, grid_brick.cpp:148-154; 0 outside) */
+int vrb_debug_sample_density(vrb_ctx* ctx, int slot, int frame, const float* ipos_xyz, size_t n, int mode, float* out);
 /* voldata::DenseGrid(w,h,d,const float*) (voldata/src/grid_dense.cpp:57-95): global min/max + 8-bit quantise.
  * out_u8 (host, n bytes) and out_minmax[2]; if d_out_u8 != NULL the quantised grid is also left on the device. */
 int vrb_dense_from_float(vrb_ctx* ctx, const float* data, const uint32_t dim[3], uint8_t* out_u8,
@@ -170,8 +175,11 @@ int vrb_trace_deterministic(vrb_ctx* ctx, const vrb_params* params);
  * 1 and 2 are cross-checks: 2 must reproduce 1 (same paths, same counters), 0 is compared statistically */
 int vrb_set_kernel(vrb_ctx* ctx, int kind);
 /* scheduling options of the production kernel (none changes the image): "lpt" (heaviest tiles first, default 1),
- * "cull" (screen-space culling of the volume's box when the environment is hidden, default 1), "pass" (samples per
- * pixel and internal pass, default 16). Environment variables VRB200_LPT / VRB200_CULL / VRB200_PASS set the defaults. */
+ * "cull" (hidden environment only: pixels outside the screen rectangle of the volume's box and 8x4 tiles onto which no
+ * brick with a positive majorant projects are exactly zero and are not traced, default 1), "pass" (samples per pixel and
+ * internal pass, default 16), "count_culled" (default 0: the counting build traces every sample, i.e. counts the events of
+ * the reference algorithm; 1: it keeps the culling and counts the events the production launch executes).
+ * Environment variables VRB200_LPT / VRB200_CULL / VRB200_PASS set the defaults. */
 int vrb_set_option(vrb_ctx* ctx, const char* name, int value);
 /* color *= s (finalise VRB_ACCUM_SUM buffers) */
 int vrb_scale(vrb_ctx* ctx, float s);

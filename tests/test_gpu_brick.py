@@ -112,3 +112,61 @@ def test_too_many_bricks_is_an_error(ctx):
     with pytest.raises(VrbError) as e:
         ctx.grid_build_from_dense(vox, 0.0, 1.0)
     assert e.value.status == _capi.VRB_ERR_TOO_MANY_BRICKS and "1024" in str(e.value)
+
+
+@pytest.mark.parametrize("name", ["smoke", "blobs"])
+def test_decoded_apron_blocks_equal_the_canonical_fetch(ctx, smoke_grid, name):
+    """The production kernel's trilinear fetch reads DECODED 9^3 apron blocks (one slot load + 8 fp32 loads); it must
+    return the canonical fetch (records + u8 atlas, lookup_density_trilinear, common.glsl:289-297) bit for bit at any
+    point -- inside bricks, across brick faces / edges / corners, in empty bricks, at and beyond the grid border --
+    and both must agree with trilinear interpolation of BrickGrid::lookup (grid_brick.cpp:148-154) evaluated on the host."""
+    ctx.grid_clear()
+    if name == "smoke":
+        ctx.grid_upload_brick(smoke_grid)
+    else:
+        rng = np.random.default_rng(5)
+        vox = (rng.random((40, 72, 56)) * 255).astype(np.uint8)
+        vox[rng.random(vox.shape) < 0.5] = 0
+        vox[:, :24, :] = 0                    # whole empty bricks next to full ones
+        vox[8:16, 40:48, 8:16] = 77           # a constant brick (collapsed range)
+        ctx.grid_build_from_dense(vox, 0.25, 3.0)      # lo = 0.25: "empty" bricks decode to a non-zero constant
+    g = ctx.grid_download()
+    dec = g.decode_all()
+    ez, ey, ex = dec.shape
+    rng = np.random.default_rng(11)
+    n = 200_000
+    pts = (rng.random((n, 3)) * (np.array([ex, ey, ez]) + 6) - 3).astype(np.float32)        # up to 3 voxels outside
+    # brick faces / edges / corners: coordinates within +-1 voxel of multiples of 8
+    k = n // 2
+    snap = rng.integers(0, 3, size=(k, 3)) > 0
+    near = (np.round(pts[:k] / 8) * 8 + (rng.random((k, 3)) * 2 - 1)).astype(np.float32)
+    pts[:k] = np.where(snap, near, pts[:k])
+    a = ctx.sample_density(pts, mode=0)
+    b = ctx.sample_density(pts, mode=1)
+    assert np.array_equal(a, b)
+    assert np.count_nonzero(a) > n // 20
+    # host evaluation: 8 taps of the decoded voxels at ipos - 0.5 (0 outside), mix(x, y, a) = x * (1 - a) + y * a in fp32
+    q = pts - np.float32(0.5)
+    fl = np.floor(q)
+    f = (q - fl).astype(np.float32)
+    i0 = fl.astype(np.int64)
+    pad = np.zeros((ez + 8, ey + 8, ex + 8), np.float32)
+    pad[4:4 + ez, 4:4 + ey, 4:4 + ex] = dec
+
+    def tap(dx, dy, dz):
+        x, y, z = i0[:, 0] + dx + 4, i0[:, 1] + dy + 4, i0[:, 2] + dz + 4
+        ok = (x >= 0) & (x < ex + 8) & (y >= 0) & (y < ey + 8) & (z >= 0) & (z < ez + 8)
+        return np.where(ok, pad[np.clip(z, 0, ez + 7), np.clip(y, 0, ey + 7), np.clip(x, 0, ex + 7)], np.float32(0))
+
+    def mix(x, y, w):
+        return (x * (np.float32(1) - w) + y * w).astype(np.float32)
+    rows = [mix(tap(0, dy, dz), tap(1, dy, dz), f[:, 0]) for dz in (0, 1) for dy in (0, 1)]
+    want = mix(mix(rows[0], rows[1], f[:, 1]), mix(rows[2], rows[3], f[:, 1]), f[:, 2])
+    # the voxel decode differs by an ulp between GL's u8 / 255.f and voldata's u8 * (1 / 255.f), the lerps by FMA contraction
+    assert np.allclose(a, want, rtol=2e-6, atol=1e-7)
+    # nearest voxel (lookup_density_brick)
+    c = ctx.sample_density(pts, mode=2)
+    ip = np.floor(pts).astype(np.int64)
+    inside = np.all((ip >= 0) & (ip < np.array([ex, ey, ez])), axis=1)
+    assert np.all(c[~inside] == 0)
+    assert np.allclose(c[inside], dec[ip[inside, 2], ip[inside, 1], ip[inside, 0]], rtol=1e-6, atol=0)

@@ -19,7 +19,7 @@ ACCUM_MEAN, ACCUM_SUM = 0, 1
 SYMBOLS = [
     "vrb_create", "vrb_destroy", "vrb_last_error", "vrb_status_string", "vrb_abi_version", "vrb_set_stream", "vrb_sync",
     "vrb_resize", "vrb_grid_clear", "vrb_grid_free", "vrb_grid_upload_brick", "vrb_grid_build_from_dense",
-    "vrb_grid_build_from_dense_device", "vrb_grid_info", "vrb_grid_download", "vrb_dense_from_float",
+    "vrb_grid_build_from_dense_device", "vrb_grid_info", "vrb_grid_download", "vrb_debug_sample_density", "vrb_dense_from_float",
     "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_set_option", "vrb_scale",
     "vrb_clear", "vrb_set_counting", "vrb_get_counters", "vrb_tonemap", "vrb_download_color", "vrb_download_color_ldr",
     "vrb_download_framebuffer", "vrb_upload_color", "vrb_color_device_ptr", "vrb_bind_color", "vrb_reduce", "vrb_copy_rows",
@@ -106,6 +106,7 @@ def load_library(path: str = LIB_PATH):
     L.vrb_grid_build_from_dense_device.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3, cf, cf]
     L.vrb_grid_info.argtypes = [vp, ci, ci, C.POINTER(BrickView)]
     L.vrb_grid_download.argtypes = [vp, ci, ci, C.POINTER(BrickView)]
+    L.vrb_debug_sample_density.argtypes = [vp, ci, ci, vp, C.c_size_t, ci, vp]
     L.vrb_dense_from_float.argtypes = [vp, vp, C.c_uint32 * 3, vp, C.c_float * 2]
     L.vrb_env_upload.argtypes = [vp, vp, ci, ci]
     L.vrb_env_download_impmap.argtypes = [vp, ci, vp]
@@ -217,6 +218,14 @@ class Context:
             v.range_mips[i] = _ptr(mips[i])
         self._ck(self.lib.vrb_grid_download(self.handle, slot, frame, C.byref(v)))
         return BrickGridData(nb, ad, cnt, ind, rng, atl if atlas else np.zeros((0, ad[1], ad[0]), np.uint8), mips)
+
+    def sample_density(self, ipos_xyz, mode=0, slot=SLOT_DENSITY, frame=0):
+        """Density at index-space points through the tracer's fetch functions: mode 0 trilinear (records + u8 atlas),
+        1 trilinear (decoded apron blocks, the production path), 2 nearest voxel at floor(p)."""
+        pts = np.ascontiguousarray(ipos_xyz, np.float32).reshape(-1, 3)
+        out = np.empty(len(pts), np.float32)
+        self._ck(self.lib.vrb_debug_sample_density(self.handle, slot, frame, _ptr(pts), len(pts), mode, _ptr(out)))
+        return out
 
     def dense_from_float(self, data):
         data = np.ascontiguousarray(data, np.float32)

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
             float d;
             float3 tf_rgb = f3(1.f);
             if (TF) {
-                const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * density_trilinear(a.density, at) * a.p.vol_inv_majorant);
+                const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * (MT::decoded ? density_trilinear_decoded(a.density, at) : density_trilinear(a.density, at)) * a.p.vol_inv_majorant);
                 d = a.p.vol_majorant * rgba.w;
                 tf_rgb = f3(rgba.x, rgba.y, rgba.z);
             } else {

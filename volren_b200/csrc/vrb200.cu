@@ -9,6 +9,7 @@
 #include "vr_trace2.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -42,6 +43,9 @@ struct DeviceGrid {
     uint2* recp = nullptr;       // padded (nb + 2)^3 records for the trilinear fetch
     uint8_t* atlas_lin = nullptr;   // n_slots bricks + one all-zero brick
     size_t n_slots = 0;
+    uint32_t* cslot = nullptr;      // (nb + 1)^3 cells -> decoded apron block (0 = shared zero block)
+    float* datlas = nullptr;        // (n_dblocks + 1) x 729 decoded voxels
+    size_t n_dblocks = 0;
     // majorant tables of the persistent kernel, valid for maj_key
     float* maj[4] = { nullptr, nullptr, nullptr, nullptr };
     uint64_t maj_key = 0;
@@ -90,6 +94,7 @@ struct vrb_ctx {
     uint64_t cost_key = 0;       // view the costs in tile_cost belong to (0 = none)
     bool lpt = true;             // VRB200_LPT=0 disables
     bool cull = true;            // VRB200_CULL=0 disables the screen-space box culling
+    bool count_culled = false;   // option "count_culled": the counting build keeps the culling (events of the production launch, not of the reference algorithm)
     int tile_coords_tx = 0;      // tiles_x the packed coordinates in tile_iota were made for
     bool counting = false;
     int kernel = 0;            // 0 = persistent FastMath (production), 1 = simple strict cross-check, 2 = persistent StrictMath
@@ -136,6 +141,7 @@ void free_grid(DeviceGrid& g, cudaStream_t s) {
     pool_free(g.indirection, s); pool_free(g.range, s); pool_free(g.atlas, s);
     for (auto& m : g.mips) pool_free(m, s);
     pool_free(g.rec, s); pool_free(g.recp, s); pool_free(g.atlas_lin, s);
+    pool_free(g.cslot, s); pool_free(g.datlas, s);
     for (auto& m : g.maj) pool_free(m, s);
     g = DeviceGrid();
 }
@@ -169,6 +175,43 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
     if (g.n_slots) {
         k_linearize_atlas<<<grid_for(g.n_slots * 64, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.atlas, g.atlas_dim, g.atlas_lin, g.n_slots);
         CK_LAUNCH();
+    }
+    // decoded apron blocks for the production trilinear fetch (vr_trace.cuh density_trilinear_decoded)
+    {
+        const size_t nc = size_t(g.nb.x + 1) * (g.nb.y + 1) * (g.nb.z + 1);
+        uint32_t *flags = nullptr, *excl = nullptr;
+        void* tmp = nullptr;
+        size_t tmp_bytes = 0;
+        if (!g.cslot) CK(pool_alloc(&g.cslot, nc * 4, ctx->stream));
+        CK(pool_alloc(&flags, nc * 4, ctx->stream));
+        CK(pool_alloc(&excl, (nc + 1) * 4, ctx->stream));
+        k_cell_flags<<<grid_for(nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.rec, g.nb, flags);
+        CK_LAUNCH();
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, excl, nc, ctx->stream));
+        CK(pool_alloc(&tmp, tmp_bytes, ctx->stream));
+        CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, excl, nc, ctx->stream));
+        k_cell_slots<<<grid_for(nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(flags, excl, nc, g.cslot);
+        CK_LAUNCH();
+        uint32_t last[2] = { 0, 0 };    // exclusive sum and flag of the last cell -> number of blocks
+        CK(cudaMemcpyAsync(&last[0], excl + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&last[1], flags + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const size_t n_blocks = size_t(last[0]) + last[1];
+        if (!g.datlas || n_blocks > g.n_dblocks) {
+            pool_free(g.datlas, ctx->stream);
+            g.datlas = nullptr;
+            CK(pool_alloc(&g.datlas, (n_blocks + 1) * DBRICK * 4, ctx->stream));
+            g.n_dblocks = n_blocks;
+        }
+        CK(cudaMemsetAsync(g.datlas, 0, DBRICK * 4, ctx->stream));      // block 0: zeros
+        if (n_blocks) {
+            GridView v;
+            memset(&v, 0, sizeof v);
+            v.nb = g.nb; v.rec = g.rec; v.atlas_lin = g.atlas_lin;
+            k_decode_cells<<<grid_for(nc * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(v, g.cslot, g.datlas);
+            CK_LAUNCH();
+        }
+        pool_free(flags, ctx->stream); pool_free(excl, ctx->stream); pool_free(tmp, ctx->stream);
     }
     g.valid = true;
     return VRB_OK;
@@ -283,6 +326,8 @@ GridView make_view(const DeviceGrid& g) {
     v.recp = g.recp;
     v.psx = g.nb.x + 2;
     v.psxy = (g.nb.x + 2) * (g.nb.y + 2);
+    v.cslot = g.cslot;
+    v.datlas = g.datlas;
     return v;
 }
 
@@ -546,6 +591,35 @@ int vrb_grid_info(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out) {
     return VRB_OK;
 }
 
+// density at index-space points through the tracer's own fetch functions (parity tests):
+// mode 0 = lookup_density_trilinear via records + u8 atlas, 1 = the same via the decoded apron blocks, 2 = nearest voxel at floor(p)
+__global__ void k_sample_density(const GridView g, const float* __restrict__ pts, size_t n, int mode, float* __restrict__ out) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const float3 p = f3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+        out[i] = mode == 0 ? density_trilinear(g, p) : mode == 1 ? density_trilinear_decoded(g, p) : brick_value(g, int(floorf(p.x)), int(floorf(p.y)), int(floorf(p.z)));
+    }
+}
+
+int vrb_debug_sample_density(vrb_ctx* ctx, int slot, int frame, const float* ipos_xyz, size_t n, int mode, float* out) {
+    int st = check_slot_frame(ctx, slot, frame);
+    if (st) return st;
+    auto it = ctx->frames.find(frame);
+    if (it == ctx->frames.end() || !it->second.slot[slot].valid) return fail(ctx, VRB_ERR_STATE, "no grid in slot %d frame %d", slot, frame);
+    if (!ipos_xyz || !out || mode < 0 || mode > 2) return fail(ctx, VRB_ERR_INVALID, "bad arguments");
+    if (n == 0) return VRB_OK;
+    DeviceGuard guard(ctx->device);
+    float *d_p = nullptr, *d_o = nullptr;
+    CK(pool_alloc(&d_p, n * 12, ctx->stream));
+    CK(pool_alloc(&d_o, n * 4, ctx->stream));
+    CK(cudaMemcpyAsync(d_p, ipos_xyz, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    k_sample_density<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(make_view(it->second.slot[slot]), d_p, n, mode, d_o);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(out, d_o, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    pool_free(d_p, ctx->stream); pool_free(d_o, ctx->stream);
+    return VRB_OK;
+}
+
 int vrb_grid_download(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out) {
     int st = vrb_grid_info(ctx, slot, frame, out);
     if (st) return st;
@@ -720,7 +794,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     // ---- screen-space culling of the volume's box (hidden environment only; never in the counting build) ----
     const int fold_x0 = a.x0, fold_y0 = a.y0, fold_x1 = a.x1, fold_y1 = a.y1;       // the caller's region
     bool box_cull_ok = false;
-    if (!params->show_environment && !ctx->counting && ctx->cull) {
+    if (!params->show_environment && (!ctx->counting || ctx->count_culled) && ctx->cull) {
         // view_dir (common.glsl:76-80): dir ~ cam_transform * (px, py, z), px = (x + jitter - w/2) / h, z = -0.5 / tan(fov/2).
         // A box corner c maps to v = cam_transform^-1 (c - cam_pos); in front of the camera (v.z < 0) it projects to
         // px = v.x * z / v.z. The bounding rectangle of the 8 projections (+ 1 pixel) contains every pixel that can hit.
@@ -867,6 +941,7 @@ int vrb_set_option(vrb_ctx* ctx, const char* name, int value) {
     if (!name) return fail(ctx, VRB_ERR_INVALID, "NULL option name");
     if (!strcmp(name, "lpt")) ctx->lpt = value != 0;
     else if (!strcmp(name, "cull")) ctx->cull = value != 0;
+    else if (!strcmp(name, "count_culled")) ctx->count_culled = value != 0;
     else if (!strcmp(name, "pass")) { if (value < 1) return fail(ctx, VRB_ERR_INVALID, "pass must be >= 1"); ctx->pass_samples = value; }
     else return fail(ctx, VRB_ERR_INVALID, "unknown option '%s'", name);
     return VRB_OK;
