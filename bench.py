@@ -253,9 +253,10 @@ def main():
     # spp slices: rank r traces S of the S*world samples of a step into a SUM buffer, one NCCL reduce(SUM) to rank 0
     pr = PartitionedRenderer(color, trace_fn, partition="spp")
 
-    def step():
-        """one step: S samples per pixel on every rank (weak scaling), then the accumulation-buffer reduce"""
-        pr.render(S * world)
+    def step(last=True):
+        """one step: S more samples per pixel on every rank (weak scaling). The float4 accumulation buffers are reduced to
+        rank 0 ONCE per frame: by the last step of the frame, inside the timed region."""
+        pr.render(S * world, reduce=last)
 
     # ---- counting pass (defines the algorithmic bytes of one launch) ----
     ctx.set_counting(True)
@@ -288,7 +289,7 @@ def main():
         barrier()
         kev_cur[0] = kev[k]
         ev[k][0].record()
-        step()
+        step(last=(k == args.steps - 1))        # the K timed steps are one frame of K * S * N samples: one NCCL reduce at its end
         ev[k][1].record()
         kev_cur[0] = None
         barrier()
@@ -383,7 +384,7 @@ def main():
             "dtype": "f32", "data": "reference assets (smoke.brick, lut.txt, hdr) committed under tests/golden/assets",
             "config": {
                 "workload": "configs[1]: smoke.brick + lut.txt TF (pathtracer_brick_tf), 1920x1080, 128 bounces",
-                "spp_per_step": S, "full_config_spp": FULL_SPP, "partition": "spp slices + NCCL reduce" if world > 1 else "single GPU",
+                "spp_per_step": S, "full_config_spp": FULL_SPP, "partition": "spp slices, one NCCL reduce(SUM) of the float4 buffers at the end of the K-step frame (inside the timed region)" if world > 1 else "single GPU",
                 "l2": "flushed between timed iterations (256 MiB fill); the 1.9 MB volume is L2-resident by nature",
             },
             "roofline": {

@@ -53,9 +53,15 @@ def _worker(rank, world, port, partition, out_dir):
     def trace_fn(first, n, tile, accum):
         o.trace(sc, p, first, n, color=view, tile=tile, accum_mode=accum)
 
-    pr = PartitionedRenderer(color, trace_fn, partition=partition)
+    deferred = partition.endswith("_deferred")
+    pr = PartitionedRenderer(color, trace_fn, partition=partition.split("_")[0])
     pr.reset()
-    work = [pr.render(3), pr.render(2)]                              # two progressive batches: 5 spp in total
+    if deferred:                                                     # one collective per frame
+        work = [pr.render(3, reduce=False), pr.render(2, reduce=False)]
+        pr.finish()
+        pr.finish()                                                  # idempotent
+    else:
+        work = [pr.render(3), pr.render(2)]                          # two progressive batches: 5 spp in total
     if rank == 0:
         np.save(os.path.join(out_dir, f"{partition}.npy"), view.copy())
     np.save(os.path.join(out_dir, f"{partition}_work{rank}.npy"), np.array(work))
@@ -63,12 +69,12 @@ def _worker(rank, world, port, partition, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("partition", ["tile", "spp"])
+@pytest.mark.parametrize("partition", ["tile", "spp", "tile_deferred", "spp_deferred"])
 def test_partitioned_render_world2_gloo(partition, tmp_path, oracle, smoke_grid, env_rgb, env_pyramid):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import readme_scene
-    port = 29500 + (os.getpid() % 2000) + (0 if partition == "tile" else 1)
+    port = 29500 + (os.getpid() % 2000) + ["tile", "spp", "tile_deferred", "spp_deferred"].index(partition)
     mp.spawn(_worker, args=(2, port, partition, str(tmp_path)), nprocs=2, join=True)
     got = np.load(tmp_path / f"{partition}.npy")
     W, H = 32, 24
@@ -76,7 +82,7 @@ def test_partitioned_render_world2_gloo(partition, tmp_path, oracle, smoke_grid,
     sc = oracle.make_scene(smoke_grid, env_rgb, env_pyramid)
     want, _ = oracle.trace(sc, p, 1, 5)                              # single process, reference running mean over samples 1..5
     w0, w1 = np.load(tmp_path / f"{partition}_work0.npy"), np.load(tmp_path / f"{partition}_work1.npy")
-    if partition == "tile":
+    if partition.startswith("tile"):
         assert np.array_equal(got, want)                             # assembly is exact
         assert w0[0].tolist() == [0, 12] and w1[0].tolist() == [12, 24]
     else:

@@ -432,26 +432,49 @@ __global__ void k_tile_keys(const unsigned int* __restrict__ tile_live, const un
 __global__ void __launch_bounds__(256) k_fold(float4* __restrict__ color, const float4* __restrict__ lbuf, size_t lbuf_stride, int W, int x0, int y0, int x1, int y1,
                                               int tx0, int ty0, int tx1, int ty1, int first_sample, int n_samples, int accum_mode,
                                               const unsigned int* __restrict__ tile_live, const unsigned int* __restrict__ info, int tiles_x) {
-    const int rw = x1 - x0;
-    const size_t n = size_t(rw) * (y1 - y0);
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
-        const int x = x0 + int(i % rw), y = y0 + int(i / rw);
-        const size_t p = size_t(y) * W + x;
-        bool traced = x >= tx0 && x < tx1 && y >= ty0 && y < ty1;
-        if (traced && tile_live && info[1] == 0u) traced = tile_live[((y - ty0) >> 2) * tiles_x + ((x - tx0) >> 3)] != 0u;    // k_tile_mask
-        float4 acc = color[p];
-        if (!traced && accum_mode != VRB_ACCUM_MEAN) continue;      // sum mode: + 0
+    // block = 64 x 4 pixels (grid covers the region): coalesced 1 KiB rows, no integer division
+    const int x = x0 + blockIdx.x * 64 + (threadIdx.x & 63), y = y0 + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= x1 || y >= y1) return;
+    const size_t p = size_t(y) * W + x;
+    bool traced = x >= tx0 && x < tx1 && y >= ty0 && y < ty1;
+    if (traced && tile_live && info[1] == 0u) traced = tile_live[((y - ty0) >> 2) * tiles_x + ((x - tx0) >> 3)] != 0u;    // k_tile_mask
+    float4 acc = color[p];
+    if (!traced) {
+        // every sample is (0, 0, 0, 0): the sum does not change; the running mean of an all-zero pixel stays zero
+        if (accum_mode != VRB_ACCUM_MEAN || (acc.x == 0.f && acc.y == 0.f && acc.z == 0.f && acc.w == 0.f)) return;
         for (int j = 0; j < n_samples; ++j) {
-            const float4 L = traced ? __ldcs(lbuf + size_t(j) * lbuf_stride + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (accum_mode == VRB_ACCUM_MEAN) {
-                const float w = 1.f / float(first_sample + j);
-                acc.x = mix_rn(acc.x, L.x, w); acc.y = mix_rn(acc.y, L.y, w); acc.z = mix_rn(acc.z, L.z, w); acc.w = mix_rn(acc.w, L.w, w);
-            } else {
-                acc.x += L.x; acc.y += L.y; acc.z += L.z; acc.w += L.w;
-            }
+            const float w = 1.f / float(first_sample + j);
+            acc.x = mix_rn(acc.x, 0.f, w); acc.y = mix_rn(acc.y, 0.f, w); acc.z = mix_rn(acc.z, 0.f, w); acc.w = mix_rn(acc.w, 0.f, w);
         }
         color[p] = acc;
+        return;
     }
+    const float4* src = lbuf + p;
+    int j = 0;
+    for (; j + 4 <= n_samples; j += 4) {            // four independent loads in flight per thread
+        float4 L[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) L[k] = __ldcs(src + size_t(j + k) * lbuf_stride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (accum_mode == VRB_ACCUM_MEAN) {
+                const float w = 1.f / float(first_sample + j + k);
+                acc.x = mix_rn(acc.x, L[k].x, w); acc.y = mix_rn(acc.y, L[k].y, w); acc.z = mix_rn(acc.z, L[k].z, w); acc.w = mix_rn(acc.w, L[k].w, w);
+            } else {
+                acc.x += L[k].x; acc.y += L[k].y; acc.z += L[k].z; acc.w += L[k].w;
+            }
+        }
+    }
+    for (; j < n_samples; ++j) {
+        const float4 L = __ldcs(src + size_t(j) * lbuf_stride);
+        if (accum_mode == VRB_ACCUM_MEAN) {
+            const float w = 1.f / float(first_sample + j);
+            acc.x = mix_rn(acc.x, L.x, w); acc.y = mix_rn(acc.y, L.y, w); acc.z = mix_rn(acc.z, L.z, w); acc.w = mix_rn(acc.w, L.w, w);
+        } else {
+            acc.x += L.x; acc.y += L.y; acc.z += L.z; acc.w += L.w;
+        }
+    }
+    color[p] = acc;
 }
 
 }  // namespace vr

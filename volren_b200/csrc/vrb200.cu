@@ -192,11 +192,14 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
         CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, excl, nc, ctx->stream));
         k_cell_slots<<<grid_for(nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(flags, excl, nc, g.cslot);
         CK_LAUNCH();
-        uint32_t last[2] = { 0, 0 };    // exclusive sum and flag of the last cell -> number of blocks
-        CK(cudaMemcpyAsync(&last[0], excl + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(&last[1], flags + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        const size_t n_blocks = size_t(last[0]) + last[1];
+        size_t n_blocks = nc;           // small lattices (<= 64 MiB of blocks): worst case, no read-back and no host sync
+        if (nc * DBRICK * 4 > (size_t(64) << 20)) {
+            uint32_t last[2] = { 0, 0 };    // exclusive sum and flag of the last cell -> number of blocks
+            CK(cudaMemcpyAsync(&last[0], excl + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(&last[1], flags + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            n_blocks = size_t(last[0]) + last[1];
+        }
         if (!g.datlas || n_blocks > g.n_dblocks) {
             pool_free(g.datlas, ctx->stream);
             g.datlas = nullptr;
@@ -895,7 +898,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         a.tile_cost = nullptr;
         a.n_live = nullptr;
         if (nothing_visible) {
-            k_fold<<<grid_for(size_t(fold_x1 - fold_x0) * (fold_y1 - fold_y0), 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
+            k_fold<<<dim3((fold_x1 - fold_x0 + 63) / 64, (fold_y1 - fold_y0 + 3) / 4), 256, 0, ctx->stream>>>(
                 ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode, nullptr, nullptr, 0);
             CK_LAUNCH();
             continue;
@@ -927,8 +930,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
         void* kargs[] = { (void*)&a };
         CK(cudaLaunchKernel(fn, dim3(blocks), dim3(VR_TRACE_BLOCK), kargs, 0, ctx->stream));
-        const size_t n_region = size_t(fold_x1 - fold_x0) * (fold_y1 - fold_y0);
-        k_fold<<<grid_for(n_region, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
+        k_fold<<<dim3((fold_x1 - fold_x0 + 63) / 64, (fold_y1 - fold_y0 + 3) / 4), 256, 0, ctx->stream>>>(
             ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode,
             mask ? ctx->tile_live : nullptr, mask ? ctx->live_info : nullptr, a.tiles_x);
         CK_LAUNCH();

@@ -50,13 +50,19 @@ class PartitionedRenderer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.samples = 0
+        self.holds_sum = False
+        self.pending = False
 
     def reset(self):
         self.samples = 0
+        self.holds_sum = False          # spp mode: `color` is a local SUM that has not been reduced yet
+        self.pending = False            # tile mode: bands traced since the last gather
         self.color.zero_()
 
-    def render(self, n_samples: int):
-        """n more samples per pixel (job-wide). Returns the work this rank did: (first, n) or (y0, y1)."""
+    def render(self, n_samples: int, reduce: bool = True):
+        """n more samples per pixel (job-wide). Returns the work this rank did: (first, n) or (y0, y1).
+        reduce=False defers the collective: the frame is complete (on rank dst) only after finish() -- one reduce per
+        frame instead of one per batch."""
         H, W = int(self.color.shape[0]), int(self.color.shape[1])
         first = self.samples + 1
         if self.world == 1:
@@ -66,30 +72,52 @@ class PartitionedRenderer:
         if self.partition == "spp":
             # every rank keeps a running SUM of its own slices; rank dst's buffer doubles as the reduction target, so its
             # mean of the previous batches is turned back into a sum first
-            if self.rank == self.dst and self.samples > 0:
-                self.color.mul_(float(self.samples))
-            elif self.rank != self.dst:
-                self.color.zero_()
+            if not self.holds_sum:
+                if self.rank == self.dst and self.samples > 0:
+                    self.color.mul_(float(self.samples))
+                elif self.rank != self.dst:
+                    self.color.zero_()
+                self.holds_sum = True
             mine = spp_slices(first, n_samples, self.world)[self.rank]
             if mine[1] > 0:
                 self.trace_fn(mine[0], mine[1], None, ACCUM_SUM)
-            self.dist.reduce(self.color, dst=self.dst, op=self.dist.ReduceOp.SUM, group=self.group)
             self.samples += n_samples
-            if self.rank == self.dst:
-                self.color.mul_(1.0 / float(self.samples))
+            if reduce:
+                self.finish()
             return mine
         # tiles: every rank owns a band of rows and keeps the reference running mean there; rows outside the band are
         # zero, so the SUM reduction assembles the image exactly (x + 0 == x)
         y0, y1 = row_bands(H, self.world)[self.rank]
-        if self.samples > 0:     # rows that are not this rank's own (gathered or scratch) must not enter the next sum
+        if self.samples > 0 and not self.pending:     # rows that are not this rank's own (gathered or scratch) must not enter the next sum
             self.color[:y0].zero_()
             self.color[y1:].zero_()
         if y0 < y1:
             self.trace_fn(first, n_samples, (0, y0, W, y1), ACCUM_MEAN)
+        self.samples += n_samples
+        self.pending = True
+        if reduce:
+            self.finish()
+        return (y0, y1)
+
+    def finish(self):
+        """The one collective of a frame: after it rank dst holds the MEAN image of all samples rendered since reset()."""
+        if self.world == 1:
+            return
+        if self.partition == "spp":
+            if not self.holds_sum:
+                return
+            self.dist.reduce(self.color, dst=self.dst, op=self.dist.ReduceOp.SUM, group=self.group)
+            if self.rank == self.dst:
+                self.color.mul_(1.0 / float(self.samples))
+            self.holds_sum = False
+            return
+        if not self.pending:
+            return
+        H = int(self.color.shape[0])
+        y0, y1 = row_bands(H, self.world)[self.rank]
         keep = self.color[y0:y1].clone() if self.rank != self.dst else None
         self.dist.reduce(self.color, dst=self.dst, op=self.dist.ReduceOp.SUM, group=self.group)
         if keep is not None:     # reduce() may scribble partial sums into non-destination buffers (gloo does)
             self.color.zero_()
             self.color[y0:y1] = keep
-        self.samples += n_samples
-        return (y0, y1)
+        self.pending = False
