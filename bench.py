@@ -377,6 +377,12 @@ def main():
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
+        traffic, traffic_src = None, "no capture committed"
+        try:        # DRAM bytes of one launch of the same kernel on the same workload, from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+            traffic, traffic_src = tj["dram_read_bytes"] + tj["dram_write_bytes"], tj["source"]
+        except Exception:
+            pass
         achieved = alg_bytes / (kms * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -389,7 +395,8 @@ def main():
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": None, "peak_kind": peak_kind, "kernel": "k_trace_persistent<TF, FastMath>", "kernel_ms": kms,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, " + traffic_src + ")",
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_kind": peak_kind, "kernel": "k_trace_persistent<TF, FastMath>", "kernel_ms": kms,
                 "algorithmic_bytes_per_sample": alg_bytes / counters["n_samples"], "counters_per_sample": {k: v / counters["n_samples"] for k, v in counters.items()},
                 "executed": {"bytes_per_sample": exec_bytes / counters["n_samples"], "achieved": exec_bytes / (kms * 1e-3) / 1e9,
                              "traced_fraction": counters_exec["n_samples"] / counters["n_samples"],
