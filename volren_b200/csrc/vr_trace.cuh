@@ -55,6 +55,7 @@ struct GridView {
     // shared by every cell whose 8 bricks are all (0, 0)-range or outside the grid
     const uint32_t* cslot;
     const float* datlas;
+    const float* dmax;         // per brick: max of brick_value over the brick's 12^3 tap window (k_brick_dmax)
 };
 constexpr uint32_t DBRICK = 729u;
 
@@ -67,7 +68,7 @@ struct TraceArgs {
     float4* color;
     int x0, y0, x1, y1;
     int first_sample, n_samples, accum_mode;
-    unsigned long long* counters;  // 7 x u64 (vrb_counters order) or nullptr
+    unsigned long long* counters;  // 8 x u64 (vrb_counters order, then the early rejections) or nullptr
     Mat4 emis_from_density;        // vol_emission_inv_transform * vol_density_transform (common.glsl:325)
     float cam_z;                   // view_dir's z = -.5f / tan(.5f * M_PI * cam_fov / 180.f) (common.glsl:78), host libm
     // persistent kernel only
@@ -86,22 +87,28 @@ struct TraceArgs {
     // screen-space brick mask (hidden environment only): tile slots >= *n_live hold tiles no non-empty brick projects onto;
     // nullptr: every slot is live and n_jobs is the host's count
     const unsigned int* n_live;
+    // early rejection of tentative collisions: colmax[brick] >= every value `d` the collision test `rng * majorant < d`
+    // (common.glsl:442 / :490) can see at a point inside the brick, for the current parameters (k_collision_bound);
+    // nullptr: not available (option "early" off, emission grid bound, non-monotone LUT)
+    const float* colmax;
 };
 
 template <bool COUNT> struct Cnt;
 template <> struct Cnt<false> {
     VR_DEV void maj() {} VR_DEV void dens() {} VR_DEV void emis() {} VR_DEV void nee() {} VR_DEV void env() {} VR_DEV void real() {} VR_DEV void samp() {}
+    VR_DEV void early() {}
 };
 template <> struct Cnt<true> {
-    uint32_t n_samp = 0, n_maj = 0, n_dens = 0, n_emis = 0, n_nee = 0, n_env = 0, n_real = 0;
+    uint32_t n_samp = 0, n_maj = 0, n_dens = 0, n_emis = 0, n_nee = 0, n_env = 0, n_real = 0, n_early = 0;
+    VR_DEV void early() { ++n_early; }      // tentative collisions rejected before the fetch (a subset of n_dens)
     VR_DEV void maj() { ++n_maj; } VR_DEV void dens() { ++n_dens; } VR_DEV void emis() { ++n_emis; } VR_DEV void nee() { ++n_nee; }
     VR_DEV void env() { ++n_env; } VR_DEV void real() { ++n_real; } VR_DEV void samp() { ++n_samp; }
 };
 VR_DEV void flush_counters(const TraceArgs&, const Cnt<false>&) {}
 VR_DEV void flush_counters(const TraceArgs& a, const Cnt<true>& c) {
-    const uint32_t v[7] = { c.n_samp, c.n_maj, c.n_dens, c.n_emis, c.n_nee, c.n_env, c.n_real };
+    const uint32_t v[8] = { c.n_samp, c.n_maj, c.n_dens, c.n_emis, c.n_nee, c.n_env, c.n_real, c.n_early };
 #pragma unroll
-    for (int i = 0; i < 7; ++i) atomicAdd(a.counters + i, (unsigned long long)v[i]);
+    for (int i = 0; i < 8; ++i) atomicAdd(a.counters + i, (unsigned long long)v[i]);
 }
 
 // exact u8 / 255.f (GL unorm8 -> float) without a divide: reciprocal multiply + one FMA correction step
@@ -123,7 +130,7 @@ VR_DEV float brick_value(const GridView& g, int x, int y, int z) {
     float unorm = 0.f;
     if (r.x != 0xffffffffu)
         unorm = unorm8_to_float(__ldg(g.atlas_lin + size_t(r.x) * 512u + uint32_t(((z & 7) << 6) | ((y & 7) << 3) | (x & 7))));
-    return lo + unorm * (hi - lo);
+    return fmaf(unorm, hi - lo, lo);      // explicit: the same rounding at every call site (tracer, decoded blocks, brick bounds)
 }
 
 // lookup_majorant (common.glsl:278-281) without the density_scale factor
@@ -137,7 +144,12 @@ VR_DEV float brick_majorant(const GridView& g, float3 ipos, int mip) {
 }
 
 // stochastic_tricubic_filter (common.glsl:221-244): 9 draws, weighted reservoir over the 4 B-spline taps.
-// FastMath tests `r * max(1e-3, sum) < w` instead of `r < w / max(1e-3, sum)` (no division).
+// FastMath tests `r * sum < w` instead of `r < w / max(1e-3, sum)` (no division; the running sums of the B-spline weights
+// are w0 + w1 in [1/6, 5/6], 1 - w3 >= 5/6 and 1, so the max() never acts) and evaluates the weights in Horner form with
+// the 1/6 folded into the coefficients (21 instead of 34 instructions per axis).
+#ifndef VR_LEAN_FILTER
+#define VR_LEAN_FILTER 1
+#endif
 template <class MT>
 VR_DEV int3 stochastic_tricubic_filter(float3 ipos, uint32_t& seed) {
     const float qx = ipos.x - 0.5f, qy = ipos.y - 0.5f, qz = ipos.z - 0.5f;
@@ -150,18 +162,29 @@ VR_DEV int3 stochastic_tricubic_filter(float3 ipos, uint32_t& seed) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float t1 = t[a], t2 = t1 * t1;
-        float w = (1.f / 6.f) * (-t1 * t2 + 3 * t2 - 3 * t1 + 1);
-        float sum = w;
         int k = 0;
-        w = (1.f / 6.f) * (3 * t1 * t2 - 6 * t2 + 4);
-        sum = w + sum;
-        if (MT::fast ? (r[a] * fmaxf(1e-3f, sum) < w) : (r[a] < w / fmaxf(1e-3f, sum))) k = 1;
-        w = (1.f / 6.f) * (-3 * t1 * t2 + 3 * t2 + 3 * t1 + 1);
-        sum = w + sum;
-        if (MT::fast ? (r[3 + a] * fmaxf(1e-3f, sum) < w) : (r[3 + a] < w / fmaxf(1e-3f, sum))) k = 2;
-        w = (1.f / 6.f) * t1 * t2;
-        sum = w + sum;
-        if (MT::fast ? (r[6 + a] * fmaxf(1e-3f, sum) < w) : (r[6 + a] < w / fmaxf(1e-3f, sum))) k = 3;
+        if (MT::fast && VR_LEAN_FILTER) {
+            const float w0 = fmaf(fmaf(fmaf(-1.f / 6.f, t1, 0.5f), t1, -0.5f), t1, 1.f / 6.f);
+            const float w1 = fmaf(fmaf(0.5f, t1, -1.f), t2, 2.f / 3.f);
+            const float w2 = fmaf(fmaf(fmaf(-0.5f, t1, 0.5f), t1, 0.5f), t1, 1.f / 6.f);
+            const float w3 = (1.f / 6.f) * t1 * t2;
+            const float s1 = w0 + w1, s2 = s1 + w2, s3 = s2 + w3;
+            if (r[a] * s1 < w1) k = 1;
+            if (r[3 + a] * s2 < w2) k = 2;
+            if (r[6 + a] * s3 < w3) k = 3;
+        } else {
+            float w = (1.f / 6.f) * (-t1 * t2 + 3 * t2 - 3 * t1 + 1);
+            float sum = w;
+            w = (1.f / 6.f) * (3 * t1 * t2 - 6 * t2 + 4);
+            sum = w + sum;
+            if (MT::fast ? (r[a] * fmaxf(1e-3f, sum) < w) : (r[a] < w / fmaxf(1e-3f, sum))) k = 1;
+            w = (1.f / 6.f) * (-3 * t1 * t2 + 3 * t2 + 3 * t1 + 1);
+            sum = w + sum;
+            if (MT::fast ? (r[3 + a] * fmaxf(1e-3f, sum) < w) : (r[3 + a] < w / fmaxf(1e-3f, sum))) k = 2;
+            w = (1.f / 6.f) * t1 * t2;
+            sum = w + sum;
+            if (MT::fast ? (r[6 + a] * fmaxf(1e-3f, sum) < w) : (r[6 + a] < w / fmaxf(1e-3f, sum))) k = 3;
+        }
         idx[a] = k;
     }
     return make_int3(int(fx) + idx[0] - 1, int(fy) + idx[1] - 1, int(fz) + idx[2] - 1);
@@ -279,6 +302,47 @@ __global__ void __launch_bounds__(256) k_decode_cells(const GridView g, const ui
             const int lx = int(v % 9u), ly = int((v / 9u) % 9u), lz = int(v / 81u);
             datlas[size_t(s) * DBRICK + v] = brick_value(g, x0 + lx, y0 + ly, z0 + lz);
         }
+    }
+}
+
+// ---- per-brick density bound (early rejection of tentative collisions, vr_trace2.cuh) ---------------------
+// dmax[brick] = the exact maximum of brick_value() over the 12^3 voxel window -2 ... +9 around the brick: every tap a
+// lookup at a point inside the brick can touch (stochastic tricubic: floor(p - .5) + {-1 ... 2}, common.glsl:221-244;
+// trilinear: floor(p - .5) + {0, 1}, :289-297) -- the same window voldata dilates its ranges by (grid_brick.cpp:83-92),
+// but over the DECODED values the tracer reads, so `value <= dmax` holds bit for bit (the fp16 range is rounded to
+// nearest and can sit below a decoded voxel). One warp per brick; a brick whose 27 neighbours are all unallocated (or
+// outside the grid: texelFetch -> 0) needs no voxel loop. A non-finite value in the window yields +inf (never rejects).
+__global__ void __launch_bounds__(256) k_brick_dmax(const GridView g, float* __restrict__ dmax) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
+    const int lane = threadIdx.x & 31;
+    for (size_t i = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 5; i < n; i += (size_t(gridDim.x) * blockDim.x) >> 5) {
+        const int bx = int(i % g.nb.x), by = int((i / g.nb.x) % g.nb.y), bz = int(i / (size_t(g.nb.x) * g.nb.y));
+        float hi = -INFINITY;
+        bool bad = false, allocated = false;
+        if (lane < 27) {
+            const int x = bx + lane % 3 - 1, y = by + (lane / 3) % 3 - 1, z = bz + lane / 9 - 1;
+            float v = 0.f;
+            if (unsigned(x) < g.nb.x && unsigned(y) < g.nb.y && unsigned(z) < g.nb.z) {
+                const uint2 r = g.rec[(size_t(z) * g.nb.y + y) * g.nb.x + x];
+                allocated = r.x != 0xffffffffu;
+                v = fmaf(0.f, range_hi(r.y) - range_lo(r.y), range_lo(r.y));     // brick_value of an unallocated brick
+            }
+            hi = v;
+            bad = !isfinite(v);
+        }
+        if (__any_sync(FULL, allocated)) {
+            hi = -INFINITY;
+            for (int v = lane; v < 1728; v += 32) {
+                const float val = brick_value(g, 8 * bx - 2 + v % 12, 8 * by - 2 + (v / 12) % 12, 8 * bz - 2 + v / 144);
+                hi = fmaxf(hi, val);
+                bad |= !isfinite(val);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, o));
+        bad = __any_sync(FULL, bad);
+        if (lane == 0) dmax[i] = bad ? INFINITY : hi;
     }
 }
 
