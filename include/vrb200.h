@@ -144,9 +144,7 @@ int vrb_grid_download(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out);
 /* test hook: the density the tracer itself fetches at n index-space points (x, y, z triples, host memory).
  * mode 0 = lookup_density_trilinear (common.glsl:289-297, without density_scale) through the records + u8 atlas,
  * mode 1 = the same through the decoded apron blocks the production kernel reads (must equal mode 0 bit for bit),
- * mode 2 = lookup_density_brick at floor(p) (common.glsl:268-275 == BrickGrid::lookup, grid_brick.cpp:148-154; 0 outside),
- * mode 3 = the density bound of the brick containing p: max of mode 2 over the brick's 12^3 tap window (voxels -2 ... +9,
- *          the dilation of grid_brick.cpp:83-92), used to reject tentative collisions before the fetch; +inf outside */
+ * mode 2 = lookup_density_brick at floor(p) (common.glsl:268-275 == BrickGrid::lookup, grid_brick.cpp:148-154; 0 outside) */
 int vrb_debug_sample_density(vrb_ctx* ctx, int slot, int frame, const float* ipos_xyz, size_t n, int mode, float* out);
 /* voldata::DenseGrid(w,h,d,const float*) (voldata/src/grid_dense.cpp:57-95): global min/max + 8-bit quantise.
  * out_u8 (host, n bytes) and out_minmax[2]; if d_out_u8 != NULL the quantised grid is also left on the device. */
@@ -180,10 +178,8 @@ int vrb_set_kernel(vrb_ctx* ctx, int kind);
  * "cull" (hidden environment only: pixels outside the screen rectangle of the volume's box and 8x4 tiles onto which no
  * brick with a positive majorant projects are exactly zero and are not traced, default 1), "pass" (samples per pixel and
  * internal pass, default 16), "count_culled" (default 0: the counting build traces every sample, i.e. counts the events of
- * the reference algorithm; 1: it keeps the culling and counts the events the production launch executes), "early"
- * (default 1: a tentative collision whose test draw already fails against the brick's density bound is rejected without
- * fetching the density -- the draw sits a fixed number of LCG steps ahead, the outcome of common.glsl:442/:490 is unchanged).
- * Environment variables VRB200_LPT / VRB200_CULL / VRB200_PASS / VRB200_EARLY set the defaults. */
+ * the reference algorithm; 1: it keeps the culling and counts the events the production launch executes).
+ * Environment variables VRB200_LPT / VRB200_CULL / VRB200_PASS set the defaults. */
 int vrb_set_option(vrb_ctx* ctx, const char* name, int value);
 /* color *= s (finalise VRB_ACCUM_SUM buffers) */
 int vrb_scale(vrb_ctx* ctx, float s);
@@ -192,9 +188,6 @@ int vrb_clear(vrb_ctx* ctx);
 /* enable (1) / disable (0) the counting build of the kernels and reset the counters */
 int vrb_set_counting(vrb_ctx* ctx, int enable);
 int vrb_get_counters(vrb_ctx* ctx, vrb_counters* out);
-/* of the n_dens tentative collisions counted since vrb_set_counting, how many the production kernel rejected before
- * fetching the density (option "early"); diagnostic only, the events of the reference algorithm are vrb_counters */
-int vrb_get_early_rejections(vrb_ctx* ctx, uint64_t* out);
 
 /* ---- tonemap + readback (shader/tonemap.glsl, tonemap.fs, blit.fs; bindings.cpp:141-166) --------- */
 /* in_place != 0: shader/tonemap.glsl on `color` (src/main.cpp:540-550);

@@ -170,31 +170,3 @@ def test_decoded_apron_blocks_equal_the_canonical_fetch(ctx, smoke_grid, name):
     inside = np.all((ip >= 0) & (ip < np.array([ex, ey, ez])), axis=1)
     assert np.all(c[~inside] == 0)
     assert np.allclose(c[inside], dec[ip[inside, 2], ip[inside, 1], ip[inside, 0]], rtol=1e-6, atol=0)
-
-
-def test_brick_density_bound_is_the_exact_window_maximum(ctx):
-    """k_brick_dmax: per brick, the maximum of the decoded voxel values (lookup_density_brick) over the 12^3 window
-    -2 ... +9 around the brick (the tap footprint of the stochastic tricubic / trilinear filters, the dilation of
-    grid_brick.cpp:83-92), 0 outside the grid. Checked against a brute-force maximum of the tracer's own nearest fetch."""
-    rng = np.random.default_rng(5)
-    d, h, w = 28, 40, 52                                   # ragged: not multiples of 8
-    vox = (rng.random((d, h, w)) ** 3 * 255).astype(np.uint8)
-    vox[rng.random(vox.shape) < 0.5] = 0
-    vox[:, :, 24:44] = 0                                   # a run of empty bricks (no voxel loop) next to allocated ones
-    ctx.grid_build_from_dense(vox, 0.25, 3.0, frame=7)
-    info = ctx.grid_download(frame=7, atlas=False)
-    nbx, nby, nbz = (int(v) for v in info.n_bricks)
-    # decoded voxel values on the padded lattice [-8, 8 nb + 8)
-    zs, ys, xs = np.meshgrid(np.arange(-8, 8 * nbz + 8), np.arange(-8, 8 * nby + 8), np.arange(-8, 8 * nbx + 8), indexing="ij")
-    pts = np.stack([xs, ys, zs], -1).reshape(-1, 3).astype(np.float32) + 0.5
-    val = ctx.sample_density(pts, mode=2, frame=7).reshape(zs.shape)
-    want = np.empty((nbz, nby, nbx), np.float32)
-    for bz in range(nbz):
-        for by in range(nby):
-            for bx in range(nbx):
-                want[bz, by, bx] = val[8 * bz + 6:8 * bz + 18, 8 * by + 6:8 * by + 18, 8 * bx + 6:8 * bx + 18].max()
-    bz, by, bx = np.meshgrid(np.arange(nbz), np.arange(nby), np.arange(nbx), indexing="ij")
-    centres = np.stack([bx, by, bz], -1).reshape(-1, 3).astype(np.float32) * 8 + 4
-    got = ctx.sample_density(centres, mode=3, frame=7).reshape(want.shape)
-    assert np.array_equal(got, want)
-    assert np.isinf(ctx.sample_density(np.array([[-1.0, 0, 0]], np.float32), mode=3, frame=7)[0])

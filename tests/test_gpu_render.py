@@ -377,50 +377,3 @@ def test_screen_space_brick_mask_is_exact(smoke_ctx, oracle, smoke_grid, lut_raw
     smoke_ctx.clear()
     smoke_ctx.trace(params(cams[0], True), 1, 4)
     assert smoke_ctx.download_color()[..., 3].max() > 0
-
-
-def test_early_rejection_of_tentative_collisions_is_exact(smoke_ctx, oracle, smoke_grid, lut_raw):
-    """Option "early": a tentative collision is rejected before the density fetch when the collision test's draw (a fixed
-    number of LCG steps ahead) already fails against the brick's bound. The outcome of `rng * majorant < d`
-    (common.glsl:442 / :490) must not change: images and event counters are identical with the option on and off -- both
-    kernels, visible and hidden environment, sum mode, a camera inside the volume, a non-monotone LUT (bound unusable)."""
-    from volren_b200 import scene
-    W, H = 200, 120
-    lut, _ = oracle.lut_upload(lut_raw)
-    bad_lut = lut.copy()
-    bad_lut[:, 3] = bad_lut[::-1, 3]
-    smoke_ctx.resize(W, H)
-
-    def params(cam, use_tf, show_env, density=None):
-        st = scene.RenderSettings(bounces=12, seed=11, use_transferfunc=use_tf, show_environment=show_env)
-        scene.scale_and_move_to_unit_cube(smoke_grid.matrix(), smoke_grid.index_extent(), st)
-        if density is not None:
-            st.density_scale = density
-        return scene.make_params(W, H, cam, st, smoke_grid.matrix(), smoke_grid.index_extent(), smoke_grid.min_maj)
-
-    cams = [scene.Camera(),
-            scene.Camera(pos=np.array([.9, .5, .3], np.float32), dir=scene.normalize([-1, -.2, -.6]), fov_degree=55.0),
-            scene.Camera(pos=np.array([.05, .1, .02], np.float32), dir=scene.normalize([.3, 1, .2]))]
-    n_checked = 0
-    for table in (lut, bad_lut):
-        smoke_ctx.tf_upload(table)
-        for cam in cams:
-            for use_tf, show_env, density in ((True, False, None), (False, True, None), (False, False, 20.0), (True, True, 400.0)):
-                p = params(cam, use_tf, show_env, density)
-                images, counters = [], []
-                for early in (1, 0):
-                    smoke_ctx.set_option("early", early)
-                    smoke_ctx.clear()
-                    smoke_ctx.trace(p, 1, 3)
-                    smoke_ctx.trace(p, 4, 2, accum_mode=1)
-                    images.append(smoke_ctx.download_color())
-                    smoke_ctx.set_counting(True)
-                    smoke_ctx.trace(p, 1, 2)
-                    counters.append(smoke_ctx.get_counters().as_dict())
-                    smoke_ctx.set_counting(False)
-                assert np.array_equal(images[0], images[1]), (use_tf, show_env, density)
-                assert counters[0] == counters[1], (use_tf, show_env, density)
-                n_checked += 1
-    smoke_ctx.set_option("early", 1)
-    smoke_ctx.tf_upload(lut)
-    assert n_checked == 24 and images[0].max() > 0

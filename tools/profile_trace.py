@@ -45,5 +45,4 @@ for i in range(a.launches):
 if a.count:
     c = ctx.get_counters().as_dict(); n = c["n_samples"]
     print({k: v / n for k, v in c.items()})
-    print("early rejections / tentative collisions: %.4f" % (ctx.get_early_rejections() / max(1, c["n_dens"])))
 ctx.close()

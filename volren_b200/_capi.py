@@ -20,7 +20,7 @@ SYMBOLS = [
     "vrb_create", "vrb_destroy", "vrb_last_error", "vrb_status_string", "vrb_abi_version", "vrb_set_stream", "vrb_sync",
     "vrb_resize", "vrb_grid_clear", "vrb_grid_free", "vrb_grid_upload_brick", "vrb_grid_build_from_dense",
     "vrb_grid_build_from_dense_device", "vrb_grid_info", "vrb_grid_download", "vrb_debug_sample_density", "vrb_dense_from_float",
-    "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_set_option", "vrb_get_early_rejections", "vrb_scale",
+    "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_set_option", "vrb_scale",
     "vrb_clear", "vrb_set_counting", "vrb_get_counters", "vrb_tonemap", "vrb_download_color", "vrb_download_color_ldr",
     "vrb_download_framebuffer", "vrb_upload_color", "vrb_color_device_ptr", "vrb_bind_color", "vrb_reduce", "vrb_copy_rows",
 ]
@@ -115,7 +115,6 @@ def load_library(path: str = LIB_PATH):
     L.vrb_trace_deterministic.argtypes = [vp, C.POINTER(Params)]
     L.vrb_set_kernel.argtypes = [vp, ci]
     L.vrb_set_option.argtypes = [vp, C.c_char_p, ci]
-    L.vrb_get_early_rejections.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.vrb_scale.argtypes = [vp, cf]
     L.vrb_clear.argtypes = [vp]
     L.vrb_set_counting.argtypes = [vp, ci]
@@ -279,11 +278,6 @@ class Context:
         c = Counters()
         self._ck(self.lib.vrb_get_counters(self.handle, C.byref(c)))
         return c
-
-    def get_early_rejections(self) -> int:
-        n = C.c_uint64(0)
-        self._ck(self.lib.vrb_get_early_rejections(self.handle, C.byref(n)))
-        return int(n.value)
 
     def tonemap(self, exposure, gamma, in_place=True, tonemapping=True):
         self._ck(self.lib.vrb_tonemap(self.handle, exposure, gamma, int(in_place), int(tonemapping)))

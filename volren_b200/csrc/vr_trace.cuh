@@ -55,7 +55,6 @@ struct GridView {
     // shared by every cell whose 8 bricks are all (0, 0)-range or outside the grid
     const uint32_t* cslot;
     const float* datlas;
-    const float* dmax;         // per brick: max of brick_value over the brick's 12^3 tap window (k_brick_dmax)
 };
 constexpr uint32_t DBRICK = 729u;
 
@@ -68,7 +67,7 @@ struct TraceArgs {
     float4* color;
     int x0, y0, x1, y1;
     int first_sample, n_samples, accum_mode;
-    unsigned long long* counters;  // 8 x u64 (vrb_counters order, then the early rejections) or nullptr
+    unsigned long long* counters;  // 7 x u64 (vrb_counters order) or nullptr
     Mat4 emis_from_density;        // vol_emission_inv_transform * vol_density_transform (common.glsl:325)
     float cam_z;                   // view_dir's z = -.5f / tan(.5f * M_PI * cam_fov / 180.f) (common.glsl:78), host libm
     // persistent kernel only
@@ -87,28 +86,22 @@ struct TraceArgs {
     // screen-space brick mask (hidden environment only): tile slots >= *n_live hold tiles no non-empty brick projects onto;
     // nullptr: every slot is live and n_jobs is the host's count
     const unsigned int* n_live;
-    // early rejection of tentative collisions: colmax[brick] >= every value `d` the collision test `rng * majorant < d`
-    // (common.glsl:442 / :490) can see at a point inside the brick, for the current parameters (k_collision_bound);
-    // nullptr: not available (option "early" off, emission grid bound, non-monotone LUT)
-    const float* colmax;
 };
 
 template <bool COUNT> struct Cnt;
 template <> struct Cnt<false> {
     VR_DEV void maj() {} VR_DEV void dens() {} VR_DEV void emis() {} VR_DEV void nee() {} VR_DEV void env() {} VR_DEV void real() {} VR_DEV void samp() {}
-    VR_DEV void early() {}
 };
 template <> struct Cnt<true> {
-    uint32_t n_samp = 0, n_maj = 0, n_dens = 0, n_emis = 0, n_nee = 0, n_env = 0, n_real = 0, n_early = 0;
-    VR_DEV void early() { ++n_early; }      // tentative collisions rejected before the fetch (a subset of n_dens)
+    uint32_t n_samp = 0, n_maj = 0, n_dens = 0, n_emis = 0, n_nee = 0, n_env = 0, n_real = 0;
     VR_DEV void maj() { ++n_maj; } VR_DEV void dens() { ++n_dens; } VR_DEV void emis() { ++n_emis; } VR_DEV void nee() { ++n_nee; }
     VR_DEV void env() { ++n_env; } VR_DEV void real() { ++n_real; } VR_DEV void samp() { ++n_samp; }
 };
 VR_DEV void flush_counters(const TraceArgs&, const Cnt<false>&) {}
 VR_DEV void flush_counters(const TraceArgs& a, const Cnt<true>& c) {
-    const uint32_t v[8] = { c.n_samp, c.n_maj, c.n_dens, c.n_emis, c.n_nee, c.n_env, c.n_real, c.n_early };
+    const uint32_t v[7] = { c.n_samp, c.n_maj, c.n_dens, c.n_emis, c.n_nee, c.n_env, c.n_real };
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(a.counters + i, (unsigned long long)v[i]);
+    for (int i = 0; i < 7; ++i) atomicAdd(a.counters + i, (unsigned long long)v[i]);
 }
 
 // exact u8 / 255.f (GL unorm8 -> float) without a divide: reciprocal multiply + one FMA correction step
@@ -130,7 +123,7 @@ VR_DEV float brick_value(const GridView& g, int x, int y, int z) {
     float unorm = 0.f;
     if (r.x != 0xffffffffu)
         unorm = unorm8_to_float(__ldg(g.atlas_lin + size_t(r.x) * 512u + uint32_t(((z & 7) << 6) | ((y & 7) << 3) | (x & 7))));
-    return fmaf(unorm, hi - lo, lo);      // explicit: the same rounding at every call site (tracer, decoded blocks, brick bounds)
+    return fmaf(unorm, hi - lo, lo);      // explicit: the same rounding at every call site (tracer, decoded apron blocks)
 }
 
 // lookup_majorant (common.glsl:278-281) without the density_scale factor
@@ -302,47 +295,6 @@ __global__ void __launch_bounds__(256) k_decode_cells(const GridView g, const ui
             const int lx = int(v % 9u), ly = int((v / 9u) % 9u), lz = int(v / 81u);
             datlas[size_t(s) * DBRICK + v] = brick_value(g, x0 + lx, y0 + ly, z0 + lz);
         }
-    }
-}
-
-// ---- per-brick density bound (early rejection of tentative collisions, vr_trace2.cuh) ---------------------
-// dmax[brick] = the exact maximum of brick_value() over the 12^3 voxel window -2 ... +9 around the brick: every tap a
-// lookup at a point inside the brick can touch (stochastic tricubic: floor(p - .5) + {-1 ... 2}, common.glsl:221-244;
-// trilinear: floor(p - .5) + {0, 1}, :289-297) -- the same window voldata dilates its ranges by (grid_brick.cpp:83-92),
-// but over the DECODED values the tracer reads, so `value <= dmax` holds bit for bit (the fp16 range is rounded to
-// nearest and can sit below a decoded voxel). One warp per brick; a brick whose 27 neighbours are all unallocated (or
-// outside the grid: texelFetch -> 0) needs no voxel loop. A non-finite value in the window yields +inf (never rejects).
-__global__ void __launch_bounds__(256) k_brick_dmax(const GridView g, float* __restrict__ dmax) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
-    const int lane = threadIdx.x & 31;
-    for (size_t i = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 5; i < n; i += (size_t(gridDim.x) * blockDim.x) >> 5) {
-        const int bx = int(i % g.nb.x), by = int((i / g.nb.x) % g.nb.y), bz = int(i / (size_t(g.nb.x) * g.nb.y));
-        float hi = -INFINITY;
-        bool bad = false, allocated = false;
-        if (lane < 27) {
-            const int x = bx + lane % 3 - 1, y = by + (lane / 3) % 3 - 1, z = bz + lane / 9 - 1;
-            float v = 0.f;
-            if (unsigned(x) < g.nb.x && unsigned(y) < g.nb.y && unsigned(z) < g.nb.z) {
-                const uint2 r = g.rec[(size_t(z) * g.nb.y + y) * g.nb.x + x];
-                allocated = r.x != 0xffffffffu;
-                v = fmaf(0.f, range_hi(r.y) - range_lo(r.y), range_lo(r.y));     // brick_value of an unallocated brick
-            }
-            hi = v;
-            bad = !isfinite(v);
-        }
-        if (__any_sync(FULL, allocated)) {
-            hi = -INFINITY;
-            for (int v = lane; v < 1728; v += 32) {
-                const float val = brick_value(g, 8 * bx - 2 + v % 12, 8 * by - 2 + (v / 12) % 12, 8 * bz - 2 + v / 144);
-                hi = fmaxf(hi, val);
-                bad |= !isfinite(val);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, o));
-        bad = __any_sync(FULL, bad);
-        if (lane == 0) dmax[i] = bad ? INFINITY : hi;
     }
 }
 

@@ -51,40 +51,6 @@ __global__ void k_majorant_table(const __grid_constant__ TraceArgs a, int level,
     }
 }
 
-// Upper bound of the value `d` in the collision test `rng * majorant < d` (common.glsl:442 / :490) for a tentative
-// collision anywhere inside a brick, from the brick's exact density bound dmax (k_brick_dmax):
-//   non-TF: d = vol_density_scale * tap, tap <= dmax bit for bit, and a float multiplication by a non-negative constant is
-//           monotone -> the bound is the identical expression on dmax (no margin, exact);
-//   TF    : d = vol_majorant * tf_lookup(vol_density_scale * trilinear * vol_inv_majorant).a with a non-decreasing LUT
-//           alpha (checked by the host). The table index is followed in double with margins that cover the rounding of the
-//           seven lerps of the trilinear fetch (<= 2^-19 relative), of the products and of the approximate division of
-//           the FastMath window (<= 2^-21), and the result is rounded up.
-// The tracker rejects a tentative collision without fetching the density when `rng * majorant >= bound`: the outcome of
-// the reference's test is unchanged (images are bit-identical with the option off, tests/test_gpu_render.py).
-template <bool TF>
-__global__ void k_collision_bound(const __grid_constant__ TraceArgs a, const float* __restrict__ dmax, float* __restrict__ out, size_t n) {
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
-        const float m = dmax[i];
-        if (!TF) { out[i] = a.p.vol_density_scale * m; continue; }
-        float bound = INFINITY;
-        if (isfinite(m)) {
-            const double k = double(a.p.vol_density_scale) * double(a.p.vol_inv_majorant);     // >= 0 (host)
-            const double x = k * (double(m) + fabs(double(m)) * 0x1p-18);
-            const double nn = double(a.tf_size), width = double(a.p.tf_window_width), left = double(a.p.tf_window_left);
-            double s = (x - left) / width * nn;
-            s += (fabs(x) + fabs(left)) * 0x1p-20 / width * nn + fabs(s) * 0x1p-19 + 1e-9;
-            const double smax = double(1.0f - 1e-6f) * nn * (1.0 + 0x1p-22);
-            s = fmin(fmax(s, 0.0), smax);
-            const double fl = floor(s);
-            const uint32_t idx = min(uint32_t(fl), a.tf_size - 1u), idx1 = min(idx + 1u, a.tf_size - 1u);
-            const double f = s - fl;
-            const double alpha = double(a.lut[idx].w) * (1.0 - f) + double(a.lut[idx1].w) * f;
-            bound = __double2float_ru(double(a.p.vol_majorant) * alpha * (1.0 + 0x1p-19));
-        }
-        out[i] = bound;
-    }
-}
-
 VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
     const int bx = int(floorf(ipos.x)) >> (3 + mip), by = int(floorf(ipos.y)) >> (3 + mip), bz = int(floorf(ipos.z)) >> (3 + mip);
     const uint32_t nx = a.density.nb.x >> mip, ny = a.density.nb.y >> mip, nz = a.density.nb.z >> mip;
@@ -92,9 +58,6 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
     return __ldg(a.maj[mip] + (size_t(bz) * ny + by) * nx + bx);
 }
 
-#ifndef VR_EARLY
-#define VR_EARLY 1          // 0: build without the early rejection of tentative collisions (A/B builds)
-#endif
 #ifndef VR_TRACE_BLOCK
 #define VR_TRACE_BLOCK 128
 #endif
@@ -172,30 +135,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 mip = fminf(mip + 0.25f, 3.f);
                 if (!(tau > 0.f)) {
                     t += MT::div(tau, majorant);
-                    if (!(t >= tfar)) {     // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
-                        stage = SG_COLLIDE;
-                        // Early rejection: the collision test's draw sits a fixed number of LCG steps ahead (9 filter draws
-                        // without a transfer function, 9 dead emission draws on a camera segment), so it can be made
-                        // before the density is fetched. If it already fails against the brick's bound (k_collision_bound)
-                        // this is a null collision whatever the tap: redraw tau and keep stepping, no COLLIDE stage.
-                        if (MT::fast && VR_EARLY && a.colmax && (shadow || !a.p.has_emission)) {
-                            const float3 at = ipos + t * idir;
-                            const int bx = int(floorf(at.x)) >> 3, by = int(floorf(at.y)) >> 3, bz = int(floorf(at.z)) >> 3;
-                            if (unsigned(bx) < a.density.nb.x && unsigned(by) < a.density.nb.y && unsigned(bz) < a.density.nb.z) {
-                                uint32_t s2 = seed;
-                                if (!TF) rng_skip<9>(s2);
-                                if (!shadow) rng_skip<9>(s2);
-                                if (!(rng(s2) * majorant < __ldg(a.colmax + (size_t(bz) * a.density.nb.y + by) * a.density.nb.x + bx))) {
-                                    cnt.dens();
-                                    cnt.early();
-                                    seed = s2;
-                                    tau = -MT::log(1.f - rng(seed));
-                                    mip = fmaxf(0.f, mip - 2.f);
-                                    stage = SG_STEP;
-                                }
-                            }
-                        }
-                    }
+                    if (!(t >= tfar)) stage = SG_COLLIDE;   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
                 }
                 if (++steps > MAX_RAY_STEPS) { t = INFINITY; stage = SG_STEP; }
             }

@@ -49,10 +49,6 @@ struct DeviceGrid {
     // majorant tables of the persistent kernel, valid for maj_key
     float* maj[4] = { nullptr, nullptr, nullptr, nullptr };
     uint64_t maj_key = 0;
-    // early rejection of tentative collisions: exact per-brick density bound (k_brick_dmax) and the bound of the collision
-    // test's right-hand side for the parameters of maj_key (k_collision_bound)
-    float* dmax = nullptr;
-    float* colmax = nullptr;
 };
 
 struct Frame {
@@ -98,7 +94,6 @@ struct vrb_ctx {
     uint64_t cost_key = 0;       // view the costs in tile_cost belong to (0 = none)
     bool lpt = true;             // VRB200_LPT=0 disables
     bool cull = true;            // VRB200_CULL=0 disables the screen-space box culling
-    bool early = true;           // VRB200_EARLY=0 disables the early rejection of tentative collisions (option "early")
     bool count_culled = false;   // option "count_culled": the counting build keeps the culling (events of the production launch, not of the reference algorithm)
     int tile_coords_tx = 0;      // tiles_x the packed coordinates in tile_iota were made for
     bool counting = false;
@@ -148,7 +143,6 @@ void free_grid(DeviceGrid& g, cudaStream_t s) {
     pool_free(g.rec, s); pool_free(g.recp, s); pool_free(g.atlas_lin, s);
     pool_free(g.cslot, s); pool_free(g.datlas, s);
     for (auto& m : g.maj) pool_free(m, s);
-    pool_free(g.dmax, s); pool_free(g.colmax, s);
     g = DeviceGrid();
 }
 
@@ -221,15 +215,6 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
             CK_LAUNCH();
         }
         pool_free(flags, ctx->stream); pool_free(excl, ctx->stream); pool_free(tmp, ctx->stream);
-    }
-    // exact per-brick density bound for the early rejection of tentative collisions
-    {
-        if (!g.dmax) CK(pool_alloc(&g.dmax, n * 4, ctx->stream));
-        GridView v;
-        memset(&v, 0, sizeof v);
-        v.nb = g.nb; v.rec = g.rec; v.atlas_lin = g.atlas_lin;
-        k_brick_dmax<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(v, g.dmax);
-        CK_LAUNCH();
     }
     g.valid = true;
     return VRB_OK;
@@ -346,7 +331,6 @@ GridView make_view(const DeviceGrid& g) {
     v.psxy = (g.nb.x + 2) * (g.nb.y + 2);
     v.cslot = g.cslot;
     v.datlas = g.datlas;
-    v.dmax = g.dmax;
     return v;
 }
 
@@ -427,7 +411,7 @@ int vrb_create(int device, vrb_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     DeviceGuard guard(device);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->counters, 7 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ctx->job_counter, sizeof(unsigned int)) != cudaSuccess) {
         delete ctx;
         return VRB_ERR_CUDA;
@@ -442,9 +426,8 @@ int vrb_create(int device, vrb_ctx** out) {
     }
     if (const char* e = getenv("VRB200_LPT")) ctx->lpt = atoi(e) != 0;
     if (const char* e = getenv("VRB200_CULL")) ctx->cull = atoi(e) != 0;
-    if (const char* e = getenv("VRB200_EARLY")) ctx->early = atoi(e) != 0;
     if (const char* e = getenv("VRB200_PASS")) ctx->pass_samples = std::max(1, atoi(e));
-    cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
+    cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream);
     *out = ctx;
     return VRB_OK;
 }
@@ -616,12 +599,6 @@ int vrb_grid_info(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out) {
 __global__ void k_sample_density(const GridView g, const float* __restrict__ pts, size_t n, int mode, float* __restrict__ out) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         const float3 p = f3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
-        if (mode == 3) {        // the density bound of the brick that contains p (k_brick_dmax); +inf outside the grid
-            const int bx = int(floorf(p.x)) >> 3, by = int(floorf(p.y)) >> 3, bz = int(floorf(p.z)) >> 3;
-            const bool in = unsigned(bx) < g.nb.x && unsigned(by) < g.nb.y && unsigned(bz) < g.nb.z;
-            out[i] = in ? g.dmax[(size_t(bz) * g.nb.y + by) * g.nb.x + bx] : INFINITY;
-            continue;
-        }
         out[i] = mode == 0 ? density_trilinear(g, p) : mode == 1 ? density_trilinear_decoded(g, p) : brick_value(g, int(floorf(p.x)), int(floorf(p.y)), int(floorf(p.z)));
     }
 }
@@ -631,7 +608,7 @@ int vrb_debug_sample_density(vrb_ctx* ctx, int slot, int frame, const float* ipo
     if (st) return st;
     auto it = ctx->frames.find(frame);
     if (it == ctx->frames.end() || !it->second.slot[slot].valid) return fail(ctx, VRB_ERR_STATE, "no grid in slot %d frame %d", slot, frame);
-    if (!ipos_xyz || !out || mode < 0 || mode > 3) return fail(ctx, VRB_ERR_INVALID, "bad arguments");
+    if (!ipos_xyz || !out || mode < 0 || mode > 2) return fail(ctx, VRB_ERR_INVALID, "bad arguments");
     if (n == 0) return VRB_OK;
     DeviceGuard guard(ctx->device);
     float *d_p = nullptr, *d_o = nullptr;
@@ -801,18 +778,8 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             else k_majorant_table<false><<<blocks, 256, 0, ctx->stream>>>(a, l, g.maj[l], n);
             CK_LAUNCH();
         }
-        if (!g.colmax) CK(pool_alloc(&g.colmax, n0 * 4, ctx->stream));
-        const int blocks0 = grid_for(n0, 256, ctx->sm_count);
-        if (tf) k_collision_bound<true><<<blocks0, 256, 0, ctx->stream>>>(a, g.dmax, g.colmax, n0);
-        else k_collision_bound<false><<<blocks0, 256, 0, ctx->stream>>>(a, g.dmax, g.colmax, n0);
-        CK_LAUNCH();
         g.maj_key = key;
     }
-    // the bound is a bound only for a non-negative scale and, with a transfer function, a non-decreasing alpha over a
-    // positive window (the condition of the brick mask below)
-    a.colmax = ctx->early && params->vol_density_scale >= 0.f &&
-                       (!tf || (ctx->lut_monotone && params->tf_window_width > 0.f && params->vol_inv_majorant >= 0.f && params->vol_majorant >= 0.f))
-                   ? g.colmax : nullptr;
     a.job_counter = ctx->job_counter;
     // ---- per-launch sample buffer: passes of at most `pass` samples per pixel (16 B per sample and pixel) ----
     const size_t n_px = size_t(ctx->w) * ctx->h;
@@ -976,7 +943,6 @@ int vrb_set_option(vrb_ctx* ctx, const char* name, int value) {
     if (!name) return fail(ctx, VRB_ERR_INVALID, "NULL option name");
     if (!strcmp(name, "lpt")) ctx->lpt = value != 0;
     else if (!strcmp(name, "cull")) ctx->cull = value != 0;
-    else if (!strcmp(name, "early")) ctx->early = value != 0;
     else if (!strcmp(name, "count_culled")) ctx->count_culled = value != 0;
     else if (!strcmp(name, "pass")) { if (value < 1) return fail(ctx, VRB_ERR_INVALID, "pass must be >= 1"); ctx->pass_samples = value; }
     else return fail(ctx, VRB_ERR_INVALID, "unknown option '%s'", name);
@@ -1024,7 +990,7 @@ int vrb_set_counting(vrb_ctx* ctx, int enable) {
     if (!ctx) return VRB_ERR_INVALID;
     DeviceGuard guard(ctx->device);
     ctx->counting = enable != 0;
-    CK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream));
     return VRB_OK;
 }
 
@@ -1035,16 +1001,6 @@ int vrb_get_counters(vrb_ctx* ctx, vrb_counters* out) {
     CK(cudaMemcpyAsync(v, ctx->counters, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     out->n_samples = v[0]; out->n_maj = v[1]; out->n_dens = v[2]; out->n_emis = v[3]; out->n_nee = v[4]; out->n_env = v[5]; out->n_real = v[6];
-    return VRB_OK;
-}
-
-int vrb_get_early_rejections(vrb_ctx* ctx, uint64_t* out) {
-    if (!ctx || !out) return VRB_ERR_INVALID;
-    DeviceGuard guard(ctx->device);
-    unsigned long long v = 0;
-    CK(cudaMemcpyAsync(&v, ctx->counters + 7, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    *out = v;
     return VRB_OK;
 }
 
