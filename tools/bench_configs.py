@@ -3,8 +3,11 @@
   C1  smoke.brick + hdr, 1024x1024, README command (non-TF kernel, environment visible)
   C3  synthetic 1024^3 fBm cloud -> GPU brick build -> 1920x1080, density 100, albedo .8 (atlas ~ 1 GiB: HBM-resident)
   C4  synthetic 512x512x1800 CT-like grid + 256-entry RGBA LUT (TF kernel), 1920x1080
+  C5  animated 256^3 fBm frames, datagen_denoise-style noisy (1..33 spp) / clean pairs at 1024x1024, parameters drawn like
+      scripts/datagen_denoise.py:60-80 with random.seed(42), fp16 (N, 3, H, W) output; per frame: GPU brick build from the
+      dense grid, two renders, two read-backs (--frames, --clean-spp; the named config is 64 frames x 4096 clean spp)
 
-    python tools/bench_configs.py [--configs C1,C3,C4] [--scale 1.0] [--spp 16] [--launches 4]
+    python tools/bench_configs.py [--configs C1,C3,C4,C5] [--scale 1.0] [--spp 16] [--launches 4]
 
 Per config one JSON line: brick-build time and GB/s (algorithmic bytes: 1 B/voxel read + 1 B/allocated voxel written +
 8 B/brick), samples/s of the tracking kernel, event counters per sample and the algorithmic GB/s they imply.
@@ -49,6 +52,96 @@ def fbm_cloud(n, seed=42, octaves=5, base=4, threshold=0.30):
     d = (acc[0, 0] * fall - threshold).clamp_(min=0)
     d /= d.max()
     return (d * 255).round().to(torch.uint8).contiguous()
+
+
+def fbm_frames(n, frames, seed=42, octaves=5, base=4, threshold=0.30):
+    """The C5 animation: one fBm field taller in y than the grid; frame t is the window shifted by 0.05 * t of the grid edge."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ny = n + int(round(0.05 * (frames - 1) * n)) + 1
+    acc = torch.zeros((1, 1, n, ny, n), device="cuda", dtype=torch.float16)
+    amp, norm = 0.5, 0.0
+    for o in range(octaves):
+        f = base * 2 ** o
+        fy = max(2, int(round(f * ny / n)))
+        lattice = torch.rand((1, 1, f + 1, fy + 1, f + 1), device="cuda", generator=g, dtype=torch.float32).half()
+        acc += amp * F.interpolate(lattice, size=(n, ny, n), mode="trilinear", align_corners=True)
+        norm += amp
+        amp *= 0.5
+    acc /= norm
+    ax = torch.linspace(-1, 1, n, device="cuda", dtype=torch.float16)
+    r = torch.sqrt(ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2)
+    t = ((1.0 - r) / 0.6).clamp(0, 1)
+    fall = t * t * (3 - 2 * t)
+    out = []
+    for k in range(frames):
+        y0 = int(round(0.05 * k * n))
+        d = (acc[0, 0, :, y0:y0 + n, :] * fall - threshold).clamp_(min=0)
+        d = d / d.max().clamp(min=1e-3)
+        out.append((d * 255).round().to(torch.uint8).contiguous())
+    return out
+
+
+def run_c5(ctx, frames, clean_spp, n=256, W=1024, H=1024):
+    """datagen_denoise.py:60-130 on synthetic frames: parameters drawn in the script's order with random.seed(42)."""
+    import math
+    import random
+    random.seed(42)
+
+    def sphere():
+        z = 1.0 - 2.0 * random.random()
+        r = math.sqrt(max(0.0, 1.0 - z * z))
+        phi = 2.0 * math.pi * random.random()
+        return np.array([r * math.cos(phi), r * math.sin(phi), z], np.float32)
+
+    def draw():
+        p = {}
+        p["samples"] = random.randint(1, 32 + 1); p["max_bounces"] = random.randint(1, 128 + 1)
+        p["seed_input"] = random.randint(0, 2 ** 31); p["seed_target"] = random.randint(0, 2 ** 31)
+        p["env_strength"] = 0.5 + random.random() * 10; p["env_show"] = random.random() < 0.1
+        p["lut_n_bins"] = random.randint(2, 32 + 1); p["lut_window_left"] = random.random() * 0.25; p["lut_window_width"] = random.random()
+        p["vol_albedo"] = (random.random(), random.random(), random.random()); p["vol_phase"] = -0.9 + random.random() * 1.8
+        p["vol_density_scale"] = 0.01 + random.random() * 5
+        p["cam_pos_sample"] = sphere(); p["cam_dir_sample"] = sphere(); p["cam_fov"] = 25 + random.random() * 70
+        return p
+
+    vols = fbm_frames(n, frames)
+    plist = [draw() for _ in range(frames)]
+    ctx.resize(W, H)
+    inputs = np.zeros((frames, 3, H, W), np.float16)
+    targets = np.zeros((frames, 3, H, W), np.float16)
+    g = DenseInfo((n, n, n))
+    samples = 0
+    build_ms = []
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i, q in enumerate(plist):
+        build_ms.append(timed(lambda: ctx.grid_build_from_dense_device(vols[i].data_ptr(), (n, n, n), 0.0, 1.0)))
+        s = scene.RenderSettings(bounces=q["max_bounces"], albedo=q["vol_albedo"], phase=q["vol_phase"], env_strength=q["env_strength"],
+                                 show_environment=q["env_show"], use_transferfunc=False)
+        scene.scale_and_move_to_unit_cube(g.matrix(), g.index_extent(), s)      # Renderer::commit
+        s.density_scale = q["vol_density_scale"]
+        M = np.asarray(s.volume_transform, np.float32) @ g.matrix()
+        bb_min, bb_max = (M @ np.array([0, 0, 0, 1], np.float32))[:3], (M @ np.array([n, n, n, 1], np.float32))[:3]
+        center = bb_min + (bb_max - bb_min) * 0.5
+        radius = float(np.linalg.norm(bb_max - center))
+        pos = center + q["cam_pos_sample"] * radius
+        cam = scene.Camera(pos=pos.astype(np.float32), dir=scene.normalize(center + q["cam_dir_sample"] * radius * 0.1 - pos), fov_degree=q["cam_fov"])
+        for seed, spp, dst in ((q["seed_input"], q["samples"], inputs), (q["seed_target"], clean_spp, targets)):
+            s.seed = seed if seed < 2 ** 31 else seed - 2 ** 32
+            p = scene.make_params(W, H, cam, s, g.matrix(), g.index_extent(), g.min_maj)
+            ctx.clear()
+            ctx.trace(p, 1, spp)
+            rgb = ctx.download_color(3)                                      # fbo_data(): linear RGB fp32
+            dst[i] = np.transpose(np.flip(rgb, axis=0).astype(np.float16), [2, 1, 0])     # datagen_denoise.py:113-114 (square images)
+            samples += W * H * spp
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(json.dumps(dict(config=f"C5 {frames} animated {n}^3 fBm frames, datagen_denoise-style pairs (noisy 1..33 spp, clean {clean_spp} spp; named: 64 frames, 4096 spp)",
+                          resolution=[W, H], frames=frames, clean_spp=clean_spp, wall_s=dt, frames_per_s=frames / dt, samples=samples,
+                          samples_per_s=samples / dt, brick_build_ms_median=float(np.median(build_ms)), output="fp16 (N,3,H,W) noisy + clean",
+                          finite=bool(np.isfinite(inputs.astype(np.float32)).all() and np.isfinite(targets.astype(np.float32)).all()),
+                          mean_clean=float(targets.astype(np.float32).mean()), partition="single GPU (tile partition: volren_b200.multigpu, tests/test_multigpu_gloo.py)")), flush=True)
 
 
 def ct_phantom(w, h, d, seed=42):
@@ -125,6 +218,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="scales the synthetic grid edge (1.0 = the named sizes)")
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--launches", type=int, default=4)
+    ap.add_argument("--frames", type=int, default=8, help="C5: number of animation frames (named config: 64)")
+    ap.add_argument("--clean-spp", type=int, default=256, help="C5: samples of the clean image (named config: 4096)")
     a = ap.parse_args()
     ctx = vr.Context(0)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -136,6 +231,9 @@ def main():
             grid = formats.load_brick(os.path.join(A, "smoke.brick"))
             ctx.grid_upload_brick(grid)
             run("C1 smoke.brick + hdr, README command", ctx, readme_scene(grid, 1024, 1024), 1024, 1024, False, a.spp, a.launches, {})
+            continue
+        if name == "C5":
+            run_c5(ctx, a.frames, a.clean_spp)
             continue
         if name == "C3":
             n = int(1024 * a.scale) // 8 * 8
