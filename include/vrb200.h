@@ -138,6 +138,38 @@ int vrb_grid_build_from_dense(vrb_ctx* ctx, int slot, int frame, const uint8_t* 
 /* same, voxels already resident in DEVICE memory of ctx's device */
 int vrb_grid_build_from_dense_device(vrb_ctx* ctx, int slot, int frame, const void* d_voxels_u8,
                                      const uint32_t dim[3], float vmin, float vmax);
+/* voldata::BrickGrid::BrickGrid(const Grid&) for ANY Grid source (grid_brick.cpp:60-142 with the virtual Grid::lookup,
+ * e.g. NanoVDBGrid, grid_nvdb.cpp:64-67): the caller evaluates grid.lookup(uvec3(x, y, z)) once for every voxel of the
+ * padded lattice x in [-2, 8 n_bricks.x + 2) (likewise y, z; negative coordinates wrap to uint32 as in the reference's
+ * dilated windows, :87) into padded_values[(z + 2) * py * px + (y + 2) * px + (x + 2)]; vrb_brick_lattice returns
+ * n_bricks = roundup8(ceil(extent / 8)) (:62) and the padded dimensions (px, py, pz) = 8 n_bricks + 4.
+ * Bit-exact with the serial reference including its first-seen std::min/std::max order. Host memory, borrowed. */
+int vrb_brick_lattice(const uint32_t extent[3], uint32_t n_bricks[3], uint32_t padded_dim[3]);
+int vrb_grid_build_from_values(vrb_ctx* ctx, int slot, int frame, const float* padded_values, const uint32_t extent[3]);
+
+/* ---- NanoVDB sources (voldata/src/grid_nvdb.cpp; NanoVDB ABI 32 as pinned by the reference's openvdb submodule) ---- */
+/* What voldata::NanoVDBGrid::NanoVDBGrid(path, gridname) (grid_nvdb.cpp:8-28) derives from a grid. */
+typedef struct vrb_nvdb_info {
+    uint64_t grid_offset;            /* byte offset of the serialized grid buffer inside the file image */
+    uint64_t grid_size;              /* GridData::mGridSize */
+    uint64_t active_voxels;          /* NanoVDBGrid::num_voxels (grid_nvdb.cpp:78-80) */
+    uint32_t extent[3];              /* index_extent: ibb.max - ibb.min + 1, 0 for an empty grid (:15) */
+    int32_t ibb_min[3];              /* :14 */
+    float minorant, majorant;        /* root minimum / maximum (:16-17) */
+    float transform[16];             /* :19-27 map matrix + translation, shifted by ibb_min; column-major */
+} vrb_nvdb_info;
+/* nanovdb::io::readGrid(path, gridname) + the constructor's checks on the bytes of a .nvdb file (segment files and raw
+ * grid buffers, codec NONE -- the reference builds NanoVDB without ZIP/BLOSC): locates the first grid of that name,
+ * verifies that it is a valid float fog volume whose node offsets stay inside the buffer, fills *out. Pure host code,
+ * no context needed. On failure returns VRB_ERR_INVALID with the reference's exception text in err[err_len]. */
+int vrb_nvdb_open(const void* file, size_t bytes, const char* gridname, vrb_nvdb_info* out, char* err, size_t err_len);
+/* NanoVDBGrid::lookup (grid_nvdb.cpp:64-67) for n index positions ipos[3 n] (uint32, as Grid::lookup takes them) of a
+ * grid buffer accepted by vrb_nvdb_open (grid = file + grid_offset). Host code: the Grid interface of the host model. */
+int vrb_nvdb_lookup(const void* grid, const int32_t ibb_min[3], const uint32_t* ipos, size_t n, float* out);
+/* voldata::BrickGrid::BrickGrid(const Grid&) for a NanoVDBGrid source (what Volume::current_grid_brick does with a
+ * loaded .nvdb, volume.cpp:89-91 -> grid_brick.cpp:60-142): one H2D copy of the grid buffer, lookup() tabulated on the
+ * padded brick lattice by a device accessor, then the any-Grid brick build. Bit-exact w.r.t. the serial reference. */
+int vrb_grid_build_from_nvdb(vrb_ctx* ctx, int slot, int frame, const void* grid, const vrb_nvdb_info* info);
 /* sizes of an uploaded/built grid; then a second call with buffers allocated copies it back */
 int vrb_grid_info(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* sizes_out);
 int vrb_grid_download(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out);

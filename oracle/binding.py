@@ -106,6 +106,7 @@ class Oracle:
         L.vro_dense_from_float.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_void_p, C.c_float * 2]
         L.vro_brick_dims.argtypes = [C.c_uint32 * 3, C.c_uint32 * 3]
         L.vro_brick_build.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_float, C.c_float, C.POINTER(BrickView)]
+        L.vro_brick_build_values.argtypes = [C.c_void_p, C.c_uint32 * 3, C.POINTER(BrickView)]
         L.vro_brick_lookup.restype = C.c_float
         L.vro_lut_upload.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.vro_env_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -162,6 +163,23 @@ class Oracle:
         ad = tuple(view.atlas_dim)
         atlas = np.ascontiguousarray(atlas[: ad[2]])
         return BrickGridData(nb, ad, view.brick_count, ind, rng, atlas, mips, (vmin, vmax))
+
+    def brick_build_values(self, padded_values, extent_whd, min_maj=(0.0, 0.0)) -> BrickGridData:
+        """BrickGrid(const Grid&) for any Grid: lookup() values on the padded lattice [-2, 8 nb + 2)^3, array [z][y][x]."""
+        val = np.ascontiguousarray(padded_values, np.float32)
+        st, nb = self.brick_dims(tuple(extent_whd))
+        if st:
+            raise RuntimeError("exceeded max brick count of 1024")
+        assert val.shape == (nb[2] * 8 + 4, nb[1] * 8 + 4, nb[0] * 8 + 4), val.shape
+        ind, rng, atlas, mips = alloc_brick_arrays(nb)
+        view = BrickView()
+        view.indirection, view.range, view.atlas = _ptr(ind), _ptr(rng), _ptr(atlas)
+        for i in range(3):
+            view.range_mips[i] = _ptr(mips[i])
+        st = self.lib.vro_brick_build_values(_ptr(val), (C.c_uint32 * 3)(*extent_whd), C.byref(view))
+        assert st == 0
+        ad = tuple(view.atlas_dim)
+        return BrickGridData(nb, ad, view.brick_count, ind, rng, np.ascontiguousarray(atlas[: ad[2]]), mips, min_maj)
 
     def lut_upload(self, rgba):
         rgba = np.ascontiguousarray(rgba, np.float32).reshape(-1, 4)
@@ -272,6 +290,18 @@ class VoldataRef:
         L.ref_brick_copy.argtypes = [C.c_void_p] * 7
         L.ref_brick_decode_all.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_brick_free.argtypes = [C.c_void_p]
+        # NanoVDB adapter of the reference (grid_nvdb.cpp) + generic Grid* access
+        L.ref_nvdb_build.restype = C.c_void_p
+        L.ref_nvdb_build.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_float, C.c_double, C.c_double * 3]
+        L.ref_nvdb_write.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p]
+        L.ref_nvdb_load.restype = C.c_void_p
+        L.ref_nvdb_load.argtypes = [C.c_char_p, C.c_char_p]
+        L.ref_nvdb_ibb_min.argtypes = [C.c_void_p, C.c_int32 * 3]
+        L.ref_grid_info.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_float * 2, C.c_float * 16]
+        L.ref_grid_lookup_padded.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_void_p]
+        L.ref_brick_from_grid.restype = C.c_void_p
+        L.ref_brick_from_grid.argtypes = [C.c_void_p]
+        L.ref_grid_free.argtypes = [C.c_void_p]
 
     def to_half(self, f):
         return int(self.lib.ref_to_half(float(f)))
@@ -290,6 +320,37 @@ class VoldataRef:
         self.lib.ref_dense_voxels(g, _ptr(out))
         self.lib.ref_dense_free(g)
         return out, (float(mm[0]), float(mm[1]))
+
+    # --- NanoVDB (grid_nvdb.cpp) ---
+    def nvdb_write(self, path, grids):
+        """grids: list of (name, ijk int32 [n,3], values float32 [n], background, voxel_size, origin xyz) -> one .nvdb file,
+        written by the reference's NanoVDB headers (tools::createNanoGrid + io::writeGrids, uncompressed)."""
+        handles = (C.c_void_p * len(grids))()
+        for i, (name, ijk, values, background, voxel_size, origin) in enumerate(grids):
+            ijk = np.ascontiguousarray(ijk, np.int32).reshape(-1, 3)
+            values = np.ascontiguousarray(values, np.float32)
+            handles[i] = self.lib.ref_nvdb_build(_ptr(ijk), _ptr(values), len(values), name.encode(), background, voxel_size, (C.c_double * 3)(*origin))
+        assert self.lib.ref_nvdb_write(handles, len(grids), path.encode()) == 0
+
+    def nvdb_load(self, path, gridname="density"):
+        """voldata::NanoVDBGrid(path, gridname) -> dict with extent, ibb_min, min_maj, transform (rows = glm columns),
+        the lookup() values on the padded brick lattice and the reference's BrickGrid built from it; None if it throws."""
+        g = self.lib.ref_nvdb_load(path.encode(), gridname.encode())
+        if not g:
+            return None
+        ext, mm, tr, ibb = (C.c_uint32 * 3)(), (C.c_float * 2)(), (C.c_float * 16)(), (C.c_int32 * 3)()
+        self.lib.ref_grid_info(g, ext, mm, tr)
+        self.lib.ref_nvdb_ibb_min(g, ibb)
+        nb = tuple(((int(np.ceil(np.float32(np.ceil(np.float32(e) / np.float32(8))) / np.float32(8)))) * 1) << 3 for e in ext)
+        padded = np.empty((nb[2] * 8 + 4, nb[1] * 8 + 4, nb[0] * 8 + 4), np.float32)
+        self.lib.ref_grid_lookup_padded(g, (C.c_uint32 * 3)(*nb), _ptr(padded))
+        b = self.lib.ref_brick_from_grid(g)
+        brick = self._brick_to_data(b) if b else None
+        if b:
+            self.lib.ref_brick_free(b)
+        self.lib.ref_grid_free(g)
+        return dict(extent=tuple(ext), ibb_min=tuple(ibb), min_maj=(float(mm[0]), float(mm[1])),
+                    transform=np.array(list(tr), np.float32).reshape(4, 4), n_bricks=nb, padded=padded, brick=brick)
 
     def _brick_to_data(self, b) -> BrickGridData:
         nb = (C.c_uint32 * 3)()

@@ -20,6 +20,10 @@
 
 #include "grid_dense.h"
 #include "grid_brick.h"
+#include "grid_nvdb.h"          // the reference's NanoVDB adapter (voldata/src/grid_nvdb.cpp), header-only NanoVDB 32.7
+#include <nanovdb/io/IO.h>
+#include <nanovdb/tools/GridBuilder.h>
+#include <nanovdb/tools/CreateNanoGrid.h>
 
 #include <cereal/types/utility.hpp>
 #include <cereal/types/atomic.hpp>
@@ -126,5 +130,52 @@ void ref_brick_decode_all(void* g, float* out) {
         out[i++] = b->lookup(glm::uvec3(x, y, z));
 }
 void ref_brick_free(void* g) { delete (BrickGrid*)g; }
+
+// ---- NanoVDB (voldata/src/grid_nvdb.cpp; fixtures are written with the reference's own NanoVDB headers) ----
+// Sparse float fog volume from (coord, value) pairs; returns a heap GridHandle.
+void* ref_nvdb_build(const int32_t* ijk, const float* values, size_t n, const char* name, float background, double voxel_size, const double origin[3]) {
+    nanovdb::tools::build::Grid<float> builder(background, name, nanovdb::GridClass::FogVolume);
+    builder.setTransform(voxel_size, nanovdb::Vec3d(origin[0], origin[1], origin[2]));
+    auto acc = builder.getAccessor();
+    for (size_t i = 0; i < n; ++i) acc.setValue(nanovdb::Coord(ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]), values[i]);
+    auto* h = new nanovdb::GridHandle<nanovdb::HostBuffer>(nanovdb::tools::createNanoGrid(builder));
+    return h;
+}
+// writes the handles as consecutive file segments (io::writeGrids, uncompressed)
+int ref_nvdb_write(void* const* handles, int n, const char* path) {
+    std::vector<nanovdb::GridHandle<nanovdb::HostBuffer>> v;
+    for (int i = 0; i < n; ++i) v.push_back(std::move(*(nanovdb::GridHandle<nanovdb::HostBuffer>*)handles[i]));
+    try { nanovdb::io::writeGrids<nanovdb::HostBuffer, std::vector>(path, v); } catch (...) { return -1; }
+    for (int i = 0; i < n; ++i) delete (nanovdb::GridHandle<nanovdb::HostBuffer>*)handles[i];
+    return 0;
+}
+// voldata::NanoVDBGrid(path, gridname) (grid_nvdb.cpp:8-28); returned as Grid*
+void* ref_nvdb_load(const char* path, const char* gridname) {
+    try { return static_cast<Grid*>(new NanoVDBGrid(path, gridname)); } catch (...) { return nullptr; }
+}
+void ref_nvdb_ibb_min(void* g, int32_t out[3]) {
+    auto* n = static_cast<NanoVDBGrid*>((Grid*)g);
+    out[0] = n->ibb_min.x; out[1] = n->ibb_min.y; out[2] = n->ibb_min.z;
+}
+// ---- generic Grid* ----
+void ref_grid_info(void* g, uint32_t extent[3], float min_maj[2], float transform[16]) {
+    auto* gr = (Grid*)g;
+    const glm::uvec3 e = gr->index_extent();
+    extent[0] = e.x; extent[1] = e.y; extent[2] = e.z;
+    const auto mm = gr->minorant_majorant();
+    min_maj[0] = mm.first; min_maj[1] = mm.second;
+    memcpy(transform, &gr->transform[0][0], 64);
+}
+// Grid::lookup on the padded lattice [-2, 8 nb + 2)^3 exactly as BrickGrid(const Grid&) addresses it (grid_brick.cpp:87)
+void ref_grid_lookup_padded(void* g, const uint32_t nb[3], float* out) {
+    auto* gr = (Grid*)g;
+    size_t i = 0;
+    for (int z = -2; z < int(nb[2] * 8) + 2; ++z) for (int y = -2; y < int(nb[1] * 8) + 2; ++y) for (int x = -2; x < int(nb[0] * 8) + 2; ++x)
+        out[i++] = gr->lookup(glm::uvec3(glm::ivec3(x, y, z)));
+}
+void* ref_brick_from_grid(void* g) {
+    try { return new BrickGrid(*(Grid*)g); } catch (std::runtime_error&) { return nullptr; }
+}
+void ref_grid_free(void* g) { delete (Grid*)g; }
 
 }

@@ -220,7 +220,35 @@ static inline void decode_ptr(uint32_t d, uint32_t p[3]) { /* grid_brick.cpp:39-
     p[0] = (d >> 22) & 1023u; p[1] = (d >> 12) & 1023u; p[2] = (d >> 2) & 1023u;
 }
 
+/* Grid::lookup as BrickGrid(const Grid&) sees it: a virtual call with a uvec3 (negative window coordinates wrapped) */
+typedef float (*vro_lookup_fn)(const void* src, uint32_t x, uint32_t y, uint32_t z);
+typedef struct { const uint8_t* vox; const uint32_t* dim; float vmin, vmax; } vro_dense_src;
+static float lookup_dense(const void* p, uint32_t x, uint32_t y, uint32_t z) {
+    const vro_dense_src* s = (const vro_dense_src*)p;
+    return vro_dense_lookup(s->vox, s->dim, s->vmin, s->vmax, x, y, z);
+}
+/* any other Grid (e.g. NanoVDBGrid::lookup, grid_nvdb.cpp:64-67): its values tabulated on the padded lattice
+ * [-2, 8 nb + 2)^3, the set of voxels the constructor addresses (x fastest, origin (-2, -2, -2)) */
+typedef struct { const float* val; uint32_t px, py; } vro_values_src;
+static float lookup_values(const void* p, uint32_t x, uint32_t y, uint32_t z) {
+    const vro_values_src* s = (const vro_values_src*)p;
+    return s->val[((size_t)((int32_t)z + 2) * s->py + (size_t)((int32_t)y + 2)) * s->px + (size_t)((int32_t)x + 2)];
+}
+static int brick_build_any(vro_lookup_fn lookup, const void* grid, const uint32_t dim[3], vrb_brick_view* out);
+
 int vro_brick_build(const uint8_t* vox, const uint32_t dim[3], float vmin, float vmax, vrb_brick_view* out) {
+    const vro_dense_src s = { vox, dim, vmin, vmax };
+    return brick_build_any(lookup_dense, &s, dim, out);
+}
+int vro_brick_build_values(const float* padded_values, const uint32_t extent[3], vrb_brick_view* out) {
+    uint32_t nb[3];
+    const int st = vro_brick_dims(extent, nb);
+    if (st) return st;
+    const vro_values_src s = { padded_values, nb[0] * 8 + 4, nb[1] * 8 + 4 };
+    return brick_build_any(lookup_values, &s, extent, out);
+}
+
+static int brick_build_any(vro_lookup_fn lookup, const void* grid, const uint32_t dim[3], vrb_brick_view* out) {
     uint32_t nb[3];
     const int st = vro_brick_dims(dim, nb);
     if (st) return st;
@@ -234,7 +262,7 @@ int vro_brick_build(const uint8_t* vox, const uint32_t dim[3], float vmin, float
         float lmin = FLT_MAX, lmax = -FLT_MAX;
         for (int z = -2; z < 10; ++z) for (int y = -2; y < 10; ++y) for (int x = -2; x < 10; ++x) {
             /* negative coordinates wrap to huge unsigned values -> DenseGrid::lookup returns 0 */
-            const float v = vro_dense_lookup(vox, dim, vmin, vmax, (uint32_t)((int)(bx * 8) + x), (uint32_t)((int)(by * 8) + y), (uint32_t)((int)(bz * 8) + z));
+            const float v = lookup(grid, (uint32_t)((int)(bx * 8) + x), (uint32_t)((int)(by * 8) + y), (uint32_t)((int)(bz * 8) + z));
             lmin = v < lmin ? v : lmin;
             lmax = lmax < v ? v : lmax;
         }
@@ -245,7 +273,7 @@ int vro_brick_build(const uint8_t* vox, const uint32_t dim[3], float vmin, float
         out->indirection[bi] = (px << 22) | (py << 12) | (pz << 2);
         const float lo = vro_from_half((uint16_t)(out->range[bi] & 0xffff)), hi = vro_from_half((uint16_t)(out->range[bi] >> 16));
         for (uint32_t z = 0; z < 8; ++z) for (uint32_t y = 0; y < 8; ++y) for (uint32_t x = 0; x < 8; ++x) {
-            const float v = vro_dense_lookup(vox, dim, vmin, vmax, bx * 8 + x, by * 8 + y, bz * 8 + z);
+            const float v = lookup(grid, bx * 8 + x, by * 8 + y, bz * 8 + z);
             const float vn = gl_clamp((v - lo) / (hi - lo), 0.f, 1.f); /* glm::clamp = min(max(x,lo),hi) */
             /* uint8_t(std::round(255 * NaN)) is UB in the reference (fp16 range collapse, 0/0); x86 yields 0 */
             const float r = roundf(255 * vn);

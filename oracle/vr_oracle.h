@@ -55,6 +55,8 @@ float vro_dense_lookup(const uint8_t* vox, const uint32_t dim[3], float vmin, fl
 
 int vro_brick_dims(const uint32_t dim[3], uint32_t n_bricks[3]);
 int vro_brick_build(const uint8_t* vox, const uint32_t dim[3], float vmin, float vmax, vrb_brick_view* out);
+/* the same constructor for any other Grid: lookup() values tabulated on the padded lattice [-2, 8 nb + 2)^3 */
+int vro_brick_build_values(const float* padded_values, const uint32_t extent[3], vrb_brick_view* out);
 float vro_brick_lookup(const vro_grid* g, uint32_t x, uint32_t y, uint32_t z);
 
 int vro_lut_upload(const float* rgba, uint32_t n, float* out);

@@ -1,0 +1,269 @@
+"""NanoVDB ingestion: voldata::NanoVDBGrid (grid_nvdb.cpp) + BrickGrid(const Grid&) for non-dense
+sources. The fixture tests/golden/nvdb_golden.npz holds a two-grid .nvdb file written by the reference's own NanoVDB
+headers and what the UNMODIFIED reference adapter and brick constructor make of it (make_nvdb_golden.py).
+
+CPU: the oracle restatements (oracle/nvdb_np.py, vro_brick_build_values) and the product's host-side reader/accessor
+(vrb_nvdb_open / vrb_nvdb_lookup, no device needed) against the fixture. GPU: the device accessor + any-Grid brick build
+through the C ABI, bit for bit."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+NAMES = ("density", "temperature")
+
+
+@pytest.fixture(scope="module")
+def nvdb_golden():
+    return np.load(os.path.join(GOLDEN, "nvdb_golden.npz"))
+
+
+def _volpy():
+    import sys
+    pkg = os.path.join(os.path.dirname(GOLDEN), os.pardir, "volren_b200")
+    pkg = os.path.abspath(pkg)
+    if not os.path.exists(os.path.join(pkg, "volren")):
+        pytest.fail("the C++ host is not built (python -m volren_b200.build --host)")
+    sys.path.insert(0, pkg)
+    try:
+        import volpy as m
+    finally:
+        sys.path.remove(pkg)
+    return m
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _golden_brick_equals(g, name, got):
+    assert tuple(g[name + ".n_bricks"]) == got.n_bricks and tuple(g[name + ".atlas_dim"]) == got.atlas_dim
+    assert int(g[name + ".brick_count"][0]) == got.brick_count
+    assert np.array_equal(g[name + ".range"], got.range), "range"
+    assert np.array_equal(g[name + ".indirection"], got.indirection), "indirection"
+    assert np.array_equal(g[name + ".atlas"], got.atlas), "atlas"
+    for i in range(3):
+        assert np.array_equal(g[name + f".mip{i}"], got.mips[i]), f"mip{i}"
+
+
+# ---- CPU: oracle pins ----------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_nvdb_restatement_matches_reference(nvdb_golden, name):
+    from oracle.nvdb_np import Grid
+    g = Grid(nvdb_golden["nvdb_file"].tobytes(), name)
+    d = g.derived()
+    assert d["extent"] == tuple(nvdb_golden[name + ".extent"]) and d["ibb_min"] == tuple(nvdb_golden[name + ".ibb_min"])
+    assert np.array_equal(_bits(d["min_maj"]), _bits(nvdb_golden[name + ".min_maj"]))
+    assert np.array_equal(_bits(d["transform"]), _bits(nvdb_golden[name + ".transform"]))
+    assert np.array_equal(_bits(g.padded_lattice(tuple(nvdb_golden[name + ".n_bricks"]))), _bits(nvdb_golden[name + ".padded"]))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_any_grid_brick_build_matches_reference(oracle, nvdb_golden, name):
+    """vro_brick_build_values == the reference's BrickGrid(NanoVDBGrid), incl. the sign of a -0 minimum (first-seen std::min)."""
+    got = oracle.brick_build_values(nvdb_golden[name + ".padded"], tuple(int(v) for v in nvdb_golden[name + ".extent"]))
+    _golden_brick_equals(nvdb_golden, name, got)
+
+
+def test_fixture_regenerates_from_the_reference(voldata_ref, nvdb_golden, tmp_path):
+    """Where the reference is present: the committed file bytes still load to the committed values through the real thing."""
+    p = tmp_path / "fixture.nvdb"
+    p.write_bytes(nvdb_golden["nvdb_file"].tobytes())
+    for name in NAMES:
+        g = voldata_ref.nvdb_load(str(p), name)
+        assert g is not None and g["extent"] == tuple(nvdb_golden[name + ".extent"])
+        assert np.array_equal(_bits(g["padded"]), _bits(nvdb_golden[name + ".padded"]))
+        assert np.array_equal(g["brick"].atlas, nvdb_golden[name + ".atlas"])
+    assert voldata_ref.nvdb_load(str(p), "nope") is None
+
+
+# ---- CPU: the product's host-side reader and accessor ------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reader_matches_reference(nvdb_golden, name):
+    import volren_b200 as vr
+    n = vr.NanoVDBGridData(nvdb_golden["nvdb_file"], name)
+    assert n.extent == tuple(nvdb_golden[name + ".extent"]) and n.ibb_min == tuple(nvdb_golden[name + ".ibb_min"])
+    assert np.array_equal(_bits(n.min_maj), _bits(nvdb_golden[name + ".min_maj"]))
+    assert np.array_equal(_bits(n.transform), _bits(nvdb_golden[name + ".transform"]))
+    assert np.array_equal(_bits(n.padded_lattice()), _bits(nvdb_golden[name + ".padded"]))
+    assert n.num_voxels == {"density": 43018, "temperature": 5050}[name]           # active voxels written by make_nvdb_golden.py
+    # far outside every root tile -> background
+    assert n.lookup([[1 << 20, 5, 5], [5, 1 << 22, 5]]).tolist() == [0.0, 0.0]
+
+
+def test_reader_raw_buffer_files_tiles_and_background(nvdb_golden):
+    """Raw grid-buffer files (GridHandle::read by name), constant tiles at every level and a non-zero background:
+    the product accessor against the painting oracle on patched copies of the fixture."""
+    import volren_b200 as vr
+    from oracle.nvdb_np import Grid, find_grid
+    data = nvdb_golden["nvdb_file"].tobytes()
+    off, size = find_grid(data, "density")
+    raw = bytearray(data[off:off + size])
+    a = vr.NanoVDBGridData(bytes(raw), "density")                      # a raw buffer is found by GridData::mGridName
+    assert a.info.grid_offset == 0 and a.extent == tuple(nvdb_golden["density.extent"])
+    with pytest.raises(vr.VrbError, match="No raw grid named"):
+        vr.NanoVDBGridData(bytes(raw), "temperature")
+    # patch: background 0.25; the first child of the first lower node becomes a constant tile 7.5; the table entry next to
+    # the only child of the first upper node (child mask off) gets the tile value 3.25
+    tree = 672
+    leaf0, lower0, upper0, root = struct.unpack_from("<4q", raw, tree)
+    struct.pack_into("<f", raw, tree + root + 28, 0.25)
+    for node, mask_off, table_off, words, value, clear in ((tree + lower0, 32 + 512, 1088, 64, 7.5, True), (tree + upper0, 32 + 4096, 8256, 512, 3.25, False)):
+        mask = np.frombuffer(bytes(raw[node + mask_off:node + mask_off + words * 8]), np.uint64)
+        on = [w * 64 + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1]
+        idx = on[0] if clear else on[0] ^ 1
+        assert clear or idx not in on
+        if clear:
+            w = struct.unpack_from("<Q", raw, node + mask_off + (idx >> 6) * 8)[0] & ~(1 << (idx & 63))
+            struct.pack_into("<Q", raw, node + mask_off + (idx >> 6) * 8, w)
+        struct.pack_into("<q", raw, node + table_off + idx * 8, 0)
+        struct.pack_into("<f", raw, node + table_off + idx * 8, value)
+    # re-wrap as a one-grid segment file so that both readers take it
+    name = b"density\0"
+    meta = bytearray(176)
+    struct.pack_into("<4Q", meta, 0, len(raw), len(raw), 0, 0)
+    struct.pack_into("<I", meta, 136, len(name))
+    seg = struct.pack("<QIHH", 0x304244566f6e614e, 32 << 21 | 7 << 10, 1, 0) + bytes(meta) + name + bytes(raw)
+    n = vr.NanoVDBGridData(seg, "density")
+    want = Grid(seg, "density").padded_lattice(vr._capi.brick_lattice(n.extent)[0])
+    got = n.padded_lattice()
+    assert np.array_equal(_bits(got), _bits(want))
+    vals = set(np.unique(got).tolist())
+    assert 7.5 in vals                                                # the lower-node tile lies inside the lattice
+    assert n.lookup([[1 << 20, 5, 5]]).tolist() == [0.25]             # outside every root tile -> the root's background
+
+
+def test_reader_rejects_what_the_reference_rejects(nvdb_golden):
+    import volren_b200 as vr
+    from oracle.nvdb_np import find_grid
+    data = bytearray(nvdb_golden["nvdb_file"].tobytes())
+    off, size = find_grid(bytes(data), "density")
+    with pytest.raises(vr.VrbError, match="Grid name 'nope' not found in file"):
+        vr.NanoVDBGridData(bytes(data), "nope")
+    with pytest.raises(vr.VrbError, match="unknown type"):
+        vr.NanoVDBGridData(b"\0" * 4096, "density")
+    with pytest.raises(vr.VrbError, match="Failed to read Tree"):
+        vr.NanoVDBGridData(bytes(data[:off + size // 2]), "density")                  # truncated
+    for field, value in ((632, 1), (636, 2)):                                           # level set; double grid
+        bad = bytearray(data)
+        struct.pack_into("<I", bad, off + field, value)
+        with pytest.raises(vr.VrbError, match="Empty or invalid NanoVDB grid!"):
+            vr.NanoVDBGridData(bytes(bad), "density")
+    bad = bytearray(data)
+    struct.pack_into("<H", bad, 14, 1)                                                 # codec ZIP: the reference is built without it
+    with pytest.raises(vr.VrbError, match="ZIP compression codec was disabled"):
+        vr.NanoVDBGridData(bytes(bad), "density")
+    bad = bytearray(data)
+    struct.pack_into("<I", bad, 8, 31 << 21)                                           # older ABI
+    with pytest.raises(vr.VrbError, match="Incompatible file format"):
+        vr.NanoVDBGridData(bytes(bad), "density")
+    # a child link that leaves the buffer is caught by the open-time walk, not by a crash in the accessor
+    bad = bytearray(data)
+    tree = off + 672
+    root = struct.unpack_from("<4q", bad, tree)[3]
+    struct.pack_into("<q", bad, tree + root + 64 + 8, 1 << 40)
+    with pytest.raises(vr.VrbError, match="node offsets leave the buffer"):
+        vr.NanoVDBGridData(bytes(bad), "density")
+
+
+def test_host_volume_loads_nvdb(nvdb_golden, tmp_path):
+    """The C++ host (voldata::Volume::load_grid -> NanoVDBGrid, volume.cpp:198-200) through volpy: members, lookup, errors."""
+    volpy = _volpy()
+    p = tmp_path / "fixture.nvdb"
+    p.write_bytes(nvdb_golden["nvdb_file"].tobytes())
+    for name in NAMES:
+        g = volpy.Volume.load_grid(str(p), name)
+        ext = tuple(int(v) for v in nvdb_golden[name + ".extent"])
+        assert repr(g.index_extent()) == "uvec3(%d, %d, %d)" % ext
+        assert np.array_equal(_bits(g.minorant_majorant()), _bits(nvdb_golden[name + ".min_maj"]))
+        assert np.array_equal(_bits(np.array(g.transform)), _bits(nvdb_golden[name + ".transform"]))
+        pad = nvdb_golden[name + ".padded"]
+        rng = np.random.default_rng(5)
+        for _ in range(300):
+            x, y, z = (int(rng.integers(-2, pad.shape[2 - i] - 2)) for i in range(3))
+            assert np.float32(g.lookup(volpy.uvec3(x & 0xffffffff, y & 0xffffffff, z & 0xffffffff))) == pad[z + 2, y + 2, x + 2]
+    with pytest.raises(RuntimeError, match="not found in file"):
+        volpy.Volume.load_grid(str(p), "flame")
+    # a folder of .nvdb files: every requested name is looked up in every file, absent names are skipped (volume.cpp:286-290)
+    seq = tmp_path / "seq"
+    seq.mkdir()
+    (seq / "a.nvdb").write_bytes(nvdb_golden["nvdb_file"].tobytes())
+    vol = volpy.Volume.load_folder(str(seq), ["density", "flame", "temperature"])
+    assert vol.n_grid_frames() == 1
+    assert np.float32(vol.minorant_majorant("temperature")[1]) == nvdb_golden["temperature.min_maj"][1]
+    assert np.float32(vol.minorant_majorant("density")[1]) == nvdb_golden["density.min_maj"][1]
+
+
+# ---- GPU: device accessor + any-Grid brick build ------------------------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_build_from_nvdb_matches_reference(ctx, nvdb_golden, name):
+    import volren_b200 as vr
+    n = vr.NanoVDBGridData(nvdb_golden["nvdb_file"], name)
+    ctx.grid_clear()
+    ctx.grid_build_from_nvdb(n)
+    _golden_brick_equals(nvdb_golden, name, ctx.grid_download())
+    # the same bricks from the host-tabulated lattice (the path of any other Grid source)
+    ctx.grid_build_from_values(nvdb_golden[name + ".padded"], n.extent, frame=1)
+    _golden_brick_equals(nvdb_golden, name, ctx.grid_download(frame=1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extent", [(1, 1, 1), (9, 8, 8), (30, 17, 41), (64, 64, 64)])
+def test_gpu_build_from_values_matches_oracle(ctx, oracle, extent):
+    """Arbitrary float lattices: negative values, +-0 ties, constant bricks, huge and denormal ranges, values outside the
+    extent (the constructor reads the whole brick lattice), NaN-free."""
+    import volren_b200 as vr
+    rng = np.random.default_rng(sum(extent))
+    nb, pd = vr._capi.brick_lattice(extent)
+    val = rng.standard_normal((pd[2], pd[1], pd[0])).astype(np.float32)
+    val[rng.random(val.shape) < 0.5] = 0.0
+    val[rng.random(val.shape) < 0.05] = -0.0
+    val[:, :, pd[0] // 2:] *= 1e-6
+    val[: pd[2] // 3] = np.float32(0.75)                        # constant region -> empty bricks
+    val[-5:, -5:, -5:] = np.float32(7e4)                        # above the fp16 range -> inf majorant
+    val[2:6, 2:6, 2:6] = np.float32(1e-41)                      # denormal
+    ctx.grid_clear()
+    ctx.grid_build_from_values(val, extent)
+    got, want = ctx.grid_download(), oracle.brick_build_values(val, extent)
+    assert got.n_bricks == want.n_bricks and got.atlas_dim == want.atlas_dim and got.brick_count == want.brick_count
+    assert np.array_equal(got.range, want.range) and np.array_equal(got.indirection, want.indirection)
+    assert np.array_equal(got.atlas, want.atlas)
+    for i in range(3):
+        assert np.array_equal(got.mips[i], want.mips[i])
+
+
+@pytest.mark.gpu
+def test_gpu_host_renders_a_nvdb_volume(nvdb_golden, ctx, env_rgb, tmp_path):
+    """volpy: Volume('x.nvdb') -> commit (BrickGrid(NanoVDBGrid) on the device) -> render == the C-ABI path on the same grid."""
+    import volren_b200 as vr
+    from test_gpu_host import _params_of
+    volpy = _volpy()
+    p = tmp_path / "fixture.nvdb"
+    p.write_bytes(nvdb_golden["nvdb_file"].tobytes())
+    W = H = 48
+    volpy.create_context(W, H)
+    r = volpy.Renderer()
+    r.init()
+    r.volume = volpy.Volume(str(p))
+    r.environment = volpy.Environment(os.path.join(GOLDEN, "assets", "table_mountain_2_puresky_1k.hdr"))
+    r.scale_and_move_to_unit_cube()
+    r.bounces = 8
+    r.commit()
+    r.render(4)
+    data = np.array(r.fbo_data()).reshape(H, W, 3)
+    params = _params_of(r)
+    n = vr.NanoVDBGridData(nvdb_golden["nvdb_file"], "density")
+    ctx.grid_clear()
+    ctx.grid_build_from_nvdb(n)
+    ctx.env_upload(env_rgb)
+    ctx.resize(W, H)
+    ctx.trace(params, 1, 4)
+    assert np.array_equal(data, ctx.download_color()[..., :3])
+    assert data.max() > 0 and np.isfinite(data).all()

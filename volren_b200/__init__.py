@@ -5,6 +5,6 @@ host/ (Renderer API, CLI, `volpy`). This Python package is the thin ctypes face 
 tests and bench.py; it raises when the CUDA library is missing (no CPU fallback).
 """
 from . import _capi, formats, scene  # noqa: F401
-from ._capi import Context, Counters, Params, VrbError, load_library  # noqa: F401
+from ._capi import Context, Counters, NanoVDBGridData, Params, VrbError, load_library  # noqa: F401
 
-__all__ = ["Context", "Params", "Counters", "VrbError", "load_library", "formats", "scene"]
+__all__ = ["Context", "Params", "Counters", "VrbError", "NanoVDBGridData", "load_library", "formats", "scene"]

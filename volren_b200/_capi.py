@@ -19,7 +19,7 @@ ACCUM_MEAN, ACCUM_SUM = 0, 1
 SYMBOLS = [
     "vrb_create", "vrb_destroy", "vrb_last_error", "vrb_status_string", "vrb_abi_version", "vrb_set_stream", "vrb_sync",
     "vrb_resize", "vrb_grid_clear", "vrb_grid_free", "vrb_grid_upload_brick", "vrb_grid_build_from_dense",
-    "vrb_grid_build_from_dense_device", "vrb_grid_info", "vrb_grid_download", "vrb_debug_sample_density", "vrb_dense_from_float",
+    "vrb_grid_build_from_dense_device", "vrb_brick_lattice", "vrb_grid_build_from_values", "vrb_nvdb_open", "vrb_nvdb_lookup", "vrb_grid_build_from_nvdb", "vrb_grid_info", "vrb_grid_download", "vrb_debug_sample_density", "vrb_dense_from_float",
     "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_set_option", "vrb_scale",
     "vrb_clear", "vrb_set_counting", "vrb_get_counters", "vrb_tonemap", "vrb_download_color", "vrb_download_color_ldr",
     "vrb_download_framebuffer", "vrb_upload_color", "vrb_color_device_ptr", "vrb_bind_color", "vrb_reduce", "vrb_copy_rows",
@@ -64,6 +64,13 @@ class BrickView(C.Structure):
     ]
 
 
+class NvdbInfo(C.Structure):
+    """vrb_nvdb_info: what voldata::NanoVDBGrid(path, gridname) derives from a grid (grid_nvdb.cpp:8-28)."""
+    _fields_ = [("grid_offset", C.c_uint64), ("grid_size", C.c_uint64), ("active_voxels", C.c_uint64),
+                ("extent", C.c_uint32 * 3), ("ibb_min", C.c_int32 * 3), ("minorant", C.c_float), ("majorant", C.c_float),
+                ("transform", C.c_float * 16)]
+
+
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_samples", "n_maj", "n_dens", "n_emis", "n_nee", "n_env", "n_real")]
 
@@ -104,6 +111,11 @@ def load_library(path: str = LIB_PATH):
     L.vrb_grid_upload_brick.argtypes = [vp, ci, ci, C.POINTER(BrickView)]
     L.vrb_grid_build_from_dense.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3, cf, cf]
     L.vrb_grid_build_from_dense_device.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3, cf, cf]
+    L.vrb_brick_lattice.argtypes = [C.c_uint32 * 3, C.c_uint32 * 3, C.c_uint32 * 3]
+    L.vrb_grid_build_from_values.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3]
+    L.vrb_nvdb_open.argtypes = [vp, C.c_size_t, C.c_char_p, C.POINTER(NvdbInfo), C.c_char_p, C.c_size_t]
+    L.vrb_nvdb_lookup.argtypes = [vp, C.c_int32 * 3, vp, C.c_size_t, vp]
+    L.vrb_grid_build_from_nvdb.argtypes = [vp, ci, ci, vp, C.POINTER(NvdbInfo)]
     L.vrb_grid_info.argtypes = [vp, ci, ci, C.POINTER(BrickView)]
     L.vrb_grid_download.argtypes = [vp, ci, ci, C.POINTER(BrickView)]
     L.vrb_debug_sample_density.argtypes = [vp, ci, ci, vp, C.c_size_t, ci, vp]
@@ -131,6 +143,56 @@ def load_library(path: str = LIB_PATH):
     L.vrb_copy_rows.argtypes = [vp, vp, ci, ci]
     _lib = L
     return L
+
+
+def brick_lattice(extent_whd):
+    """(n_bricks, padded_dim) of a grid with the given index extent: roundup8(ceil(extent / 8)) (grid_brick.cpp:62), 8 nb + 4."""
+    nb, pd = (C.c_uint32 * 3)(), (C.c_uint32 * 3)()
+    st = load_library().vrb_brick_lattice((C.c_uint32 * 3)(*extent_whd), nb, pd)
+    if st:
+        raise VrbError(st, "exceeded max brick count of 1024")
+    return tuple(nb), tuple(pd)
+
+
+class NanoVDBGridData:
+    """voldata::NanoVDBGrid (voldata/src/grid_nvdb.h:13-39) over the bytes of a .nvdb file: the grid named `gridname`
+    located and validated by vrb_nvdb_open; lookup() is the host accessor of the C ABI. Raises like the reference throws."""
+
+    def __init__(self, file_bytes, gridname="density"):
+        raw = np.frombuffer(file_bytes, np.uint8) if not isinstance(file_bytes, np.ndarray) else file_bytes.view(np.uint8).reshape(-1)
+        self._file = np.ascontiguousarray(raw)
+        self.info = NvdbInfo()
+        err = C.create_string_buffer(512)
+        st = load_library().vrb_nvdb_open(_ptr(self._file), self._file.size, gridname.encode(), C.byref(self.info), err, len(err))
+        if st:
+            raise VrbError(st, err.value.decode(errors="replace"))
+        i = self.info
+        self.grid = self._file[i.grid_offset:i.grid_offset + i.grid_size]
+        self.extent, self.ibb_min = tuple(i.extent), tuple(i.ibb_min)
+        self.min_maj = (float(i.minorant), float(i.majorant))
+        self.num_voxels, self.size_bytes = int(i.active_voxels), int(i.grid_size)
+        self.transform = np.array(list(i.transform), np.float32).reshape(4, 4)     # rows = glm columns
+
+    def index_extent(self):
+        return self.extent
+
+    def matrix(self):
+        return self.transform.T.copy()
+
+    def lookup(self, ipos_xyz):
+        """NanoVDBGrid::lookup (grid_nvdb.cpp:64-67) for an [n, 3] array of uint32 index positions (wrapped negatives allowed)."""
+        ipos = np.ascontiguousarray(np.asarray(ipos_xyz).astype(np.int64) & 0xffffffff, np.uint32).reshape(-1, 3)
+        out = np.empty(len(ipos), np.float32)
+        st = load_library().vrb_nvdb_lookup(_ptr(self.grid), (C.c_int32 * 3)(*self.ibb_min), _ptr(ipos), len(ipos), _ptr(out))
+        if st:
+            raise VrbError(st, "vrb_nvdb_lookup")
+        return out
+
+    def padded_lattice(self):
+        """lookup() on [-2, 8 nb + 2)^3, array [z][y][x]: the input of Context.grid_build_from_values."""
+        nb, pd = brick_lattice(self.extent)
+        z, y, x = np.meshgrid(np.arange(-2, pd[2] - 2), np.arange(-2, pd[1] - 2), np.arange(-2, pd[0] - 2), indexing="ij")
+        return self.lookup(np.stack([x.ravel(), y.ravel(), z.ravel()], -1)).reshape(pd[2], pd[1], pd[0])
 
 
 class Context:
@@ -199,6 +261,18 @@ class Context:
 
     def grid_build_from_dense_device(self, dev_ptr, dim_whd, vmin, vmax, slot=SLOT_DENSITY, frame=0):
         self._ck(self.lib.vrb_grid_build_from_dense_device(self.handle, slot, frame, dev_ptr, (C.c_uint32 * 3)(*dim_whd), vmin, vmax))
+
+    def grid_build_from_values(self, padded_values, extent_whd, slot=SLOT_DENSITY, frame=0):
+        """BrickGrid(const Grid&) for any source: lookup() values on the padded lattice [-2, 8 nb + 2)^3, array [z][y][x]."""
+        val = np.ascontiguousarray(padded_values, np.float32)
+        nb, pd = brick_lattice(extent_whd)
+        if val.shape != (pd[2], pd[1], pd[0]):
+            raise ValueError(f"padded lattice must have shape {(pd[2], pd[1], pd[0])}, got {val.shape}")
+        self._ck(self.lib.vrb_grid_build_from_values(self.handle, slot, frame, _ptr(val), (C.c_uint32 * 3)(*extent_whd)))
+
+    def grid_build_from_nvdb(self, nvdb: "NanoVDBGridData", slot=SLOT_DENSITY, frame=0):
+        """BrickGrid(NanoVDBGrid) on the device: grid buffer upload + device accessor + any-Grid brick build."""
+        self._ck(self.lib.vrb_grid_build_from_nvdb(self.handle, slot, frame, _ptr(nvdb.grid), C.byref(nvdb.info)))
 
     def grid_info(self, slot=SLOT_DENSITY, frame=0):
         v = BrickView()

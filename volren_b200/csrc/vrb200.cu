@@ -4,6 +4,7 @@
 
 #include "vr_common.cuh"
 #include "vr_brick.cuh"
+#include "vr_nvdb.cuh"
 #include "vr_env.cuh"
 #include "vr_trace.cuh"
 #include "vr_trace2.cuh"
@@ -240,7 +241,10 @@ int compute_n_bricks(const uint32_t dim[3], uint3& nb) {
     return VRB_OK;
 }
 
-int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d_vox, const uint32_t dim[3], float vmin, float vmax) {
+// d_values != nullptr: any-Grid source, lookup() values on the padded lattice [-2, 8 nb + 2)^3 (vr_brick.cuh); else the
+// u8 voxels of a DenseGrid
+int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d_vox, const uint32_t dim[3], float vmin, float vmax,
+                             const float* d_values = nullptr) {
     uint3 nb;
     if (compute_n_bricks(dim, nb) != VRB_OK)
         return fail(ctx, VRB_ERR_TOO_MANY_BRICKS, "exceeded max brick count of 1024");
@@ -259,7 +263,10 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
     CK(pool_alloc(&block_sums, size_t(n_blocks) * 4, ctx->stream));
     CK(pool_alloc(&d_total, 8, ctx->stream));
     // A: ranges
-    if ((dim[0] & 7u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 7u) == 0) {
+    if (d_values) {
+        k_brick_range_values<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_values, nb, g.range, flags);
+        CK_LAUNCH();
+    } else if ((dim[0] & 7u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 7u) == 0) {
         // separable, coalesced reduction over the 12^3 windows (x, then y, then z)
         uint16_t *m1 = nullptr, *m2 = nullptr;
         const size_t n1 = size_t(dim[2]) * dim[1] * nb.x, n2 = size_t(dim[2]) * nb.y * nb.x;
@@ -297,7 +304,10 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
     CK(pool_alloc(&g.atlas, atlas_bytes, ctx->stream));
     if (atlas_bytes) CK(cudaMemsetAsync(g.atlas, 0, atlas_bytes, ctx->stream));
     // C: encode
-    if (total) {
+    if (total && d_values) {
+        k_brick_encode_values<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_values, nb, g.range, brick_id, g.atlas, g.atlas_dim);
+        CK_LAUNCH();
+    } else if (total) {
         k_brick_encode<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_vox, vdim, vmin, vmax, nb, g.range, brick_id, g.atlas, g.atlas_dim,
                                                                                                  ((dim[0] & 7u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 7u) == 0) ? 1 : 0);
         CK_LAUNCH();
@@ -579,6 +589,233 @@ int vrb_grid_build_from_dense(vrb_ctx* ctx, int slot, int frame, const uint8_t* 
     if (e != cudaSuccess) { pool_free(d_vox, ctx->stream); return fail(ctx, VRB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
     st = build_from_device_voxels(ctx, slot, frame, d_vox, dim, vmin, vmax);
     pool_free(d_vox, ctx->stream);
+    return st;
+}
+
+int vrb_brick_lattice(const uint32_t extent[3], uint32_t n_bricks[3], uint32_t padded_dim[3]) {
+    if (!extent || !n_bricks) return VRB_ERR_INVALID;
+    uint3 nb;
+    if (compute_n_bricks(extent, nb) != VRB_OK) return VRB_ERR_TOO_MANY_BRICKS;
+    n_bricks[0] = nb.x; n_bricks[1] = nb.y; n_bricks[2] = nb.z;
+    if (padded_dim) { padded_dim[0] = nb.x * 8 + 4; padded_dim[1] = nb.y * 8 + 4; padded_dim[2] = nb.z * 8 + 4; }
+    return VRB_OK;
+}
+
+int vrb_grid_build_from_values(vrb_ctx* ctx, int slot, int frame, const float* padded_values, const uint32_t extent[3]) {
+    int st = check_slot_frame(ctx, slot, frame);
+    if (st) return st;
+    if (!padded_values || !extent) return fail(ctx, VRB_ERR_INVALID, "bad value lattice");
+    uint3 nb;
+    if (compute_n_bricks(extent, nb) != VRB_OK) return fail(ctx, VRB_ERR_TOO_MANY_BRICKS, "exceeded max brick count of 1024");
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t(nb.x) * 8 + 4) * (size_t(nb.y) * 8 + 4) * (size_t(nb.z) * 8 + 4);
+    float* d_val = nullptr;
+    CK(pool_alloc(&d_val, n * 4, ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(d_val, padded_values, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { pool_free(d_val, ctx->stream); return fail(ctx, VRB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+    st = build_from_device_voxels(ctx, slot, frame, nullptr, extent, 0.f, 0.f, d_val);
+    pool_free(d_val, ctx->stream);
+    return st;
+}
+
+// ---- NanoVDB sources ------------------------------------------------------------------------------
+namespace {
+
+int nvdb_fail(char* err, size_t err_len, const char* fmt, ...) {
+    if (err && err_len) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, err_len, fmt, ap);
+        va_end(ap);
+    }
+    return VRB_ERR_INVALID;
+}
+
+// GridData::isValid (NanoVDB.h:1864-1875) on the first 672 bytes at p
+bool nvdb_grid_header_valid(const uint8_t* p) {
+    using namespace nvdb;
+    const uint64_t magic = rd<uint64_t>(p + G_MAGIC);
+    if (magic == MAGIC_GRID || rd<uint64_t>(p + G_DATA2) == MAGIC_GRID) return true;
+    return magic == MAGIC_NUMB && (rd<uint32_t>(p + G_VERSION) >> 21) == ABI_MAJOR && rd<uint32_t>(p + G_COUNT) > 0u &&
+           rd<uint32_t>(p + G_INDEX) < rd<uint32_t>(p + G_COUNT) && rd<uint32_t>(p + G_CLASS) < GRID_CLASS_END && rd<uint32_t>(p + G_TYPE) < GRID_TYPE_END;
+}
+
+uint64_t nvdb_string_hash(const char* s) {        // io::stringHash (io/IO.h:710-721)
+    uint64_t hash = 0;
+    for (const unsigned char* c = reinterpret_cast<const unsigned char*>(s); *c; ++c) {
+        const uint64_t overflow = hash >> (64 - 8);
+        hash *= 67;
+        hash += *c + overflow;
+    }
+    return hash;
+}
+
+// Every link the accessor follows must stay inside the buffer (the reference trusts the file; a truncated or corrupt
+// file must not crash the host or the device accessor here). O(nodes).
+bool nvdb_links_valid(const uint8_t* g, uint64_t size) {
+    using namespace nvdb;
+    if (size < GRID_SIZE + TREE_SIZE + ROOT_SIZE) return false;
+    const uint8_t* tree = g + TREE;
+    const int64_t root_off = rd<int64_t>(tree + T_NODE_OFFSET + 24);
+    if (root_off < int64_t(TREE_SIZE) || (root_off & 31) || uint64_t(root_off) + TREE + ROOT_SIZE > size) return false;
+    const uint64_t root = TREE + uint64_t(root_off);
+    const uint64_t n_tiles = rd<uint32_t>(g + root + R_TABLE_SIZE);
+    if (root + ROOT_SIZE + n_tiles * TILE_SIZE > size) return false;
+    auto inside = [&](uint64_t node, int64_t link, uint64_t node_size, uint64_t* child) {
+        const int64_t at = int64_t(node) + link;
+        if (link == 0 || at < 0 || (at & 31) || uint64_t(at) + node_size > size) return false;
+        *child = uint64_t(at);
+        return true;
+    };
+    for (uint64_t t = 0; t < n_tiles; ++t) {
+        const int64_t up = rd<int64_t>(g + root + ROOT_SIZE + t * TILE_SIZE + RT_CHILD);
+        if (up == 0) continue;
+        uint64_t upper, lower, leaf;
+        if (!inside(root, up, UPPER_SIZE, &upper)) return false;
+        for (uint32_t w = 0; w < 512; ++w) {
+            uint64_t bits = rd<uint64_t>(g + upper + UPPER_CHILD_MASK + w * 8);
+            for (; bits; bits &= bits - 1) {
+                const uint32_t nu = w * 64 + uint32_t(__builtin_ctzll(bits));
+                if (!inside(upper, rd<int64_t>(g + upper + UPPER_TABLE + size_t(nu) * 8), LOWER_SIZE, &lower)) return false;
+                for (uint32_t v = 0; v < 64; ++v) {
+                    uint64_t lbits = rd<uint64_t>(g + lower + LOWER_CHILD_MASK + v * 8);
+                    for (; lbits; lbits &= lbits - 1) {
+                        const uint32_t nl = v * 64 + uint32_t(__builtin_ctzll(lbits));
+                        if (!inside(lower, rd<int64_t>(g + lower + LOWER_TABLE + size_t(nl) * 8), LEAF_SIZE, &leaf)) return false;
+                    }
+                }
+            }
+        }
+    }
+    return true;
+}
+
+}  // namespace
+
+int vrb_nvdb_open(const void* file, size_t bytes, const char* gridname, vrb_nvdb_info* out, char* err, size_t err_len) {
+    using namespace nvdb;
+    if (err && err_len) err[0] = 0;
+    if (!file || !gridname || !out) return nvdb_fail(err, err_len, "bad argument");
+    const uint8_t* f = static_cast<const uint8_t*>(file);
+    uint64_t at = 0, found = UINT64_MAX;
+    if (bytes >= GRID_SIZE && nvdb_grid_header_valid(f)) {
+        // a raw grid buffer, possibly several grids back to back (GridHandle::read(is, gridName), GridHandle.h:405-426)
+        uint32_t n = 0;
+        const uint32_t count = rd<uint32_t>(f + G_COUNT);
+        while (true) {
+            if (at + GRID_SIZE > bytes) break;
+            if (strncmp(reinterpret_cast<const char*>(f + at + G_NAME), gridname, G_NAME_LEN) == 0) { found = at; break; }
+            if (n++ >= count) break;
+            at += rd<uint64_t>(f + at + G_BYTES);
+        }
+        if (found == UINT64_MAX) return nvdb_fail(err, err_len, "No raw grid named \"%s\"", gridname);
+    } else {
+        // segments: FileHeader (16) + gridCount x (FileMetaData (176) + name) + the grids (io/IO.h:386-431, :568-594)
+        const uint64_t key = nvdb_string_hash(gridname);
+        while (found == UINT64_MAX && at + 16 <= bytes) {
+            const uint64_t magic = rd<uint64_t>(f + at);
+            if (magic != MAGIC_NUMB && magic != MAGIC_FILE)
+                return nvdb_fail(err, err_len, "Expected a NanoVDB file, but read a file of unknown type!");
+            if ((rd<uint32_t>(f + at + 8) >> 21) != ABI_MAJOR)
+                return nvdb_fail(err, err_len, "An unrecoverable error in nanovdb::Segment::read:\n\tIncompatible file format: NanoVDB major version %u, expected %u",
+                                 rd<uint32_t>(f + at + 8) >> 21, ABI_MAJOR);
+            const uint32_t grid_count = rd<uint16_t>(f + at + 12), codec = rd<uint16_t>(f + at + 14);
+            at += 16;
+            uint64_t seek = 0, hit = UINT64_MAX;
+            for (uint32_t i = 0; i < grid_count; ++i) {
+                if (at + 176 > bytes) return nvdb_fail(err, err_len, "Failed reading FileGridMetaData");
+                const uint64_t file_size = rd<uint64_t>(f + at + 8), name_key = rd<uint64_t>(f + at + 16);
+                const uint32_t name_size = rd<uint32_t>(f + at + 136);
+                if (at + 176 + name_size > bytes) return nvdb_fail(err, err_len, "Failed reading FileGridMetaData");
+                const std::string name(reinterpret_cast<const char*>(f + at + 176), strnlen(reinterpret_cast<const char*>(f + at + 176), name_size));
+                if (hit == UINT64_MAX) {
+                    if ((name_key == 0u || name_key == key) && name == gridname) hit = seek;
+                    else seek += file_size;
+                }
+                at += 176 + name_size;
+            }
+            if (hit != UINT64_MAX) {
+                if (codec == 1) return nvdb_fail(err, err_len, "ZIP compression codec was disabled during build");
+                if (codec == 2) return nvdb_fail(err, err_len, "BLOSC compression codec was disabled during build");
+                found = at + hit;
+            } else
+                at += seek;
+        }
+        if (found == UINT64_MAX) return nvdb_fail(err, err_len, "Grid name '%s' not found in file", gridname);
+    }
+    if (found + GRID_SIZE + TREE_SIZE > bytes) return nvdb_fail(err, err_len, "Failed to read Tree from file");
+    const uint8_t* g = f + found;
+    const uint64_t grid_size = rd<uint64_t>(g + G_BYTES);
+    if (grid_size > bytes - found) return nvdb_fail(err, err_len, "Failed to read Tree from file");
+    // handle.grid<float>() is null for other value types; !isValid(); !isFogVolume() (grid_nvdb.cpp:10-12)
+    if (rd<uint32_t>(g + G_TYPE) != GRID_TYPE_FLOAT || !nvdb_grid_header_valid(g) || rd<uint32_t>(g + G_CLASS) != GRID_CLASS_FOG)
+        return nvdb_fail(err, err_len, "Empty or invalid NanoVDB grid!");
+    if (!nvdb_links_valid(g, grid_size)) return nvdb_fail(err, err_len, "Empty or invalid NanoVDB grid! (node offsets leave the buffer)");
+    memset(out, 0, sizeof *out);
+    out->grid_offset = found;
+    out->grid_size = grid_size;
+    out->active_voxels = rd<uint64_t>(g + TREE + T_VOXEL_COUNT);
+    const uint8_t* root = g + TREE + rd<int64_t>(g + TREE + T_NODE_OFFSET + 24);
+    const bool empty = rd<uint32_t>(root + R_TABLE_SIZE) == 0u;                  // GridData::isEmpty (NanoVDB.h:1992)
+    float fmin[3] = { 0.f, 0.f, 0.f };
+    for (int i = 0; i < 3; ++i) {
+        const int32_t lo = rd<int32_t>(root + R_BBOX + 4 * i), hi = rd<int32_t>(root + R_BBOX + 12 + 4 * i);
+        // both go through glm::vec3 (float) before the integer members take them (:14-15)
+        fmin[i] = empty ? 0.f : float(lo);
+        out->ibb_min[i] = int32_t(fmin[i]);
+        out->extent[i] = empty ? 0u : uint32_t(float(hi - lo + 1));
+    }
+    out->minorant = rd<float>(root + R_MINIMUM);
+    out->majorant = rd<float>(root + R_MAXIMUM);
+    float* T = out->transform;                                                     // T[4 c + r]: glm column c, row r
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) T[4 * i + j] = rd<float>(g + G_MAP_MATF + 4 * (i * 3 + j));
+        T[12 + i] = rd<float>(g + G_MAP_VECF + 4 * i);
+    }
+    T[15] = 1.f;
+    // transform[3] += transform * vec4(ibb_min, 0), glm's mat4 * vec4: (m0 x + m1 y) + (m2 z + m3 w)  (type_mat4x4.inl:561-572)
+    float add[4];
+    for (int r = 0; r < 4; ++r) {
+        const volatile float a = T[r] * fmin[0], b = T[4 + r] * fmin[1], c = T[8 + r] * fmin[2], d = T[12 + r] * 0.f;
+        const volatile float ab = a + b, cd = c + d;
+        add[r] = ab + cd;
+    }
+    for (int r = 0; r < 4; ++r) { const volatile float s = T[12 + r] + add[r]; T[12 + r] = s; }
+    return VRB_OK;
+}
+
+int vrb_nvdb_lookup(const void* grid, const int32_t ibb_min[3], const uint32_t* ipos, size_t n, float* out) {
+    if (!grid || !ibb_min || (n && (!ipos || !out))) return VRB_ERR_INVALID;
+    const uint8_t* g = static_cast<const uint8_t*>(grid);
+    for (size_t i = 0; i < n; ++i)
+        out[i] = nvdb::get_value(g, int32_t(ipos[3 * i] + uint32_t(ibb_min[0])), int32_t(ipos[3 * i + 1] + uint32_t(ibb_min[1])), int32_t(ipos[3 * i + 2] + uint32_t(ibb_min[2])));
+    return VRB_OK;
+}
+
+int vrb_grid_build_from_nvdb(vrb_ctx* ctx, int slot, int frame, const void* grid, const vrb_nvdb_info* info) {
+    int st = check_slot_frame(ctx, slot, frame);
+    if (st) return st;
+    if (!grid || !info || info->grid_size < nvdb::GRID_SIZE + nvdb::TREE_SIZE + nvdb::ROOT_SIZE) return fail(ctx, VRB_ERR_INVALID, "bad NanoVDB grid");
+    uint3 nb;
+    if (compute_n_bricks(info->extent, nb) != VRB_OK) return fail(ctx, VRB_ERR_TOO_MANY_BRICKS, "exceeded max brick count of 1024");
+    DeviceGuard guard(ctx->device);
+    const uint3 pd = make_uint3(nb.x * 8 + 4, nb.y * 8 + 4, nb.z * 8 + 4);
+    const size_t n = size_t(pd.x) * pd.y * pd.z;
+    uint8_t* d_grid = nullptr;
+    float* d_val = nullptr;
+    CK(pool_alloc(&d_grid, info->grid_size, ctx->stream));
+    cudaError_t e = pool_alloc(&d_val, n * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_grid, grid, info->grid_size, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        pool_free(d_grid, ctx->stream); pool_free(d_val, ctx->stream);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? VRB_ERR_OOM : VRB_ERR_CUDA, "NanoVDB upload failed: %s", cudaGetErrorString(e));
+    }
+    nvdb::k_nvdb_tabulate<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_grid, make_int3(info->ibb_min[0], info->ibb_min[1], info->ibb_min[2]), pd, d_val);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) st = build_from_device_voxels(ctx, slot, frame, nullptr, info->extent, 0.f, 0.f, d_val);
+    else st = fail(ctx, VRB_ERR_CUDA, "k_nvdb_tabulate launch failed: %s", cudaGetErrorString(e));
+    pool_free(d_grid, ctx->stream);
+    pool_free(d_val, ctx->stream);
     return st;
 }
 

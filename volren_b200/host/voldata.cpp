@@ -111,15 +111,28 @@ BrickGrid::BrickGrid() : Grid(), n_bricks(0), min_maj({ 0, 0 }), brick_counter(0
 static const int SCRATCH_FRAME = 0x7ffffff0;   // device-side staging slot of BrickGrid(const Grid&)
 
 BrickGrid::BrickGrid(const Grid& grid) : Grid(grid), n_bricks(0), min_maj(grid.minorant_majorant()), brick_counter(0) {
-    const DenseGrid* dense = dynamic_cast<const DenseGrid*>(&grid);
-    std::unique_ptr<DenseGrid> tmp;
-    if (!dense) {   // any other source: quantise to a DenseGrid first (the device builder consumes u8 voxels)
-        tmp.reset(new DenseGrid(grid));
-        dense = tmp.get();
-    }
     vrb_ctx* ctx = volren::Context::device();
-    const uint32_t dim[3] = { dense->n_voxels.x, dense->n_voxels.y, dense->n_voxels.z };
-    int st = vrb_grid_build_from_dense(ctx, VRB_SLOT_DENSITY, SCRATCH_FRAME, dense->voxel_data.data(), dim, dense->min_value, dense->max_value);
+    int st;
+    if (const DenseGrid* dense = dynamic_cast<const DenseGrid*>(&grid)) {
+        const uint32_t dim[3] = { dense->n_voxels.x, dense->n_voxels.y, dense->n_voxels.z };
+        st = vrb_grid_build_from_dense(ctx, VRB_SLOT_DENSITY, SCRATCH_FRAME, dense->voxel_data.data(), dim, dense->min_value, dense->max_value);
+    } else if (const NanoVDBGrid* nvdb = dynamic_cast<const NanoVDBGrid*>(&grid)) {
+        st = vrb_grid_build_from_nvdb(ctx, VRB_SLOT_DENSITY, SCRATCH_FRAME, nvdb->grid_data(), &nvdb->info);
+    } else {
+        // any other source: grid.lookup() once per voxel of the padded lattice the constructor addresses (grid_brick.cpp:87)
+        const uvec3 e = grid.index_extent();
+        const uint32_t extent[3] = { e.x, e.y, e.z };
+        uint32_t nb[3], pd[3];
+        st = vrb_brick_lattice(extent, nb, pd);
+        if (st == VRB_OK) {
+            std::vector<float> values(size_t(pd[0]) * pd[1] * pd[2]);
+            size_t i = 0;
+            for (int z = -2; z < int(pd[2]) - 2; ++z)
+                for (int y = -2; y < int(pd[1]) - 2; ++y)
+                    for (int x = -2; x < int(pd[0]) - 2; ++x) values[i++] = grid.lookup(uvec3(uint32_t(x), uint32_t(y), uint32_t(z)));
+            st = vrb_grid_build_from_values(ctx, VRB_SLOT_DENSITY, SCRATCH_FRAME, values.data(), extent);
+        }
+    }
     if (st == VRB_ERR_TOO_MANY_BRICKS) throw std::runtime_error(std::string("exceeded max brick count of ") + std::to_string(MAX_BRICKS));
     volren::check(ctx, st, "BrickGrid(const Grid&)");
     vrb_brick_view v;
@@ -170,6 +183,34 @@ std::string BrickGrid::to_string(const std::string& indent) const {
     out << indent << "atlas dim: " << vmath::to_string(atlas.size()) << std::endl;
     return out.str();
 }
+
+// ------------------------------------------------------------------------------------------------
+// NanoVDBGrid (grid_nvdb.cpp:8-28, :64-88): the file image is the handle; location, validation and the derived
+// members come from vrb_nvdb_open, lookup() from the host accessor of the C ABI
+
+NanoVDBGrid::NanoVDBGrid(const std::string& path, const std::string& gridname) : Grid() {
+    std::ifstream in(path, std::ios::binary | std::ios::ate);
+    if (!in.is_open()) throw std::ios_base::failure("Unable to open file named \"" + path + "\" for input");
+    file.resize(size_t(in.tellg()));
+    in.seekg(0);
+    in.read(reinterpret_cast<char*>(file.data()), std::streamsize(file.size()));
+    char err[512];
+    if (vrb_nvdb_open(file.data(), file.size(), gridname.c_str(), &info, err, sizeof err) != VRB_OK) throw std::runtime_error(err);
+    ibb_min = ivec3(info.ibb_min[0], info.ibb_min[1], info.ibb_min[2]);
+    extent = uvec3(info.extent[0], info.extent[1], info.extent[2]);
+    minorant = info.minorant;
+    majorant = info.majorant;
+    memcpy(&transform[0][0], info.transform, sizeof info.transform);
+}
+float NanoVDBGrid::lookup(const uvec3& ipos) const {
+    float v = 0.f;
+    vrb_nvdb_lookup(grid_data(), info.ibb_min, &ipos.x, 1, &v);
+    return v;
+}
+std::pair<float, float> NanoVDBGrid::minorant_majorant() const { return { minorant, majorant }; }
+uvec3 NanoVDBGrid::index_extent() const { return extent; }
+size_t NanoVDBGrid::num_voxels() const { return size_t(info.active_voxels); }
+size_t NanoVDBGrid::size_bytes() const { return size_t(info.grid_size); }
 
 // ------------------------------------------------------------------------------------------------
 // cereal PortableBinary (little-endian) archives, field order of serialization.cpp:36-43
@@ -399,14 +440,14 @@ static Volume::GridPtr load_dat(const fs::path& path) {
 }
 
 Volume::GridPtr Volume::load_grid(const std::string& filename, const std::string& gridname) {
-    (void)gridname;   // only multi-grid containers (.vdb/.nvdb) select by name
     const fs::path path = filename;
     const std::string extension = lower_ext(path);
     if (extension == ".dat") return load_dat(path);
     if (extension == ".dense") return load_dense_grid(path.string());
     if (extension == ".brick") return load_brick_grid(path.string());
-    if (extension == ".vdb" || extension == ".nvdb" || extension == ".dcm")
-        throw std::runtime_error("Unable to load file extension: " + extension + " (OpenVDB/NanoVDB/DICOM adapters are not part of the B200 build; convert to .brick/.dense)");
+    if (extension == ".nvdb") return std::make_shared<NanoVDBGrid>(path.string(), gridname);   // volume.cpp:198-200
+    if (extension == ".vdb" || extension == ".dcm")
+        throw std::runtime_error("Unable to load file extension: " + extension + " (OpenVDB/DICOM adapters are not part of the B200 build; convert to .nvdb/.brick/.dense)");
     throw std::runtime_error("Unable to load file extension: " + extension);
 }
 
@@ -436,7 +477,16 @@ Volume::VolumePtr Volume::load_folder(const std::string& path, std::vector<std::
     // ignore the name, so one file fills every requested slot of its frame (a .brick sequence loaded by the CLI with
     // { density, temperature, flame, flames } therefore also acts as its own emission grid). Same observable result,
     // one read per file.
+    // A .nvdb container selects by name: one load per requested name, absent names are skipped (volume.cpp:286-290).
     for (size_t i = 0; i < files.size(); ++i) {
+        if (lower_ext(files[i]) == ".nvdb") {
+            for (const auto& gridname : gridnames) {
+                try {
+                    result->update_grid_frame(i, load_grid(files[i].string(), gridname), gridname);
+                } catch (std::runtime_error&) {}
+            }
+            continue;
+        }
         try {
             const GridPtr grid = load_grid(files[i].string(), gridnames.empty() ? "density" : gridnames[0]);
             for (const auto& gridname : gridnames) result->update_grid_frame(i, grid, gridname);

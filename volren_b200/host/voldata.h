@@ -3,8 +3,11 @@
 // loaders), rebuilt around the B200 back end:
 //   * DenseGrid(w,h,d,const float*)  -> min/max reduction + 8-bit quantisation on the GPU (vrb_dense_from_float),
 //     bit-exact w.r.t. voldata/src/grid_dense.cpp:57-95
-//   * BrickGrid(const Grid&)         -> brick build on the GPU (vrb_grid_build_from_dense), bit-exact w.r.t. the serial
-//     voldata/src/grid_brick.cpp:60-142
+//   * BrickGrid(const Grid&)         -> brick build on the GPU, bit-exact w.r.t. the serial voldata/src/grid_brick.cpp:60-142:
+//     vrb_grid_build_from_dense for a DenseGrid, vrb_grid_build_from_nvdb for a NanoVDBGrid (device accessor), and
+//     vrb_grid_build_from_values (lookup() tabulated on the padded lattice) for any other Grid
+//   * NanoVDBGrid(path, gridname)    -> .nvdb reader + accessor without the NanoVDB headers (vrb_nvdb_open / _lookup),
+//     voldata/src/grid_nvdb.cpp:8-28,64-67
 //   * file formats                   -> cereal PortableBinary layout of voldata/src/serialization.cpp:16-43,66-80
 //     re-implemented without cereal
 // Interface names and semantics follow voldata/src/{grid,grid_dense,grid_brick,volume,buf3d}.h.
@@ -16,6 +19,7 @@
 #include <utility>
 #include <vector>
 
+#include "../../include/vrb200.h"
 #include "vmath.h"
 
 namespace voldata {
@@ -88,6 +92,23 @@ public:
     Buf3D<uint32_t> range;                       // 2 x fp16 (minorant, majorant)
     Buf3D<uint8_t> atlas;                        // 8^3 unorm8 voxels per allocated brick
     std::vector<Buf3D<uint32_t>> range_mipmaps;  // 3 levels of 2x2x2 min/max
+};
+
+// voldata/src/grid_nvdb.h (file constructor; converting other grids TO NanoVDB is not part of this build)
+class NanoVDBGrid : public Grid {
+public:
+    NanoVDBGrid(const std::string& path, const std::string& gridname = "density");
+    float lookup(const uvec3& ipos) const override;
+    std::pair<float, float> minorant_majorant() const override;
+    uvec3 index_extent() const override;
+    size_t num_voxels() const override;
+    size_t size_bytes() const override;
+    const uint8_t* grid_data() const { return file.data() + info.grid_offset; }   // the serialized grid buffer
+    std::vector<uint8_t> file;                   // file image (handle)
+    vrb_nvdb_info info;
+    ivec3 ibb_min;
+    uvec3 extent;
+    float minorant, majorant;
 };
 
 // voldata/src/serialization.h
