@@ -23,13 +23,19 @@ void copy3(float* dst, const vec3& v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z
 void copy9(float* dst, const mat3& m) { memcpy(dst, &m[0].x, 36); }
 void copy16(float* dst, const mat4& m) { memcpy(dst, &m[0].x, 64); }
 
-// upload one grid of one frame to one device: BrickGrids verbatim, DenseGrids through the device brick builder
+// upload one grid of one frame to one device: BrickGrids verbatim, DenseGrids and NanoVDBGrids through the device brick builder
 void upload_grid(vrb_ctx* ctx, int slot, int frame, const voldata::Volume::GridPtr& grid) {
     if (auto dense = std::dynamic_pointer_cast<voldata::DenseGrid>(grid)) {
         const uint32_t dim[3] = { dense->n_voxels.x, dense->n_voxels.y, dense->n_voxels.z };
         const int st = vrb_grid_build_from_dense(ctx, slot, frame, dense->voxel_data.data(), dim, dense->min_value, dense->max_value);
         if (st == VRB_ERR_TOO_MANY_BRICKS) throw std::runtime_error("exceeded max brick count of 1024");
         check(ctx, st, "vrb_grid_build_from_dense");
+        return;
+    }
+    if (auto nvdb = std::dynamic_pointer_cast<voldata::NanoVDBGrid>(grid)) {     // device accessor + brick build, no host round trip
+        const int st = vrb_grid_build_from_nvdb(ctx, slot, frame, nvdb->grid_data(), &nvdb->info);
+        if (st == VRB_ERR_TOO_MANY_BRICKS) throw std::runtime_error("exceeded max brick count of 1024");
+        check(ctx, st, "vrb_grid_build_from_nvdb");
         return;
     }
     const auto brick = voldata::Volume::to_brick_grid(grid);
