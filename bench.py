@@ -149,7 +149,7 @@ def run_reference(args, rank, world):
     t0 = time.perf_counter()
     o.trace(sc, params, 1, 4, color=color, n_threads=cores)
     probe = (time.perf_counter() - t0) / 4
-    spp = max(1, int(3.0 / max(probe, 1e-4)))
+    spp = max(1, int(min(3.0, 90.0 / max(args.steps, 1)) / max(probe, 1e-4)))      # ~3 s per step, the whole run <= ~90 s
     for i in range(args.warmup):
         o.trace(sc, params, 1 + i, 1, color=color, n_threads=cores)
     t0 = time.perf_counter()
@@ -351,10 +351,14 @@ def main():
                 self.pr.render(S * world)
             self.pending = True
 
-    lanes = [Lane(), Lane()]
+    lanes = [Lane() for _ in range(max(2, int(os.environ.get("VRB_E2E_LANES", "2"))))]
+    n_lanes = len(lanes)
+    # the pipeline needs a few steps to fill and one read-back to drain: time at least 40 steps so that the number is the
+    # steady state whatever --steps is (reported as e2e.steps)
+    e2e_steps = max(args.steps, 40)
 
     def e2e_step(k):
-        lane = lanes[k & 1]
+        lane = lanes[k % n_lanes]
         lane.finish()                                   # the image of step k - 2 (normally long done)
         lane.submit()
 
@@ -364,7 +368,7 @@ def main():
         lane.finish()
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(e2e_steps):
         e2e_step(k)
     for lane in lanes:
         lane.finish()
@@ -373,7 +377,7 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = samples_per_step * args.steps / float(t.item())
+    e2e_value = samples_per_step * e2e_steps / float(t.item())
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -403,7 +407,7 @@ def main():
                              "note": "events the production launch executes after its exact screen-space culling; `achieved` above uses the reference algorithm's bytes for the same image"},
                 "note": "latency/issue-bound gather workload on an L2-resident volume: see DESIGN.md for the L2 roofline",
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "lanes": n_lanes},
             "gpu_launches": args.steps * 2,     # per step: k_trace_persistent + k_fold (the tile sort is cub, memsets are not kernels of ours)
             "clocks": clocks,
         }

@@ -61,9 +61,11 @@ def test_same_seed_replay_T2(smoke_ctx, oracle, smoke_grid, env_rgb, env_pyramid
     assert np.array_equal(got[..., 3] > 0, want[..., 3] > 0) or (got[..., 3] != want[..., 3]).mean() < 0.01
 
 
-@pytest.mark.parametrize("use_tf", [False, True])
-def test_statistical_parity_T3_and_counters(smoke_ctx, oracle, smoke_grid, env_rgb, env_pyramid, lut_raw, use_tf):
-    W, H, SPP = 96, 96, 256
+@pytest.mark.parametrize("use_tf,W,H,SPP", [(False, 96, 96, 256), (True, 96, 96, 256), (False, 48, 48, 4096), (True, 48, 48, 4096)],
+                         ids=["notf-256spp", "tf-256spp", "notf-4096spp-converged", "tf-4096spp-converged"])
+def test_statistical_parity_T3_and_counters(smoke_ctx, oracle, smoke_grid, env_rgb, env_pyramid, lut_raw, use_tf, W, H, SPP):
+    """The north star's image criterion, literally at 4096 spp (on a 48^2 frame so that the two CPU oracle runs take
+    seconds) and at 256 spp on a larger frame."""
     lut, _ = oracle.lut_upload(lut_raw)
     smoke_ctx.tf_upload(lut)
     mk = (lambda seed: default_scene(smoke_grid, W, H, bounces=128, use_tf=True, seed=seed)) if use_tf else (lambda seed: readme_scene(smoke_grid, W, H, seed=seed))

@@ -118,7 +118,7 @@ VR_DEV float unorm8_to_float(uint32_t u) {
 VR_DEV float brick_value(const GridView& g, int x, int y, int z) {
     const int bx = x >> 3, by = y >> 3, bz = z >> 3;
     if (unsigned(bx) >= g.nb.x || unsigned(by) >= g.nb.y || unsigned(bz) >= g.nb.z) return 0.f;
-    const uint2 r = __ldg(g.rec + (size_t(bz) * g.nb.y + by) * g.nb.x + bx);
+    const uint2 r = __ldg(g.rec + (uint32_t(bz) * g.nb.y + uint32_t(by)) * g.nb.x + uint32_t(bx));   // n_bricks < 2^30: 32-bit index math
     const float lo = range_lo(r.y), hi = range_hi(r.y);
     float unorm = 0.f;
     if (r.x != 0xffffffffu)
@@ -326,7 +326,8 @@ VR_DEV bool intersect_box(float3 pos, float3 dir, const float* bb_min, const flo
 
 // stepDDA (common.glsl:404-409)
 VR_DEV float step_dda(float3 pos, float3 ri, int mip) {
-    const float dim = float(8 << mip), inv_dim = __uint_as_float(0x3e000000u - (uint32_t(mip) << 23));  // 1/dim, exact power of two
+    // dim = 8 << mip and 1/dim as exact powers of two, straight from the exponent bits
+    const float dim = __uint_as_float(0x41000000u + (uint32_t(mip) << 23)), inv_dim = __uint_as_float(0x3e000000u - (uint32_t(mip) << 23));
     const float ox = ri.x >= 0.f ? dim + 0.5f : -0.5f;
     const float oy = ri.y >= 0.f ? dim + 0.5f : -0.5f;
     const float oz = ri.z >= 0.f ? dim + 0.5f : -0.5f;

@@ -55,7 +55,7 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
     const int bx = int(floorf(ipos.x)) >> (3 + mip), by = int(floorf(ipos.y)) >> (3 + mip), bz = int(floorf(ipos.z)) >> (3 + mip);
     const uint32_t nx = a.density.nb.x >> mip, ny = a.density.nb.y >> mip, nz = a.density.nb.z >> mip;
     if (unsigned(bx) >= nx || unsigned(by) >= ny || unsigned(bz) >= nz) return __ldg(a.maj_oob);
-    return __ldg(a.maj[mip] + (size_t(bz) * ny + by) * nx + bx);
+    return __ldg(a.maj[mip] + (uint32_t(bz) * ny + uint32_t(by)) * nx + uint32_t(bx));   // < 2^30 entries: 32-bit index math
 }
 
 #ifndef VR_TRACE_BLOCK
