@@ -211,7 +211,11 @@ int vrb_set_kernel(vrb_ctx* ctx, int kind);
  * brick with a positive majorant projects are exactly zero and are not traced, default 1), "pass" (samples per pixel and
  * internal pass, default 16), "count_culled" (default 0: the counting build traces every sample, i.e. counts the events of
  * the reference algorithm; 1: it keeps the culling and counts the events the production launch executes).
- * Environment variables VRB200_LPT / VRB200_CULL / VRB200_PASS set the defaults. */
+ * Environment variables VRB200_LPT / VRB200_CULL / VRB200_PASS set the defaults.
+ * "async_upload" (default 0) changes the ownership rule of vrb_grid_upload_brick / vrb_env_upload / vrb_tf_upload: with 1
+ * they only enqueue (cudaMemcpyAsync semantics) -- the host buffers must stay valid and unchanged until the next vrb_sync
+ * or download on this context; pass pinned memory so that the copies really are asynchronous. A pipelined caller can
+ * then enqueue the uploads and the trace of the next frame while the previous one is still running. */
 int vrb_set_option(vrb_ctx* ctx, const char* name, int value);
 /* color *= s (finalise VRB_ACCUM_SUM buffers) */
 int vrb_scale(vrb_ctx* ctx, float s);

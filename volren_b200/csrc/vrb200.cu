@@ -95,6 +95,7 @@ struct vrb_ctx {
     uint64_t cost_key = 0;       // view the costs in tile_cost belong to (0 = none)
     bool lpt = true;             // VRB200_LPT=0 disables
     bool cull = true;            // VRB200_CULL=0 disables the screen-space box culling
+    bool async_upload = false;   // option "async_upload": upload calls return without waiting; the caller keeps the host buffers alive until vrb_sync / a download
     bool count_culled = false;   // option "count_culled": the counting build keeps the culling (events of the production launch, not of the reference algorithm)
     int tile_coords_tx = 0;      // tiles_x the packed coordinates in tile_iota were made for
     bool counting = false;
@@ -563,7 +564,7 @@ int vrb_grid_upload_brick(vrb_ctx* ctx, int slot, int frame, const vrb_brick_vie
     if (atlas_bytes) CK(cudaMemcpyAsync(g.atlas, v->atlas, atlas_bytes, cudaMemcpyHostToDevice, ctx->stream));
     for (int i = 0; i < 3; ++i) CK(cudaMemcpyAsync(g.mips[i], v->range_mips[i], mip_words(g.nb, i) * 4, cudaMemcpyHostToDevice, ctx->stream));
     st = finalize_grid(ctx, g, reuse);
-    CK(cudaStreamSynchronize(ctx->stream));   // host buffers are only borrowed for the duration of the call
+    if (!ctx->async_upload) CK(cudaStreamSynchronize(ctx->stream));   // host buffers are only borrowed for the duration of the call
     return st;
 }
 
@@ -930,7 +931,7 @@ int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h) {
         k_env_mip<<<grid, block, 0, ctx->stream>>>(ctx->impmap + imp_offset(l - 1), d * 2, ctx->impmap + imp_offset(l), d);
         CK_LAUNCH();
     }
-    CK(cudaStreamSynchronize(ctx->stream));   // host buffer is only borrowed for the duration of the call
+    if (!ctx->async_upload) CK(cudaStreamSynchronize(ctx->stream));   // host buffer is only borrowed for the duration of the call
     return VRB_OK;
 }
 
@@ -955,7 +956,7 @@ int vrb_tf_upload(vrb_ctx* ctx, const float* rgba, uint32_t n) {
         CK(cudaMalloc(&ctx->lut, size_t(n) * 16));
     }
     CK(cudaMemcpyAsync(ctx->lut, rgba, size_t(n) * 16, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->async_upload) CK(cudaStreamSynchronize(ctx->stream));
     ctx->tf_size = n;
     ctx->lut_version++;
     // k_tile_mask relies on tf(hi).a bounding tf(d).a for d <= hi: true for the CDF-corrected LUTs of transferfunc.cpp:33-58,
@@ -1181,6 +1182,7 @@ int vrb_set_option(vrb_ctx* ctx, const char* name, int value) {
     if (!strcmp(name, "lpt")) ctx->lpt = value != 0;
     else if (!strcmp(name, "cull")) ctx->cull = value != 0;
     else if (!strcmp(name, "count_culled")) ctx->count_culled = value != 0;
+    else if (!strcmp(name, "async_upload")) ctx->async_upload = value != 0;
     else if (!strcmp(name, "pass")) { if (value < 1) return fail(ctx, VRB_ERR_INVALID, "pass must be >= 1"); ctx->pass_samples = value; }
     else return fail(ctx, VRB_ERR_INVALID, "unknown option '%s'", name);
     return VRB_OK;
