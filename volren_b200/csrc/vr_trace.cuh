@@ -91,11 +91,17 @@ struct TraceArgs {
 template <bool COUNT> struct Cnt;
 template <> struct Cnt<false> {
     VR_DEV void maj() {} VR_DEV void dens() {} VR_DEV void emis() {} VR_DEV void nee() {} VR_DEV void env() {} VR_DEV void real() {} VR_DEV void samp() {}
+    VR_DEV void maj(bool) {} VR_DEV void spec_begin() {} VR_DEV void spec_rollback() {}
 };
 template <> struct Cnt<true> {
     uint32_t n_samp = 0, n_maj = 0, n_dens = 0, n_emis = 0, n_nee = 0, n_env = 0, n_real = 0;
     VR_DEV void maj() { ++n_maj; } VR_DEV void dens() { ++n_dens; } VR_DEV void emis() { ++n_emis; } VR_DEV void nee() { ++n_nee; }
     VR_DEV void env() { ++n_env; } VR_DEV void real() { ++n_real; } VR_DEV void samp() { ++n_samp; }
+    // speculative DDA steps (vr_trace2.cuh) count only once their outstanding collision is confirmed null
+    uint32_t n_spec = 0;
+    VR_DEV void maj(bool speculative) { ++n_maj; if (speculative) ++n_spec; }
+    VR_DEV void spec_begin() { n_spec = 0; }
+    VR_DEV void spec_rollback() { n_maj -= n_spec; n_spec = 0; }
 };
 VR_DEV void flush_counters(const TraceArgs&, const Cnt<false>&) {}
 VR_DEV void flush_counters(const TraceArgs& a, const Cnt<true>& c) {

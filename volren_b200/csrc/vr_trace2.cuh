@@ -91,6 +91,33 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #ifndef VR_MIN_STEP
 #define VR_MIN_STEP 16    // fewer stepping lanes than this: drain the fullest queue even below its threshold
 #endif
+// Speculative null collisions (VR_SPECULATE): 92-94 % of the tentative collisions of the bench scenes are null, and the
+// number of random draws a null collision consumes is fixed (density filter 9 | 0, emission filter 9 on camera segments,
+// 1 for the test, then the new tau). A lane that hits a tentative collision therefore records it (t, seed, majorant,
+// mip), jumps its stream ahead, draws the new tau and KEEPS STEPPING; the recorded collision is evaluated later, when
+// many lanes hold one (the 8-tap / tricubic lookup then runs with most lanes active instead of ~14). A null result
+// confirms the speculation; a real collision rolls the lane back to the recorded point (t, seed) and discards the
+// speculative steps. One collision may be outstanding per lane: a second one, or the end of the ray, parks the lane until
+// the first is resolved. Same paths, same draws, same sums in the same order as the non-speculative schedule.
+// MEASURED SLOWER on B200 (profiles/r01_v9_speculate_sweep.txt: TF 1.01 -> 1.07-1.15 ms, non-TF 8.47 -> 8.84-9.21 ms for
+// every threshold pair tried): a lane meets its next tentative collision ~2.5 steps later and parks anyway, so the
+// resolve batches grow little while ~7 % of the steps are thrown away. Off by default; bit-identical images and
+// counters with it on (the GPU test-suite passes either way).
+#ifndef VR_SPECULATE
+#define VR_SPECULATE 0
+#endif
+#ifndef VR_K_BLOCKED_TF
+#define VR_K_BLOCKED_TF 8     // resolve when this many lanes are parked behind their outstanding collision ...
+#endif
+#ifndef VR_K_BLOCKED
+#define VR_K_BLOCKED 8
+#endif
+#ifndef VR_K_PENDING_TF
+#define VR_K_PENDING_TF 24    // ... or this many lanes hold one
+#endif
+#ifndef VR_K_PENDING
+#define VR_K_PENDING 24
+#endif
 constexpr int MAX_RAY_STEPS = 1 << 20;  // hang guard only: no finite ray takes this many DDA steps
 
 template <bool TF, bool COUNT, class MT>
@@ -111,6 +138,19 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
     float3 pos = f3(0.f), dir = f3(0.f, 0.f, -1.f), thr = f3(1.f), L = f3(0.f), pend = f3(0.f);
     float3 ipos = f3(0.f), idir = f3(1.f), ri = f3(1.f);
     float t = 0.f, tfar = -1.f, tau = 0.f, mip = 3.f, f_p = 0.f, Tr = 1.f, majorant = 0.f;
+    // outstanding (speculated-null) tentative collision of this lane
+    constexpr bool SPEC = VR_SPECULATE != 0;
+    bool pending = false, second = false;     // second: parked AT another tentative collision (else: parked at the ray's end)
+    float t_c = 0.f, maj_c = 0.f, mip_c = 0.f;
+    uint32_t seed_c = 0;
+    // records the tentative collision at the lane's current state and continues as if it were null (common.glsl:451-452 / 497-498)
+    auto speculate = [&]() {
+        t_c = t; seed_c = seed; maj_c = majorant; mip_c = mip; pending = true;
+        if (shadow) rng_skip<TF ? 1 : 10>(seed); else rng_skip<TF ? 10 : 19>(seed);
+        tau = -MT::log(1.f - rng(seed));
+        mip = fmaxf(0.f, mip - 2.f);
+        cnt.spec_begin();
+    };
     // ---- warp state: the current block of 32 samples (one tile, one sample index), prepared in shared memory ----
     __shared__ float4 s_prep[VR_TRACE_BLOCK / 32][32];     // {view dir, seed after the two jitter draws}
     float4* prep = s_prep[threadIdx.x >> 5];
@@ -127,7 +167,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
             if (t < tfar) {
                 const float3 curr = ipos + t * idir;
                 const int m = round_mip(mip);
-                cnt.maj();
+                cnt.maj(SPEC && pending);
                 majorant = table_majorant(a, curr, m);
                 const float dt = step_dda(curr, ri, m);
                 t += dt;
@@ -135,12 +175,17 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 mip = fminf(mip + 0.25f, 3.f);
                 if (!(tau > 0.f)) {
                     t += MT::div(tau, majorant);
-                    if (!(t >= tfar)) stage = SG_COLLIDE;   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
+                    if (!(t >= tfar)) {                     // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
+                        if (SPEC && !pending) speculate();  // stays in STEP
+                        else { stage = SG_COLLIDE; second = true; }
+                    }
                 }
                 if (++steps > MAX_RAY_STEPS) { t = INFINITY; stage = SG_STEP; }
             }
             if (stage == SG_STEP && !(t < tfar)) {   // the ray left the volume
-                if (shadow) {
+                if (SPEC && pending) {                // ... if the outstanding collision turns out null: wait for it
+                    stage = SG_COLLIDE; second = false;
+                } else if (shadow) {
                     if (Tr != 0.f) L = L + pend * Tr;     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
                     stage = SG_SCATTER;
                 } else {
@@ -153,6 +198,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         // ================= scheduler =================
         const unsigned m_step = __ballot_sync(FULL, stage == SG_STEP);
         const unsigned m_col = __ballot_sync(FULL, stage == SG_COLLIDE);
+        const unsigned m_pend = SPEC ? __ballot_sync(FULL, pending) : 0u;
         const unsigned m_nee = __ballot_sync(FULL, stage == SG_NEE);
         const unsigned m_scat = __ballot_sync(FULL, stage == SG_SCATTER);
         const unsigned m_fin = __ballot_sync(FULL, stage == SG_FINISH);
@@ -160,7 +206,9 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         const int n_step = __popc(m_step), n_col = __popc(m_col), n_nee = __popc(m_nee), n_scat = __popc(m_scat), n_fin = __popc(m_fin);
         constexpr int KF = TF ? VR_K_FINISH_TF : VR_K_FINISH;
         constexpr int K = TF ? VR_K_EVENT_TF : VR_K_EVENT, KC = TF ? VR_K_COLLIDE_TF : VR_K_COLLIDE, MIN_STEP = TF ? VR_MIN_STEP_TF : VR_MIN_STEP;
-        bool run_col = n_col >= KC, run_nee = n_nee >= K, run_scat = n_scat >= K, run_fin = n_fin >= KF;
+        constexpr int KB = TF ? VR_K_BLOCKED_TF : VR_K_BLOCKED, KP = TF ? VR_K_PENDING_TF : VR_K_PENDING;
+        bool run_col = SPEC ? (n_col >= KB || __popc(m_pend) >= KP) : n_col >= KC;
+        bool run_nee = n_nee >= K, run_scat = n_scat >= K, run_fin = n_fin >= KF;
         if (!(run_col | run_nee | run_scat | run_fin)) {
             if (n_step >= MIN_STEP) continue;                  // keep stepping
             // too few lanes can step: drain the fullest queue
@@ -171,7 +219,64 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         }
 
         // ================= COLLIDE: tentative collision (common.glsl:436-452 / 483-498) =================
-        if (run_col && stage == SG_COLLIDE) {
+        if (SPEC) {
+            // resolves the outstanding collision of EVERY lane that holds one (parked or still stepping)
+            if (run_col && pending) {
+                cnt.dens();
+                pending = false;
+                uint32_t sd = seed_c;
+                const float3 at = ipos + t_c * idir;
+                float d;
+                float3 tf_rgb = f3(1.f);
+                if (TF) {
+                    const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * (MT::decoded ? density_trilinear_decoded(a.density, at) : density_trilinear(a.density, at)) * a.p.vol_inv_majorant);
+                    d = a.p.vol_majorant * rgba.w;
+                    tf_rgb = f3(rgba.x, rgba.y, rgba.z);
+                } else {
+                    const int3 tap = stochastic_tricubic_filter<MT>(at, sd);
+                    d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
+                }
+                bool real = false;
+                if (!shadow) {
+                    bool fetched;
+                    const float3 em = lookup_emission<MT>(a, at, sd, fetched);
+                    if (fetched) {
+                        cnt.emis();
+                        const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                        L = L + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant;
+                    }
+                    if (rng(sd) * maj_c < d) {               // real collision: the segment ends here (common.glsl:490-496)
+                        thr = thr * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                        if (TF) thr = thr * tf_rgb;
+                        real = true;
+                        stage = SG_NEE;
+                    }
+                } else {
+                    if (rng(sd) * maj_c < d) {               // common.glsl:442-451
+                        real = true;
+                        stage = SG_STEP;
+                        Tr *= fmaxf(0.f, 1.f - MT::div(a.p.vol_majorant, maj_c));
+                        if (Tr < .1f) {
+                            const float prob = 1 - Tr;
+                            if (rng(sd) < prob) { Tr = 0.f; stage = SG_SCATTER; }   // absorbed: `return 0.f`, nothing is added to L
+                            else Tr = MT::div(Tr, 1 - prob);
+                        }
+                        if (stage == SG_STEP) {              // the shadow ray goes on from the collision with the shifted stream
+                            tau = -MT::log(1.f - rng(sd));
+                            mip = fmaxf(0.f, mip_c - 2.f);
+                        }
+                    }
+                }
+                if (real) {                                  // roll back to the collision: the speculative steps never happened
+                    t = t_c;
+                    seed = sd;
+                    cnt.spec_rollback();
+                } else if (stage == SG_COLLIDE) {            // confirmed null and the lane was parked behind it
+                    stage = SG_STEP;                         // at the ray's end: the next STEP pass finishes the ray
+                    if (second) speculate();                 // at another tentative collision: that one is outstanding now
+                }
+            }
+        } else if (run_col && stage == SG_COLLIDE) {
             cnt.dens();
             stage = SG_STEP;
             const float3 at = ipos + t * idir;
