@@ -209,7 +209,7 @@ int vrb_set_kernel(vrb_ctx* ctx, int kind);
 /* scheduling options of the production kernel (none changes the image): "lpt" (heaviest tiles first, default 1),
  * "cull" (hidden environment only: pixels outside the screen rectangle of the volume's box and 8x4 tiles onto which no
  * brick with a positive majorant projects are exactly zero and are not traced, default 1), "pass" (samples per pixel and
- * internal pass, default 16), "count_culled" (default 0: the counting build traces every sample, i.e. counts the events of
+ * internal pass, default 32), "count_culled" (default 0: the counting build traces every sample, i.e. counts the events of
  * the reference algorithm; 1: it keeps the culling and counts the events the production launch executes).
  * Environment variables VRB200_LPT / VRB200_CULL / VRB200_PASS set the defaults.
  * "async_upload" (default 0) changes the ownership rule of vrb_grid_upload_brick / vrb_env_upload / vrb_tf_upload: with 1

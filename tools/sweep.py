@@ -31,7 +31,7 @@ def run(argv):
     for so in sorted(glob.glob(os.path.join(OUT, "*.so"))):
         for tf in (1, 0):
             env = dict(os.environ, VRB200_LIB=so)
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "profile_trace.py"), "--tf", str(tf), "--spp", "16", "--launches", "3"] + argv,
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "profile_trace.py"), "--tf", str(tf), "--spp", "32", "--launches", "3"] + argv,
                                  env=env, capture_output=True, text=True).stdout.strip().splitlines()
             print(f"{os.path.basename(so):40s} tf={tf}  {out[-1] if out else 'FAILED'}", flush=True)
 

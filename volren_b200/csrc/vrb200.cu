@@ -79,7 +79,8 @@ struct vrb_ctx {
     unsigned int* job_counter = nullptr;
     float4* lbuf = nullptr;      // per-launch sample buffer of the persistent kernel: lbuf_samples x (w * h) float4
     int lbuf_samples = 0;
-    int pass_samples = 16;       // samples per pixel and pass (VRB200_PASS); bounds lbuf (also capped at 1 GiB)
+    int pass_samples = 32;       // samples per pixel and pass (VRB200_PASS); bounds lbuf (also capped at 1 GiB = 32 samples at 1080p).
+                                 // B200, configs[1]: 16 -> 33.6, 32 -> 36.9, 64 -> 36.7, 128 -> 36.5 Gsamples/s (fixed costs + tail per pass)
     // heaviest-tiles-first scheduling (vr_trace2.cuh): per-tile cost of the last launch, its view key, the sorted order
     unsigned int* tile_cost = nullptr;
     unsigned int* tile_cost_sorted = nullptr;
