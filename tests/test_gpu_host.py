@@ -181,6 +181,33 @@ def test_cli_offline_render_matches_volpy(volpy, tmp_path):
     assert np.abs(img[..., 2::-1].astype(int) - want.astype(int)).max() <= 1
 
 
+def test_cli_progressive_preview(volpy, tmp_path):
+    """`--preview FILE` stands in for the interactive loop (main.cpp:477-523): progressive trace + draw() written to FILE,
+    input from FILE.cmd (applied -> reset), linear colour saved at sppx (:511-512)."""
+    import cv2
+    W, H = 96, 64
+    (tmp_path / "view.png.cmd").write_text("--cam_fov 40 --exposure 3\n")       # "input" waiting before the first frame
+    cmd = [os.path.join(PKG, "volren"), BRICK, HDR, "-w", str(W), "-h", str(H), "--spp", "8", "--batch", "2", "--bounces", "16", "--albedo", "0.8", "--phase", "0.3",
+           "--density", "100", "--env_strength", "3", "--env_rot", "270", "--gamma", "2.0", "--preview", "view.png", "--preview-interval", "0", "--output", "final.png"]
+    res = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert "8 / 8 spp" in res.stdout and "final.png written." in res.stdout
+    assert not (tmp_path / "view.png.cmd").exists()                              # consumed
+    view = cv2.imread(str(tmp_path / "view.png"), cv2.IMREAD_UNCHANGED)
+    final = cv2.imread(str(tmp_path / "final.png"), cv2.IMREAD_UNCHANGED)
+    assert view is not None and view.shape == (H, W, 4) and final is not None and final.shape == (H, W, 4)
+    r = _readme_renderer(volpy, W, H, bounces=16)                                # fov 40: what the command file set
+    r.tonemap_exposure, r.tonemap_gamma = 3.0, 2.0
+    r.render(8)
+    hdr = np.array(r.fbo_data()).reshape(H, W, 3)
+    r.draw()
+    r.save_with_alpha(str(tmp_path / "want.png"))
+    want = cv2.imread(str(tmp_path / "want.png"), cv2.IMREAD_UNCHANGED)
+    assert np.array_equal(view, want)                                            # the last preview frame == draw() of the finished image
+    lin = np.rint(np.clip(hdr[::-1], 0, 1) * 255).astype(np.uint8)              # save_ldr of the linear colour buffer
+    assert np.abs(final[..., 2::-1].astype(int) - lin.astype(int)).max() <= 1
+
+
 def test_cli_runs_a_datagen_style_script(volpy, tmp_path):
     env = dict(os.environ, VOLREN_TEST_OUT=str(tmp_path))
     res = subprocess.run([os.path.join(PKG, "volren"), os.path.join(ROOT, "tests", "scripts", "datagen_like.py"), "-w", "48", "-h", "48", "--render"],

@@ -1,16 +1,27 @@
 // main.cpp -- the `volren` command line of the B200 host. Same arguments, same order-dependent semantics and the
 // same offline loop as reference src/main.cpp (init_opengl_from_args :311-357, parse_cmd :360-435, handle_path
-// :93-102, offline loop :524-558); the interactive window / ImGui / GLFW callbacks are not part of this build, so the
-// executable always renders offline (`--render` is accepted and implied).
-// New flags: --gpus N, --partition spp|tile, --device D, --batch N (samples per launch, progress granularity).
+// :93-102, offline loop :524-558). There is no window: the interactive loop (:477-523 -- progressive trace(), draw(),
+// camera input, save at sppx) is stood in for by `--preview FILE`: the same loop with the tonemapped framebuffer written
+// to FILE (atomically, every --preview-interval seconds) for any image viewer that reloads on change, and "input" read
+// from FILE.cmd (one line of ordinary command-line flags, e.g. `--cam_pos 0 1 2 --density 50`, or `quit`). Without
+// --preview the executable renders offline (`--render` is accepted and implied).
+// New flags: --gpus N, --partition spp|tile, --device D, --batch N (samples per launch, progress granularity),
+// --preview FILE, --preview-interval SEC, --preview-keep (stay alive at sppx and wait for commands).
 #include <pybind11/embed.h>
 #include <pybind11/eval.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <filesystem>
+#include <fstream>
 #include <iostream>
+#include <sstream>
 #include <string>
+#include <thread>
+#include <vector>
+
+#include "image_io.h"
 
 #include "camera.h"
 #include "context.h"
@@ -25,6 +36,9 @@ using namespace volren;
 static bool interactive = true;   // kept for flag parity; without a window both modes run the offline loop
 static std::string out_filename = "output.png";
 static int batch_spp = 64;
+static std::string preview_file;          // --preview FILE: progressive preview (stand-in for the interactive window)
+static double preview_interval = 0.5;     // seconds between two writes of FILE
+static bool preview_keep = false;         // keep running at sppx and wait for FILE.cmd (the window would stay open)
 
 static std::shared_ptr<RendererOpenGL> renderer;
 
@@ -155,7 +169,83 @@ static void parse_cmd(int argc, char** argv) {
         else if (arg == "-w" || arg == "-h" || arg == "--title" || arg == "--major" || arg == "--minor" || arg == "--swap" || arg == "--font" || arg == "--fontsize" ||
                  arg == "--gpus" || arg == "--partition" || arg == "--device") ++i;
         else if (arg == "--batch") batch_spp = std::max(1, std::stoi(next()));
+        else if (arg == "--preview") preview_file = next();
+        else if (arg == "--preview-interval") preview_interval = std::stod(next());
+        else if (arg == "--preview-keep") preview_keep = true;
         else if (fs::is_regular_file(argv[i]) || fs::is_directory(argv[i])) handle_path(argv[i]);
+    }
+}
+
+// ------------------------------------------
+// progressive preview (main.cpp:477-523 without a window)
+
+static void write_preview() {
+    renderer->draw();                                         // tonemap.fs / blit.fs -> RGBA8 framebuffer (:516)
+    const std::vector<uint8_t> fb = renderer->read_framebuffer();
+    const fs::path target(preview_file);
+    const fs::path tmp = target.parent_path() / (target.stem().string() + ".tmp" + target.extension().string());
+    store_ldr(tmp.string(), fb.data(), int(renderer->color.w), int(renderer->color.h), 4, true);
+    fs::rename(tmp, target);                                  // viewers never see a half-written file
+}
+
+// "input": one line of command-line flags in FILE.cmd, consumed (deleted) once applied. Returns false on `quit`.
+static bool poll_preview_commands(bool& changed) {
+    const std::string cmd_file = preview_file + ".cmd";
+    std::ifstream in(cmd_file);
+    if (!in.is_open()) return true;
+    std::stringstream text;
+    text << in.rdbuf();
+    in.close();
+    fs::remove(cmd_file);
+    std::vector<std::string> tok = { "volren" };
+    std::string t;
+    while (text >> t) tok.push_back(t);
+    if (tok.size() == 1) return true;
+    if (tok[1] == "quit") return false;
+    std::vector<char*> argv;
+    for (auto& s : tok) argv.push_back(s.data());
+    parse_cmd(int(argv.size()), argv.data());
+    changed = true;
+    return true;
+}
+
+static void preview_loop() {
+    using clock = std::chrono::steady_clock;
+    current_camera()->update();
+    std::cout << "preview: " << preview_file << " (commands: " << preview_file << ".cmd)" << std::endl;
+    auto last_write = clock::now() - std::chrono::hours(1), t0 = clock::now();
+    long long traced = 0;
+    bool saved = false;
+    while (true) {
+        bool changed = false;
+        if (!poll_preview_commands(changed)) break;
+        if (changed) {                                        // CameraImpl::default_input_handler(...) -> renderer->reset() (:481-483)
+            current_camera()->update();
+            renderer->reset();
+            saved = false;
+        }
+        if (renderer->sample < renderer->sppx) {
+            const int n = std::min(batch_spp, renderer->sppx - renderer->sample);
+            renderer->trace(n);
+            Context::swap_buffers();
+            traced += n;
+            if (renderer->sample == renderer->sppx && !saved) {   // :511-512 (linear colour, flipped)
+                renderer->color.save_ldr(out_filename, true, true);
+                saved = true;
+                write_preview();
+                last_write = clock::now();
+                const double sec = std::chrono::duration<double>(clock::now() - t0).count();
+                std::cout << renderer->sample << " / " << renderer->sppx << " spp, " << double(traced) * renderer->color.w * renderer->color.h / sec / 1e9
+                          << " Gsamples/s incl. preview writes; " << out_filename << " written." << std::endl;
+                if (!preview_keep) break;
+            }
+        } else
+            std::this_thread::sleep_for(std::chrono::milliseconds(100));   // glfwWaitEventsTimeout(1.f / 10): 10 fps idle (:514)
+        if (std::chrono::duration<double>(clock::now() - last_write).count() >= preview_interval) {
+            write_preview();
+            last_write = clock::now();
+            std::cout << renderer->sample << " / " << renderer->sppx << "\r" << std::flush;
+        }
     }
 }
 
@@ -190,6 +280,12 @@ int main(int argc, char** argv) {
             renderer->commit();
         }
         renderer->reset();
+
+        if (!preview_file.empty()) {
+            preview_loop();
+            Context::shutdown();
+            return 0;
+        }
 
         // offline loop (main.cpp:524-558)
         current_camera()->update();
