@@ -204,7 +204,9 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
 int vrb_trace_deterministic(vrb_ctx* ctx, const vrb_params* params);
 /* kernel selection: 0 = persistent-thread kernel with MUFU fast math (default, production);
  * 1 = the straightforward one-thread-per-pixel kernel with IEEE math; 2 = the persistent kernel with IEEE math.
- * 1 and 2 are cross-checks: 2 must reproduce 1 (same paths, same counters), 0 is compared statistically */
+ * 1 and 2 are cross-checks: 2 must reproduce 1 (same paths, same counters), 0 is compared statistically.
+ * 3 / 4 = the two-rays-per-lane schedule (vr_trace3.cuh) with fast / IEEE math: bit-identical to 0 / 2, measured within
+ * a few percent of 0 (profiles/r01_v10_duo_and_steps_sweeps.txt). Environment variable VRB200_KERNEL sets the default. */
 int vrb_set_kernel(vrb_ctx* ctx, int kind);
 /* scheduling options of the production kernel (none changes the image): "lpt" (heaviest tiles first, default 1),
  * "cull" (hidden environment only: pixels outside the screen rectangle of the volume's box and 8x4 tiles onto which no

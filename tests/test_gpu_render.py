@@ -312,6 +312,34 @@ def test_persistent_kernel_equals_simple_kernel(smoke_ctx, oracle, smoke_grid, l
     assert np.allclose(out[0], out[1], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("use_tf", [False, True])
+def test_two_rays_per_lane_kernel_is_bit_identical(smoke_ctx, oracle, smoke_grid, lut_raw, use_tf):
+    """k_trace_duo (vr_trace3.cuh: two rays per lane, event state in shared memory) is a different SCHEDULE of the same
+    per-path arithmetic: images and event counters equal those of the one-ray persistent kernel bit for bit, with fast
+    math (3 vs 0) and with IEEE math (4 vs 2)."""
+    W, H, SPP = 150, 90, 6
+    lut, _ = oracle.lut_upload(lut_raw)
+    smoke_ctx.tf_upload(lut)
+    p = default_scene(smoke_grid, W, H, bounces=128, use_tf=True) if use_tf else readme_scene(smoke_grid, W, H)
+    smoke_ctx.resize(W, H)
+    try:
+        for base, duo in ((0, 3), (2, 4)):
+            out, cnt = [], []
+            for kind in (base, duo):
+                smoke_ctx.set_kernel(kind)
+                smoke_ctx.clear()
+                smoke_ctx.set_counting(True)
+                smoke_ctx.trace(p, 3, SPP)
+                cnt.append(smoke_ctx.get_counters().as_dict())
+                smoke_ctx.set_counting(False)
+                smoke_ctx.trace(p, 3 + SPP, SPP)          # and the non-counting build on top
+                out.append(smoke_ctx.download_color())
+            assert cnt[0] == cnt[1], (base, duo)
+            assert np.array_equal(out[0], out[1]), (base, duo)
+    finally:
+        smoke_ctx.set_kernel(0)
+
+
 def test_scheduling_options_do_not_change_the_image(smoke_ctx, oracle, smoke_grid, lut_raw):
     """Heaviest-tiles-first order, screen-space box culling and the pass size are pure scheduling: bit-identical images."""
     W, H = 200, 120                               # not a multiple of the 8x4 tile: border tiles
@@ -332,7 +360,7 @@ def test_scheduling_options_do_not_change_the_image(smoke_ctx, oracle, smoke_gri
         # a pixel row far from the volume is exactly zero with the environment hidden
         if not p.show_environment:
             assert np.all(images[0][0] == 0)
-    smoke_ctx.set_option("lpt", 1); smoke_ctx.set_option("cull", 1); smoke_ctx.set_option("pass", 16)
+    smoke_ctx.set_option("lpt", 1); smoke_ctx.set_option("cull", 1); smoke_ctx.set_option("pass", 32)
     with pytest.raises(Exception):
         smoke_ctx.set_option("nonsense", 1)
 

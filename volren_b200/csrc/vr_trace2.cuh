@@ -86,10 +86,10 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #define VR_K_COLLIDE 4
 #endif
 #ifndef VR_MIN_STEP_TF
-#define VR_MIN_STEP_TF 4
+#define VR_MIN_STEP_TF 8
 #endif
 #ifndef VR_MIN_STEP
-#define VR_MIN_STEP 16    // fewer stepping lanes than this: drain the fullest queue even below its threshold
+#define VR_MIN_STEP 24    // fewer stepping lanes than this: drain the fullest queue even below its threshold
 #endif
 // Speculative null collisions (VR_SPECULATE): 92-94 % of the tentative collisions of the bench scenes are null, and the
 // number of random draws a null collision consumes is fixed (density filter 9 | 0, emission filter 9 on camera segments,
@@ -117,6 +117,10 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #endif
 #ifndef VR_K_PENDING
 #define VR_K_PENDING 24
+#endif
+#ifndef VR_STEPS_PER_PASS
+#define VR_STEPS_PER_PASS 3       // DDA steps per scheduler pass: the five ballots + queue logic are 7 % of the issued instructions at 32 lanes;
+                                  // B200 (TF / non-TF Gsamples/s): 1 -> 37.0 / 4.01, 2 -> 39.0 / 4.19, 3 -> 38.8 / 4.26, 4 -> 38.2 / 4.16, 6 -> 36.6 / 3.88
 #endif
 constexpr int MAX_RAY_STEPS = 1 << 20;  // hang guard only: no finite ray takes this many DDA steps
 
@@ -163,6 +167,8 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
 
     while (true) {
         // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) =================
+#pragma unroll
+        for (int rep = 0; rep < VR_STEPS_PER_PASS; ++rep)
         if (stage == SG_STEP) {
             if (t < tfar) {
                 const float3 curr = ipos + t * idir;

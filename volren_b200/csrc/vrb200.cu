@@ -8,6 +8,7 @@
 #include "vr_env.cuh"
 #include "vr_trace.cuh"
 #include "vr_trace2.cuh"
+#include "vr_trace3.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -101,7 +102,7 @@ struct vrb_ctx {
     int tile_coords_tx = 0;      // tiles_x the packed coordinates in tile_iota were made for
     bool counting = false;
     int kernel = 0;            // 0 = persistent FastMath (production), 1 = simple strict cross-check, 2 = persistent StrictMath
-    int trace_blocks[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    int trace_blocks[16] = { 0 };
     uint64_t lut_version = 0;
     std::string err;
 };
@@ -439,6 +440,7 @@ int vrb_create(int device, vrb_ctx** out) {
     if (const char* e = getenv("VRB200_LPT")) ctx->lpt = atoi(e) != 0;
     if (const char* e = getenv("VRB200_CULL")) ctx->cull = atoi(e) != 0;
     if (const char* e = getenv("VRB200_PASS")) ctx->pass_samples = std::max(1, atoi(e));
+    if (const char* e = getenv("VRB200_KERNEL")) ctx->kernel = std::min(4, std::max(0, atoi(e)));
     cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream);
     *out = ctx;
     return VRB_OK;
@@ -1074,7 +1076,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     a.tiles_x = std::max(1, (a.x1 - a.x0 + 7) / 8);
     const int n_tiles = std::max(1, a.tiles_x * ((a.y1 - a.y0 + 3) / 4));
     // ---- heaviest tiles first: order the blocks by the per-tile cost the previous launch of this view measured ----
-    const bool lpt = ctx->lpt && !ctx->counting && ctx->kernel == 0;
+    const bool lpt = ctx->lpt && !ctx->counting && (ctx->kernel == 0 || ctx->kernel == 3);
     uint64_t vkey = key;
     if (a.tiles_x >= 65536 || n_tiles / a.tiles_x >= 65536) return fail(ctx, VRB_ERR_INVALID, "image too large");
     {
@@ -1108,9 +1110,18 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             ctx->tile_coords_tx = a.tiles_x;
         }
     }
-    const int variant = (tf ? 1 : 0) | (ctx->counting ? 2 : 0) | (ctx->kernel == 2 ? 4 : 0);
+    const bool duo = ctx->kernel == 3 || ctx->kernel == 4;
+    const int variant = (tf ? 1 : 0) | (ctx->counting ? 2 : 0) | ((ctx->kernel == 2 || ctx->kernel == 4) ? 4 : 0) | (duo ? 8 : 0);
     const void* fn = nullptr;
     switch (variant) {
+        case 8: fn = (const void*)k_trace_duo<false, false, FastMath>; break;
+        case 9: fn = (const void*)k_trace_duo<true, false, FastMath>; break;
+        case 10: fn = (const void*)k_trace_duo<false, true, FastMath>; break;
+        case 11: fn = (const void*)k_trace_duo<true, true, FastMath>; break;
+        case 12: fn = (const void*)k_trace_duo<false, false, StrictMath>; break;
+        case 13: fn = (const void*)k_trace_duo<true, false, StrictMath>; break;
+        case 14: fn = (const void*)k_trace_duo<false, true, StrictMath>; break;
+        case 15: fn = (const void*)k_trace_duo<true, true, StrictMath>; break;
         case 0: fn = (const void*)k_trace_persistent<false, false, FastMath>; break;
         case 1: fn = (const void*)k_trace_persistent<true, false, FastMath>; break;
         case 2: fn = (const void*)k_trace_persistent<false, true, FastMath>; break;
@@ -1191,7 +1202,7 @@ int vrb_set_option(vrb_ctx* ctx, const char* name, int value) {
 
 int vrb_set_kernel(vrb_ctx* ctx, int kind) {
     if (!ctx) return VRB_ERR_INVALID;
-    if (kind < 0 || kind > 2) return fail(ctx, VRB_ERR_INVALID, "kernel kind must be 0 (persistent, fast math), 1 (simple, strict math) or 2 (persistent, strict math)");
+    if (kind < 0 || kind > 4) return fail(ctx, VRB_ERR_INVALID, "kernel kind must be 0 (persistent, fast math), 1 (simple, strict math), 2 (persistent, strict math), 3 (two rays per lane, fast math) or 4 (two rays per lane, strict math)");
     ctx->kernel = kind;
     return VRB_OK;
 }
