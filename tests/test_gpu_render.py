@@ -407,3 +407,48 @@ def test_screen_space_brick_mask_is_exact(smoke_ctx, oracle, smoke_grid, lut_raw
     smoke_ctx.clear()
     smoke_ctx.trace(params(cams[0], True), 1, 4)
     assert smoke_ctx.download_color()[..., 3].max() > 0
+
+
+def test_cached_tile_order_follows_the_grid_contents(ctx, oracle, lut_raw):
+    """The brick mask and the tile order are cached per (view, grid contents) and re-used for several passes
+    (vrb200.cu ORDER_REUSE). Re-uploading DIFFERENT voxels into the same slot, same shape, same view, must rebuild
+    them: with the environment hidden the culled image still equals the unculled one bit for bit, for more passes than
+    the re-use window."""
+    from volren_b200 import scene
+    W, H, N = 160, 96, 40
+    lut, _ = oracle.lut_upload(lut_raw)
+    ctx.tf_upload(lut)
+    ctx.resize(W, H)
+    z, y, x = np.mgrid[0:N, 0:N, 0:N].astype(np.float32) / N
+
+    def blob(cx, cy):
+        f = np.exp(-(((x - cx) / .12) ** 2 + ((y - cy) / .12) ** 2 + ((z - .5) / .2) ** 2))
+        return (np.clip(f - 0.2, 0, 1) / 0.8 * 255).astype(np.uint8)
+
+    class G:            # what helpers.default_scene needs of a grid
+        min_maj = (0.0, 1.0)
+        def matrix(self): return np.eye(4, dtype=np.float32)
+        def index_extent(self): return (N, N, N)
+
+    from helpers import default_scene
+    p = default_scene(G(), W, H, bounces=6, use_tf=True)
+    assert not p.show_environment
+    ctx.set_option("pass", 2)
+    try:
+        results = []
+        for cx, cy in ((.25, .3), (.75, .7)):            # the two volumes light up different tiles
+            vox = blob(cx, cy)
+            per_cull = []
+            for cull in (1, 0):
+                ctx.set_option("cull", cull)
+                ctx.grid_clear()
+                ctx.grid_build_from_dense(vox, 0.0, 1.0)
+                ctx.clear()
+                ctx.trace(p, 1, 24)                       # 12 passes of 2 samples: beyond the re-use window
+                per_cull.append(ctx.download_color())
+            assert np.array_equal(per_cull[0], per_cull[1])
+            results.append(per_cull[0])
+        a, b = results[0][..., 3] > 0, results[1][..., 3] > 0
+        assert a.any() and b.any() and (a & ~b).any() and (b & ~a).any()
+    finally:
+        ctx.set_option("cull", 1); ctx.set_option("pass", 32)

@@ -51,6 +51,7 @@ struct DeviceGrid {
     // majorant tables of the persistent kernel, valid for maj_key
     float* maj[4] = { nullptr, nullptr, nullptr, nullptr };
     uint64_t maj_key = 0;
+    uint64_t version = 0;           // bumped whenever the contents change (keys the cached tile order / brick mask)
 };
 
 struct Frame {
@@ -95,6 +96,8 @@ struct vrb_ctx {
     size_t sort_tmp_bytes = 0;
     int tile_capacity = 0;
     uint64_t cost_key = 0;       // view the costs in tile_cost belong to (0 = none)
+    uint64_t order_key = 0;      // (view, grid contents, mask / cost mode) tile_order + tile_live + live_info were built for (0 = none)
+    int order_age = 0;           // passes traced with that order; it is rebuilt from the latest costs every ORDER_REUSE passes
     bool lpt = true;             // VRB200_LPT=0 disables
     bool cull = true;            // VRB200_CULL=0 disables the screen-space box culling
     bool async_upload = false;   // option "async_upload": upload calls return without waiting; the caller keeps the host buffers alive until vrb_sync / a download
@@ -170,6 +173,8 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
         CK(pool_alloc(&g.recp, size_t(g.nb.x + 2) * (g.nb.y + 2) * (g.nb.z + 2) * sizeof(uint2), ctx->stream));
     }
     g.maj_key = 0;   // the majorant tables (if any) belong to the previous contents
+    static uint64_t grid_versions = 0;
+    g.version = ++grid_versions;
     CK(cudaMemsetAsync(g.atlas_lin + g.n_slots * 512, 0, 512, ctx->stream));   // the all-zero brick
     k_make_records<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.indirection, g.range, n, ab, g.rec);
     CK_LAUNCH();
@@ -1093,7 +1098,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             cudaFree(ctx->tile_live); cudaFree(ctx->tile_key); cudaFree(ctx->live_info);
             ctx->tile_cost = ctx->tile_cost_sorted = nullptr; ctx->tile_iota = ctx->tile_order = nullptr; ctx->sort_tmp = nullptr;
             ctx->tile_live = ctx->tile_key = ctx->live_info = nullptr;
-            ctx->tile_capacity = 0; ctx->cost_key = 0;
+            ctx->tile_capacity = 0; ctx->cost_key = 0; ctx->order_key = 0;
             CK(cudaMalloc(&ctx->tile_live, size_t(n_tiles) * 4));
             CK(cudaMalloc(&ctx->tile_key, size_t(n_tiles) * 4));
             CK(cudaMalloc(&ctx->live_info, 8));
@@ -1155,7 +1160,17 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         }
         CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
         const bool cost_valid = lpt && ctx->cost_key == vkey;      // the previous pass / launch measured this view
-        if (mask) {
+        // The brick mask and the tile order are functions of (view, grid contents, mode): a static view re-uses them and
+        // re-sorts from the latest measured costs every ORDER_REUSE passes (mask + keys + 4 radix passes are ~50 us per pass)
+        constexpr int ORDER_REUSE = 8;
+        uint64_t okey = vkey ^ (g.version * 0x9e3779b97f4a7c15ull) ^ (mask ? 0x5bd1e995ull : 0ull) ^ (cost_valid ? 0xc2b2ae35ull << 8 : 0ull);
+        if (okey == 0) okey = 1;
+        if ((mask || cost_valid) && ctx->order_key == okey && ctx->order_age < ORDER_REUSE) {
+            ++ctx->order_age;
+            a.tile_order = ctx->tile_order;
+            if (mask) a.n_live = ctx->live_info;
+        } else if (mask) {
+            ctx->order_key = okey; ctx->order_age = 1;
             CK(cudaMemsetAsync(ctx->tile_live, 0, size_t(n_tiles) * 4, ctx->stream));
             CK(cudaMemsetAsync(ctx->live_info, 0, 8, ctx->stream));
             k_tile_mask<<<grid_for(n0, 128, ctx->sm_count), 128, 0, ctx->stream>>>(a, g.maj[0], ctx->tile_live, ctx->live_info, (a.y1 - a.y0 + 3) / 4);
@@ -1167,6 +1182,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             a.tile_order = ctx->tile_order;
             a.n_live = ctx->live_info;
         } else if (cost_valid) {
+            ctx->order_key = okey; ctx->order_age = 1;
             size_t tmp_bytes = ctx->sort_tmp_bytes;
             CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
             a.tile_order = ctx->tile_order;
