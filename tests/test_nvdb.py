@@ -267,3 +267,12 @@ def test_gpu_host_renders_a_nvdb_volume(nvdb_golden, ctx, env_rgb, tmp_path):
     ctx.trace(params, 1, 4)
     assert np.array_equal(data, ctx.download_color()[..., :3])
     assert data.max() > 0 and np.isfinite(data).all()
+
+
+@pytest.mark.gpu
+def test_gpu_empty_extent_is_an_error(ctx):
+    """An empty NanoVDB grid has index extent 0 (grid_nvdb.cpp:15); the reference's brick constructor then divides by
+    n_bricks.x * n_bricks.y (grid_brick.cpp:112). Here: a clear error instead of undefined behaviour."""
+    import volren_b200 as vr
+    with pytest.raises(vr.VrbError, match="empty grid"):
+        ctx.grid_build_from_values(np.zeros((12, 12, 4), np.float32), (0, 5, 5), frame=3)

@@ -614,6 +614,7 @@ int vrb_grid_build_from_values(vrb_ctx* ctx, int slot, int frame, const float* p
     int st = check_slot_frame(ctx, slot, frame);
     if (st) return st;
     if (!padded_values || !extent) return fail(ctx, VRB_ERR_INVALID, "bad value lattice");
+    if (!extent[0] || !extent[1] || !extent[2]) return fail(ctx, VRB_ERR_INVALID, "empty grid (index extent 0): nothing to build");
     uint3 nb;
     if (compute_n_bricks(extent, nb) != VRB_OK) return fail(ctx, VRB_ERR_TOO_MANY_BRICKS, "exceeded max brick count of 1024");
     DeviceGuard guard(ctx->device);
@@ -805,6 +806,8 @@ int vrb_grid_build_from_nvdb(vrb_ctx* ctx, int slot, int frame, const void* grid
     int st = check_slot_frame(ctx, slot, frame);
     if (st) return st;
     if (!grid || !info || info->grid_size < nvdb::GRID_SIZE + nvdb::TREE_SIZE + nvdb::ROOT_SIZE) return fail(ctx, VRB_ERR_INVALID, "bad NanoVDB grid");
+    // an empty NanoVDB grid has extent 0; the reference's constructor divides by n_bricks.x * n_bricks.y there (grid_brick.cpp:112)
+    if (!info->extent[0] || !info->extent[1] || !info->extent[2]) return fail(ctx, VRB_ERR_INVALID, "empty grid (index extent 0): nothing to build");
     uint3 nb;
     if (compute_n_bricks(info->extent, nb) != VRB_OK) return fail(ctx, VRB_ERR_TOO_MANY_BRICKS, "exceeded max brick count of 1024");
     DeviceGuard guard(ctx->device);
