@@ -21,7 +21,13 @@ struct EnvView {
     const float4* rgb;   // w*h texels, bottom-up, .w unused
     int w, h;
     const float* impmap; // pyramid, levels concatenated
+    const float4* split; // per 2x2 quad of every pyramid level: the split probabilities of sample_environment and their
+                         // reciprocals (k_env_split), 3 x float4 per quad; nullptr: evaluate them per sample
 };
+
+// quads of level `mip` (its texels are (512 >> mip)^2) start at quad (4^(8 - mip) - 1) / 3
+VR_HD constexpr uint32_t split_offset(int mip) { return ((1u << (2 * (8 - mip))) - 1u) / 3u; }
+constexpr uint32_t SPLIT_QUADS = ((1u << 18) - 1u) / 3u;   // levels 8 ... 0: 1 + 4 + ... + 65536
 
 VR_DEV int wrap_repeat(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
 

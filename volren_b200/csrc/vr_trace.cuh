@@ -146,6 +146,9 @@ VR_DEV float brick_majorant(const GridView& g, float3 ipos, int mip) {
 // FastMath tests `r * sum < w` instead of `r < w / max(1e-3, sum)` (no division; the running sums of the B-spline weights
 // are w0 + w1 in [1/6, 5/6], 1 - w3 >= 5/6 and 1, so the max() never acts) and evaluates the weights in Horner form with
 // the 1/6 folded into the coefficients (21 instead of 34 instructions per axis).
+#ifndef VR_ENV_SPLIT
+#define VR_ENV_SPLIT 1      // sample_environment reads the precomputed split tables (k_env_split)
+#endif
 #ifndef VR_LEAN_FILTER
 #define VR_LEAN_FILTER 1
 #endif
@@ -403,10 +406,47 @@ VR_DEV float pdf_environment(const TraceArgs& a, float3 Le_dir) {
 }
 
 // sample_environment (common.glsl:100-146): hierarchical 2x2 warping down the importance pyramid (rolled: code size)
+// The per-level quantities dsplit, e and the reciprocals the remaps multiply with depend on the quad only: k_env_split
+// evaluates them once per environment with these very expressions (FastMath: a * rcp.approx(b)), so the table path
+// returns the same bits with 2 dependent 16-byte loads and no MUFU per level instead of 2 loads + 4 MUFU.RCP.
+__global__ void k_env_split(const float* __restrict__ impmap, float4* __restrict__ split) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < SPLIT_QUADS; i += gridDim.x * blockDim.x) {
+        int mip = 8;
+        while (mip > 0 && i >= split_offset(mip - 1)) --mip;
+        const uint32_t q = i - split_offset(mip), half = (IMP_DIM >> mip) >> 1, d = IMP_DIM >> mip;
+        const uint32_t qx = q % half, qy = q / half;
+        const float* base = impmap + imp_offset(mip) + size_t(2 * qy) * d + 2 * qx;
+        const float w0 = base[0], w1 = base[1], w2 = base[d], w3 = base[d + 1];
+        const float q0 = w0 + w2, q1 = w1 + w3;
+        const float dsplit = FastMath::div(q0, fmaxf(1e-8f, q0 + q1));
+        const float el = FastMath::div(w0, q0), er = FastMath::div(w1, q1);
+        split[3 * size_t(i)] = make_float4(dsplit, FastMath::rcp(dsplit), FastMath::rcp(1.f - dsplit), 0.f);
+        split[3 * size_t(i) + 1] = make_float4(el, FastMath::rcp(el), FastMath::rcp(1.f - el), 0.f);
+        split[3 * size_t(i) + 2] = make_float4(er, FastMath::rcp(er), FastMath::rcp(1.f - er), 0.f);
+    }
+}
+
 template <class MT>
 VR_DEV float4 sample_environment(const TraceArgs& a, float px, float py, float3& w_i) {
     int posx = 0, posy = 0;
     uint32_t off = imp_offset(9);
+    if (MT::fast && VR_ENV_SPLIT && a.env.split) {
+        uint32_t qoff = 0, half = 1;          // quad offset and quads per row of the level
+#pragma unroll 1
+        for (int mip = 8; mip >= 0; --mip) {
+            const float4* q = a.env.split + 3 * size_t(qoff + uint32_t(posy) * half + uint32_t(posx));
+            const float4 s = __ldg(q);
+            const bool right = !(px < s.x);
+            px = right ? (px - s.x) * s.z : px * s.y;
+            const float4 e = __ldg(q + (right ? 2 : 1));
+            const bool top = !(py < e.x);
+            py = top ? (py - e.x) * e.z : py * e.y;
+            posx = 2 * posx + (right ? 1 : 0);
+            posy = 2 * posy + (top ? 1 : 0);
+            qoff += half * half;
+            half *= 2;
+        }
+    } else
 #pragma unroll 1
     for (int mip = 8; mip >= 0; --mip) {
         posx *= 2; posy *= 2;

@@ -75,6 +75,7 @@ struct vrb_ctx {
     float* env_stage = nullptr;      // RGB staging of vrb_env_upload (kept while the size stays the same)
     int env_w = 0, env_h = 0;
     float* impmap = nullptr;
+    float4* env_split = nullptr;   // split tables of sample_environment (k_env_split), rebuilt with the pyramid
     float4* lut = nullptr;
     uint32_t tf_size = 0;
     unsigned long long* counters = nullptr;
@@ -380,6 +381,7 @@ int fill_trace_args(vrb_ctx* ctx, const vrb_params* p, TraceArgs& a) {
     a.env.w = ctx->env_w;
     a.env.h = ctx->env_h;
     a.env.impmap = ctx->impmap;
+    a.env.split = ctx->env_split;
     a.lut = ctx->lut;
     a.tf_size = ctx->tf_size;
     a.color = ctx->color;
@@ -460,7 +462,7 @@ void vrb_destroy(vrb_ctx* ctx) {
     cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
     cudaFree(ctx->tile_live); cudaFree(ctx->tile_key); cudaFree(ctx->live_info);
     cudaFree(ctx->lbuf); cudaFree(ctx->env_stage);
-    cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
+    cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->env_split); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
     cudaStreamSynchronize(ctx->stream);
     {   // hand the pooled grid memory back to the driver
         cudaMemPool_t pool;
@@ -920,6 +922,7 @@ int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h) {
     if (!rgb || w <= 0 || h <= 0) return fail(ctx, VRB_ERR_INVALID, "bad environment map");
     DeviceGuard guard(ctx->device);
     if (!ctx->impmap) CK(cudaMalloc(&ctx->impmap, size_t(imp_offset(IMP_LEVELS)) * 4));
+    if (!ctx->env_split) CK(cudaMalloc(&ctx->env_split, size_t(SPLIT_QUADS) * 3 * sizeof(float4)));
     const size_t n = size_t(w) * h;
     if (!ctx->env_rgb || ctx->env_w != w || ctx->env_h != h) {     // same size as before: keep the allocations
         CK(cudaStreamSynchronize(ctx->stream));
@@ -933,7 +936,7 @@ int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h) {
     k_env_pad<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(d_rgb, ctx->env_rgb, n);
     CK_LAUNCH();
     ctx->env_w = w; ctx->env_h = h;
-    EnvView e { ctx->env_rgb, w, h, ctx->impmap };
+    EnvView e { ctx->env_rgb, w, h, ctx->impmap, nullptr };
     k_env_impmap<<<dim3(IMP_DIM / 16, IMP_DIM / 16), 256, 0, ctx->stream>>>(e, ctx->impmap);
     CK_LAUNCH();
     for (int l = 1; l < IMP_LEVELS; ++l) {
@@ -942,6 +945,8 @@ int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h) {
         k_env_mip<<<grid, block, 0, ctx->stream>>>(ctx->impmap + imp_offset(l - 1), d * 2, ctx->impmap + imp_offset(l), d);
         CK_LAUNCH();
     }
+    k_env_split<<<grid_for(SPLIT_QUADS, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->impmap, ctx->env_split);
+    CK_LAUNCH();
     if (!ctx->async_upload) CK(cudaStreamSynchronize(ctx->stream));   // host buffer is only borrowed for the duration of the call
     return VRB_OK;
 }
