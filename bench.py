@@ -284,6 +284,7 @@ def main():
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = ctx.get_stat("trace_launches")
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                   # L2 flush between timed iterations (not timed)
         barrier()
@@ -293,6 +294,7 @@ def main():
         ev[k][1].record()
         kev_cur[0] = None
         barrier()
+    launches = ctx.get_stat("trace_launches") - launches0      # counted by the library at its launch sites
     clocks = sampler.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     kms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
@@ -413,7 +415,7 @@ def main():
                 "note": "latency/issue-bound gather workload on an L2-resident volume: see DESIGN.md for the L2 roofline",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "lanes": n_lanes},
-            "gpu_launches": args.steps * 2,     # per step: k_trace_persistent + k_fold (the tile sort is cub, memsets are not kernels of ours)
+            "gpu_launches": int(launches),      # rank 0's own kernels in the timed region (tracking kernel + k_fold per step, brick mask + tile keys when the cached order is rebuilt)
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

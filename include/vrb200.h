@@ -219,6 +219,9 @@ int vrb_set_kernel(vrb_ctx* ctx, int kind);
  * or download on this context; pass pinned memory so that the copies really are asynchronous. A pipelined caller can
  * then enqueue the uploads and the trace of the next frame while the previous one is still running. */
 int vrb_set_option(vrb_ctx* ctx, const char* name, int value);
+/* counters of the context: "trace_launches" = hand-written kernels vrb_trace has launched so far on the production path
+ * (majorant tables, brick mask, tile keys, tracking kernel, fold; library sorts and memsets are not counted) */
+int vrb_get_stat(vrb_ctx* ctx, const char* name, uint64_t* out);
 /* color *= s (finalise VRB_ACCUM_SUM buffers) */
 int vrb_scale(vrb_ctx* ctx, float s);
 /* zero the colour buffer */

@@ -275,4 +275,5 @@ def test_gpu_empty_extent_is_an_error(ctx):
     n_bricks.x * n_bricks.y (grid_brick.cpp:112). Here: a clear error instead of undefined behaviour."""
     import volren_b200 as vr
     with pytest.raises(vr.VrbError, match="empty grid"):
-        ctx.grid_build_from_values(np.zeros((12, 12, 4), np.float32), (0, 5, 5), frame=3)
+        nb, pd = vr._capi.brick_lattice((0, 5, 5))
+        ctx.grid_build_from_values(np.zeros((pd[2], pd[1], pd[0]), np.float32), (0, 5, 5), frame=3)

@@ -20,7 +20,7 @@ SYMBOLS = [
     "vrb_create", "vrb_destroy", "vrb_last_error", "vrb_status_string", "vrb_abi_version", "vrb_set_stream", "vrb_sync",
     "vrb_resize", "vrb_grid_clear", "vrb_grid_free", "vrb_grid_upload_brick", "vrb_grid_build_from_dense",
     "vrb_grid_build_from_dense_device", "vrb_brick_lattice", "vrb_grid_build_from_values", "vrb_nvdb_open", "vrb_nvdb_lookup", "vrb_grid_build_from_nvdb", "vrb_grid_info", "vrb_grid_download", "vrb_debug_sample_density", "vrb_dense_from_float",
-    "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_set_option", "vrb_scale",
+    "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_set_option", "vrb_get_stat", "vrb_scale",
     "vrb_clear", "vrb_set_counting", "vrb_get_counters", "vrb_tonemap", "vrb_download_color", "vrb_download_color_ldr",
     "vrb_download_framebuffer", "vrb_upload_color", "vrb_color_device_ptr", "vrb_bind_color", "vrb_reduce", "vrb_copy_rows",
 ]
@@ -127,6 +127,7 @@ def load_library(path: str = LIB_PATH):
     L.vrb_trace_deterministic.argtypes = [vp, C.POINTER(Params)]
     L.vrb_set_kernel.argtypes = [vp, ci]
     L.vrb_set_option.argtypes = [vp, C.c_char_p, ci]
+    L.vrb_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
     L.vrb_scale.argtypes = [vp, cf]
     L.vrb_clear.argtypes = [vp]
     L.vrb_set_counting.argtypes = [vp, ci]
@@ -338,6 +339,11 @@ class Context:
 
     def set_option(self, name, value):
         self._ck(self.lib.vrb_set_option(self.handle, name.encode(), int(value)))
+
+    def get_stat(self, name):
+        v = C.c_uint64()
+        self._ck(self.lib.vrb_get_stat(self.handle, name.encode(), C.byref(v)))
+        return int(v.value)
 
     def scale(self, s):
         self._ck(self.lib.vrb_scale(self.handle, s))

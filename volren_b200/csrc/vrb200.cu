@@ -101,6 +101,7 @@ struct vrb_ctx {
     int order_age = 0;           // passes traced with that order; it is rebuilt from the latest costs every ORDER_REUSE passes
     bool lpt = true;             // VRB200_LPT=0 disables
     bool cull = true;            // VRB200_CULL=0 disables the screen-space box culling
+    uint64_t trace_launches = 0; // hand-written kernels launched by vrb_trace so far (vrb_get_stat "trace_launches")
     bool async_upload = false;   // option "async_upload": upload calls return without waiting; the caller keeps the host buffers alive until vrb_sync / a download
     bool count_culled = false;   // option "count_culled": the counting build keeps the culling (events of the production launch, not of the reference algorithm)
     int tile_coords_tx = 0;      // tiles_x the packed coordinates in tile_iota were made for
@@ -1031,6 +1032,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             if (tf) k_majorant_table<true><<<blocks, 256, 0, ctx->stream>>>(a, l, g.maj[l], n);
             else k_majorant_table<false><<<blocks, 256, 0, ctx->stream>>>(a, l, g.maj[l], n);
             CK_LAUNCH();
+            ++ctx->trace_launches;
         }
         g.maj_key = key;
     }
@@ -1185,6 +1187,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             CK_LAUNCH();
             k_tile_keys<<<grid_for(size_t(n_tiles), 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->tile_live, cost_valid ? ctx->tile_cost : nullptr, ctx->tile_key, ctx->live_info, n_tiles);
             CK_LAUNCH();
+            ctx->trace_launches += 2;      // k_tile_mask + k_tile_keys
             size_t tmp_bytes = ctx->sort_tmp_bytes;
             CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_key, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
             a.tile_order = ctx->tile_order;
@@ -1204,6 +1207,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
         void* kargs[] = { (void*)&a };
         CK(cudaLaunchKernel(fn, dim3(blocks), dim3(VR_TRACE_BLOCK), kargs, 0, ctx->stream));
+        ctx->trace_launches += 2;          // the tracking kernel + k_fold below
         k_fold<<<dim3((fold_x1 - fold_x0 + 63) / 64, (fold_y1 - fold_y0 + 3) / 4), 256, 0, ctx->stream>>>(
             ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode,
             mask ? ctx->tile_live : nullptr, mask ? ctx->live_info : nullptr, a.tiles_x);
@@ -1221,6 +1225,14 @@ int vrb_set_option(vrb_ctx* ctx, const char* name, int value) {
     else if (!strcmp(name, "async_upload")) ctx->async_upload = value != 0;
     else if (!strcmp(name, "pass")) { if (value < 1) return fail(ctx, VRB_ERR_INVALID, "pass must be >= 1"); ctx->pass_samples = value; }
     else return fail(ctx, VRB_ERR_INVALID, "unknown option '%s'", name);
+    return VRB_OK;
+}
+
+int vrb_get_stat(vrb_ctx* ctx, const char* name, uint64_t* out) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!name || !out) return fail(ctx, VRB_ERR_INVALID, "NULL argument");
+    if (!strcmp(name, "trace_launches")) *out = ctx->trace_launches;
+    else return fail(ctx, VRB_ERR_INVALID, "unknown statistic '%s'", name);
     return VRB_OK;
 }
 
