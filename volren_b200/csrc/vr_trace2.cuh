@@ -122,6 +122,9 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #define VR_STEPS_PER_PASS 3       // DDA steps per scheduler pass: the five ballots + queue logic are 7 % of the issued instructions at 32 lanes;
                                   // B200 (TF / non-TF Gsamples/s): 1 -> 37.0 / 4.01, 2 -> 39.0 / 4.19, 3 -> 38.8 / 4.26, 4 -> 38.2 / 4.16, 6 -> 36.6 / 3.88
 #endif
+#ifndef VR_REP_MIN
+#define VR_REP_MIN 0              // repeat a step only while this many lanes are still stepping (0: always)
+#endif
 constexpr int MAX_RAY_STEPS = 1 << 20;  // hang guard only: no finite ray takes this many DDA steps
 
 template <bool TF, bool COUNT, class MT>
@@ -168,7 +171,9 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
     while (true) {
         // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) =================
 #pragma unroll
-        for (int rep = 0; rep < VR_STEPS_PER_PASS; ++rep)
+        for (int rep = 0; rep < VR_STEPS_PER_PASS; ++rep) {
+        // a further step only while enough lanes still step (one vote instead of the full scheduler)
+        if (VR_REP_MIN > 0 && rep > 0 && __popc(__ballot_sync(FULL, stage == SG_STEP)) < VR_REP_MIN) break;
         if (stage == SG_STEP) {
             if (t < tfar) {
                 const float3 curr = ipos + t * idir;
@@ -199,6 +204,8 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                     stage = SG_FINISH;
                 }
             }
+        }
+
         }
 
         // ================= scheduler =================
