@@ -122,6 +122,11 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #define VR_STEPS_PER_PASS 3       // DDA steps per scheduler pass: the five ballots + queue logic are 7 % of the issued instructions at 32 lanes;
                                   // B200 (TF / non-TF Gsamples/s): 1 -> 37.0 / 4.01, 2 -> 39.0 / 4.19, 3 -> 38.8 / 4.26, 4 -> 38.2 / 4.16, 6 -> 36.6 / 3.88
 #endif
+#ifndef VR_STEP_PREFETCH
+#define VR_STEP_PREFETCH 0        // 1: fetch the majorants of all steps of a pass before consuming the first (bit-identical;
+                                  // measured: TF 41.0 -> 41.2, non-TF 4.37 -> 4.06 Gsamples/s: the discarded geometry costs more than the
+                                  // overlapped loads save, profiles/r01_v10_duo_and_steps_sweeps.txt)
+#endif
 #ifndef VR_REP_MIN
 #define VR_REP_MIN 0              // repeat a step only while this many lanes are still stepping (0: always)
 #endif
@@ -170,6 +175,53 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
 
     while (true) {
         // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) =================
+#if VR_STEP_PREFETCH && !VR_SPECULATE
+        // The geometry of the next R steps (positions, step lengths, mip levels) does not depend on the majorants, only on
+        // whether a tentative collision interrupts the walk: fetch all R majorants first (R loads in flight instead of a
+        // load -> use chain per step), then consume them in order; after a collision or the end of the ray the remaining
+        // ones are dropped. Same arithmetic per step, hence the same t / tau / mip sequence bit for bit.
+        if (stage == SG_STEP) {
+            constexpr int R = VR_STEPS_PER_PASS;
+            float dts[R], majs[R];
+            {
+                float tk = t, mk = mip;
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const float3 curr = ipos + tk * idir;
+                    const int m = round_mip(mk);
+                    majs[k] = (tk < tfar) ? table_majorant(a, curr, m) : 0.f;
+                    dts[k] = step_dda(curr, ri, m);
+                    tk += dts[k];
+                    mk = fminf(mk + 0.25f, 3.f);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                if (stage == SG_STEP && t < tfar) {
+                    cnt.maj();
+                    majorant = majs[k];
+                    const float dt = dts[k];
+                    t += dt;
+                    tau -= majorant * dt;
+                    mip = fminf(mip + 0.25f, 3.f);
+                    if (!(tau > 0.f)) {
+                        t += MT::div(tau, majorant);
+                        if (!(t >= tfar)) { stage = SG_COLLIDE; second = true; }   // `if (t >= far) break;` (a NaN t goes on to the lookup)
+                    }
+                    if (++steps > MAX_RAY_STEPS) { t = INFINITY; stage = SG_STEP; }
+                }
+            }
+            if (stage == SG_STEP && !(t < tfar)) {   // the ray left the volume
+                if (shadow) {
+                    if (Tr != 0.f) L = L + pend * Tr;     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
+                    stage = SG_SCATTER;
+                } else {
+                    escaped = true;
+                    stage = SG_FINISH;
+                }
+            }
+        }
+#else
 #pragma unroll
         for (int rep = 0; rep < VR_STEPS_PER_PASS; ++rep) {
         // a further step only while enough lanes still step (one vote instead of the full scheduler)
@@ -207,6 +259,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         }
 
         }
+#endif
 
         // ================= scheduler =================
         const unsigned m_step = __ballot_sync(FULL, stage == SG_STEP);
