@@ -122,6 +122,14 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #define VR_STEPS_PER_PASS 3       // DDA steps per scheduler pass: the five ballots + queue logic are 7 % of the issued instructions at 32 lanes;
                                   // B200 (TF / non-TF Gsamples/s): 1 -> 37.0 / 4.01, 2 -> 39.0 / 4.19, 3 -> 38.8 / 4.26, 4 -> 38.2 / 4.16, 6 -> 36.6 / 3.88
 #endif
+#ifndef VR_LBUF_STREAM
+#define VR_LBUF_STREAM 1          // sample-buffer stores are streaming (evict-first): written once, read once by k_fold
+#endif
+#if VR_LBUF_STREAM
+#define VR_LBUF_STORE(ptr, v) __stcs(ptr, v)
+#else
+#define VR_LBUF_STORE(ptr, v) (*(ptr) = (v))
+#endif
 #ifndef VR_STEP_PREFETCH
 #define VR_STEP_PREFETCH 0        // 1: fetch the majorants of all steps of a pass before consuming the first (bit-identical;
                                   // measured: TF 41.0 -> 41.2, non-TF 4.37 -> 4.06 Gsamples/s: the discarded geometry costs more than the
@@ -451,8 +459,8 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                     L = L + thr * mis_weight * Le;
                 }
                 cnt.samp();                                     // pathtracer_brick.glsl:36: sanitize(L), folded by k_fold
-                a.lbuf[size_t(sj) * a.lbuf_stride + size_t(py) * W + px] =
-                    make_float4(sanitize(L.x), sanitize(L.y), sanitize(L.z), sanitize(fminf(float(n_paths), 1.f)));
+                VR_LBUF_STORE(a.lbuf + size_t(sj) * a.lbuf_stride + size_t(py) * W + px,
+                              make_float4(sanitize(L.x), sanitize(L.y), sanitize(L.z), sanitize(fminf(float(n_paths), 1.f))));
                 have_item = false;
                 if (a.tile_cost && ((px ^ py ^ sj) & 3) == 0) {   // a dithered quarter of the samples is enough to rank tiles
                     unsigned now;

@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_DUO_MIN_BLOCKS) k_trace_duo
                 cnt.samp();                                     // pathtracer_brick.glsl:36: sanitize(L), folded by k_fold
                 const uint32_t pix = COLDU(C_PIX, slot);
                 const int px = int(pix & 0xffffu), py = int(pix >> 16), sj = int(COLDU(C_SJ, slot));
-                a.lbuf[size_t(sj) * a.lbuf_stride + size_t(py) * W + px] =
-                    make_float4(sanitize(L.x), sanitize(L.y), sanitize(L.z), sanitize(fminf(float(n_paths), 1.f)));
+                VR_LBUF_STORE(a.lbuf + size_t(sj) * a.lbuf_stride + size_t(py) * W + px,
+                              make_float4(sanitize(L.x), sanitize(L.y), sanitize(L.z), sanitize(fminf(float(n_paths), 1.f))));
                 SETU(C_FLAGS, slot, 0u);
                 if (a.tile_cost && ((px ^ py ^ sj) & 3) == 0) {   // a dithered quarter of the samples is enough to rank tiles
                     unsigned now;
