@@ -18,6 +18,9 @@ namespace vr {
 #ifndef VR_DUO_MIN_BLOCKS
 #define VR_DUO_MIN_BLOCKS 6      // 80 registers: B200 sweep, 4 / 5 / 6 CTAs per SM = 31.3 / 34.5 / 35.8 Gsamples/s (TF)
 #endif
+#ifndef VR_DUO_SELECT
+#define VR_DUO_SELECT 0          // 1: one step instance per repeat on a selected ray instead of one instance per ray
+#endif
 #ifndef VR_DUO_STEPS
 #define VR_DUO_STEPS 1           // DDA steps of each ray per scheduler pass
 #endif
@@ -120,13 +123,31 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_DUO_MIN_BLOCKS) k_trace_duo
         }
     };
 
+    unsigned iter = 0;
     while (true) {
         // ================= STEP: both rays (independent chains: the two majorant fetches overlap) =================
+#if VR_DUO_SELECT
+        // ONE step instance per repeat: the lane picks whichever of its rays can step (alternating when both can), so the
+        // instance runs with every lane that has a stepping ray instead of two instances with half the lanes each
+#pragma unroll
+        for (int rep = 0; rep < VR_DUO_STEPS; ++rep) {
+            const bool s0 = h0.stage == SG_STEP, s1 = h1.stage == SG_STEP;
+            if (s0 | s1) {
+                const bool pick1 = s1 && (!s0 || (((iter + rep) & 1u) != 0u));
+                HotRay c = pick1 ? h1 : h0;
+                step(c, (pick1 ? VR_TRACE_BLOCK : 0) + threadIdx.x);
+                if (pick1) { h1.t = c.t; h1.tau = c.tau; h1.mip = c.mip; h1.maj = c.maj; h1.stage = c.stage; }
+                else { h0.t = c.t; h0.tau = c.tau; h0.mip = c.mip; h0.maj = c.maj; h0.stage = c.stage; }
+            }
+        }
+        ++iter;
+#else
 #pragma unroll
         for (int rep = 0; rep < VR_DUO_STEPS; ++rep) {
             step(h0, threadIdx.x);
             step(h1, VR_TRACE_BLOCK + threadIdx.x);
         }
+#endif
 
         // ================= scheduler: lanes that hold a ray in each stage =================
         const unsigned m_step = __ballot_sync(FULL, h0.stage == SG_STEP || h1.stage == SG_STEP);
