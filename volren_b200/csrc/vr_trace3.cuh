@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_DUO_MIN_BLOCKS) k_trace_duo
         }
     };
 
-    unsigned iter = 0;
+    [[maybe_unused]] unsigned iter = 0;
     while (true) {
         // ================= STEP: both rays (independent chains: the two majorant fetches overlap) =================
 #if VR_DUO_SELECT
