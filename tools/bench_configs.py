@@ -31,6 +31,7 @@ from volren_b200 import formats, scene  # noqa: E402
 from helpers import readme_scene  # noqa: E402
 
 A = os.path.join(ROOT, "tests", "golden", "assets")
+RANK, WORLD = 0, 1
 
 
 def fbm_cloud(n, seed=42, octaves=5, base=4, threshold=0.30):
@@ -114,8 +115,13 @@ def run_c5(ctx, frames, clean_spp, n=256, W=1024, H=1024):
     build_ms = []
     import time
     torch.cuda.synchronize()
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.barrier()
     t0 = time.perf_counter()
     for i, q in enumerate(plist):
+        if i % WORLD != RANK:
+            continue
         build_ms.append(timed(lambda: ctx.grid_build_from_dense_device(vols[i].data_ptr(), (n, n, n), 0.0, 1.0)))
         s = scene.RenderSettings(bounces=q["max_bounces"], albedo=q["vol_albedo"], phase=q["vol_phase"], env_strength=q["env_strength"],
                                  show_environment=q["env_show"], use_transferfunc=False)
@@ -137,11 +143,21 @@ def run_c5(ctx, frames, clean_spp, n=256, W=1024, H=1024):
             samples += W * H * spp
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    part = "single GPU (tile partition: volren_b200.multigpu, tests/test_multigpu_gloo.py)"
+    if WORLD > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dt, float(samples)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt, samples = float(tmax[0]), int(t[1])
+        part = f"{WORLD} GPUs, frames dealt round-robin (every frame is an independent job: own volume, own parameters), max wall time over ranks"
+        if RANK != 0:
+            return
     print(json.dumps(dict(config=f"C5 {frames} animated {n}^3 fBm frames, datagen_denoise-style pairs (noisy 1..33 spp, clean {clean_spp} spp; named: 64 frames, 4096 spp)",
                           resolution=[W, H], frames=frames, clean_spp=clean_spp, wall_s=dt, frames_per_s=frames / dt, samples=samples,
                           samples_per_s=samples / dt, brick_build_ms_median=float(np.median(build_ms)), output="fp16 (N,3,H,W) noisy + clean",
                           finite=bool(np.isfinite(inputs.astype(np.float32)).all() and np.isfinite(targets.astype(np.float32)).all()),
-                          mean_clean=float(targets.astype(np.float32).mean()), partition="single GPU (tile partition: volren_b200.multigpu, tests/test_multigpu_gloo.py)")), flush=True)
+                          mean_clean=float(targets.astype(np.float32).mean()), n_gpus=WORLD, partition=part)), flush=True)
 
 
 def ct_phantom(w, h, d, seed=42):
@@ -221,7 +237,16 @@ def main():
     ap.add_argument("--frames", type=int, default=8, help="C5: number of animation frames (named config: 64)")
     ap.add_argument("--clean-spp", type=int, default=256, help="C5: samples of the clean image (named config: 4096)")
     a = ap.parse_args()
-    ctx = vr.Context(0)
+    # under torchrun (C5 only): one process per GPU, the animation frames are dealt round-robin to the ranks
+    global RANK, WORLD
+    RANK, WORLD = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        assert a.configs == "C5", "multi-rank runs are for C5 (frame-parallel); bench.py covers the spp-sliced scaling"
+    ctx = vr.Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     env = formats.load_hdr(os.path.join(A, "table_mountain_2_puresky_1k.hdr"))
     ctx.env_upload(env)
