@@ -146,6 +146,9 @@ VR_DEV float brick_majorant(const GridView& g, float3 ipos, int mip) {
 // FastMath tests `r * sum < w` instead of `r < w / max(1e-3, sum)` (no division; the running sums of the B-spline weights
 // are w0 + w1 in [1/6, 5/6], 1 - w3 >= 5/6 and 1, so the max() never acts) and evaluates the weights in Horner form with
 // the 1/6 folded into the coefficients (21 instead of 34 instructions per axis).
+#ifndef VR_DECODED_TAP
+#define VR_DECODED_TAP 0    // 1: the non-TF kernel's single tricubic tap reads the decoded blocks too
+#endif
 #ifndef VR_ENV_SPLIT
 #define VR_ENV_SPLIT 1      // sample_environment reads the precomputed split tables (k_env_split)
 #endif
@@ -266,6 +269,15 @@ VR_DEV float density_trilinear_decoded(const GridView& g, float3 ipos) {
     const float v000 = __ldg(b), v100 = __ldg(b + 1), v010 = __ldg(b + 9), v110 = __ldg(b + 10);
     const float v001 = __ldg(b + 81), v101 = __ldg(b + 82), v011 = __ldg(b + 90), v111 = __ldg(b + 91);
     return mixf(mixf(mixf(v000, v100, fx), mixf(v010, v110, fx), fy), mixf(mixf(v001, v101, fx), mixf(v011, v111, fx), fy), fz);
+}
+
+// One decoded voxel: the value brick_value() returns, from the block of the brick that contains it (1 slot load + 1 fp32
+// load instead of record load + range decode + byte load + unorm conversion).
+VR_DEV float decoded_value(const GridView& g, int x, int y, int z) {
+    const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+    if (unsigned(bx) >= g.nb.x || unsigned(by) >= g.nb.y || unsigned(bz) >= g.nb.z) return 0.f;
+    const uint32_t cell = (uint32_t(bz + 1) * (g.nb.y + 1u) + uint32_t(by + 1)) * (g.nb.x + 1u) + uint32_t(bx + 1);
+    return __ldg(g.datlas + size_t(__ldg(g.cslot + cell)) * DBRICK + uint32_t((z & 7) * 81 + (y & 7) * 9 + (x & 7)));
 }
 
 // ---- building the decoded apron bricks -----------------------------------------------------------------

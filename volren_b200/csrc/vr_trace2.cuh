@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 tf_rgb = f3(rgba.x, rgba.y, rgba.z);
             } else {
                 const int3 tap = stochastic_tricubic_filter<MT>(at, seed);
-                d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
+                d = a.p.vol_density_scale * ((MT::decoded && VR_DECODED_TAP) ? decoded_value(a.density, tap.x, tap.y, tap.z) : brick_value(a.density, tap.x, tap.y, tap.z));
             }
             bool parked = false;
             if (!shadow) {
