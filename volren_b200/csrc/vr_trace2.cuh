@@ -62,7 +62,9 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #define VR_TRACE_BLOCK 128
 #endif
 #ifndef VR_TRACE_MIN_BLOCKS
-#define VR_TRACE_MIN_BLOCKS 6
+#define VR_TRACE_MIN_BLOCKS 7     // CTAs per SM: 7 -> 72 registers without spills (28 warps/SM). B200, TF / non-TF Gsamples/s:
+                                  // 6 (80 regs) 40.8 / 4.36, 7 (72) 44.1 / 4.41, 8 (64, spills) 41.9 / 4.32,
+                                  // 8 with VR_COLD_SMEM (64, no spills) 44.0 / 4.47 (profiles/r01_v10_duo_and_steps_sweeps.txt)
 #endif
 // Queue thresholds, tuned on B200 (tools/sweep.py, profiles/r01_sweep*.txt): a queue's stage runs once this many lanes
 // wait in it. The TF variant has cheap events and an expensive 8-tap collision; the non-TF variant a cheap 1-tap
@@ -122,6 +124,9 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #define VR_STEPS_PER_PASS 3       // DDA steps per scheduler pass: the five ballots + queue logic are 7 % of the issued instructions at 32 lanes;
                                   // B200 (TF / non-TF Gsamples/s): 1 -> 37.0 / 4.01, 2 -> 39.0 / 4.19, 3 -> 38.8 / 4.26, 4 -> 38.2 / 4.16, 6 -> 36.6 / 3.88
 #endif
+#ifndef VR_COLD_SMEM
+#define VR_COLD_SMEM 0            // 1: radiance + pending NEE term of the lane's path live in shared memory
+#endif
 #ifndef VR_LBUF_STREAM
 #define VR_LBUF_STREAM 1          // sample-buffer stores are streaming (evict-first): written once, read once by k_fold
 #endif
@@ -155,7 +160,23 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
     int px = 0, py = 0, sj = 0, steps = 0;   // the lane's sample: pixel and sample index relative to first_sample
     unsigned t_item = 0;           // clock at which this lane took its sample
     uint32_t seed = 0, n_paths = 0;
-    float3 pos = f3(0.f), dir = f3(0.f, 0.f, -1.f), thr = f3(1.f), L = f3(0.f), pend = f3(0.f);
+    float3 pos = f3(0.f), dir = f3(0.f, 0.f, -1.f), thr = f3(1.f);
+    // radiance so far and the pending NEE term are touched by the rare events only (NEE, end of a shadow ray, emission,
+    // finish): with VR_COLD_SMEM they live in shared memory (one conflict-free column per thread) instead of 6 registers
+#if VR_COLD_SMEM
+    __shared__ float s_cold[6][VR_TRACE_BLOCK];
+#define LGET() f3(s_cold[0][threadIdx.x], s_cold[1][threadIdx.x], s_cold[2][threadIdx.x])
+#define LSET(v) do { const float3 v_ = (v); s_cold[0][threadIdx.x] = v_.x; s_cold[1][threadIdx.x] = v_.y; s_cold[2][threadIdx.x] = v_.z; } while (0)
+#define PGET() f3(s_cold[3][threadIdx.x], s_cold[4][threadIdx.x], s_cold[5][threadIdx.x])
+#define PSET(v) do { const float3 v_ = (v); s_cold[3][threadIdx.x] = v_.x; s_cold[4][threadIdx.x] = v_.y; s_cold[5][threadIdx.x] = v_.z; } while (0)
+    LSET(f3(0.f)); PSET(f3(0.f));
+#else
+    float3 L = f3(0.f), pend = f3(0.f);
+#define LGET() L
+#define LSET(v) L = (v)
+#define PGET() pend
+#define PSET(v) pend = (v)
+#endif
     float3 ipos = f3(0.f), idir = f3(1.f), ri = f3(1.f);
     float t = 0.f, tfar = -1.f, tau = 0.f, mip = 3.f, f_p = 0.f, Tr = 1.f, majorant = 0.f;
     // outstanding (speculated-null) tentative collision of this lane
@@ -221,7 +242,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
             }
             if (stage == SG_STEP && !(t < tfar)) {   // the ray left the volume
                 if (shadow) {
-                    if (Tr != 0.f) L = L + pend * Tr;     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
+                    if (Tr != 0.f) LSET(LGET() + PGET() * Tr);     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
                     stage = SG_SCATTER;
                 } else {
                     escaped = true;
@@ -257,7 +278,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 if (SPEC && pending) {                // ... if the outstanding collision turns out null: wait for it
                     stage = SG_COLLIDE; second = false;
                 } else if (shadow) {
-                    if (Tr != 0.f) L = L + pend * Tr;     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
+                    if (Tr != 0.f) LSET(LGET() + PGET() * Tr);     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
                     stage = SG_SCATTER;
                 } else {
                     escaped = true;
@@ -317,7 +338,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                     if (fetched) {
                         cnt.emis();
                         const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-                        L = L + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant;
+                        LSET(LGET() + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant);
                     }
                     if (rng(sd) * maj_c < d) {               // real collision: the segment ends here (common.glsl:490-496)
                         thr = thr * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
@@ -371,7 +392,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 if (fetched) {
                     cnt.emis();
                     const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-                    L = L + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant;
+                    LSET(LGET() + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant);
                 }
                 if (rng(seed) * majorant < d) {          // real collision: the segment ends here (common.glsl:490-496)
                     thr = thr * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
@@ -411,7 +432,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 const float mis_weight = a.p.show_environment > 0 ? MT::div(sqr(Le_pdf.w), sqr(Le_pdf.w) + sqr(f_p)) : 1.f;
                 // L += throughput * mis_weight * f_p * Tr * Le / pdf, with Tr applied when the shadow ray is done
                 const float3 c = thr * mis_weight * f_p * f3(Le_pdf.x, Le_pdf.y, Le_pdf.z);
-                pend = f3(MT::div(c.x, Le_pdf.w), MT::div(c.y, Le_pdf.w), MT::div(c.z, Le_pdf.w));
+                PSET(f3(MT::div(c.x, Le_pdf.w), MT::div(c.y, Le_pdf.w), MT::div(c.z, Le_pdf.w)));
                 Tr = 1.f;
                 shadow = true;
                 rd = w_i; start = true;
@@ -451,16 +472,17 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         if (run_fin) {     // warp-uniform: the block switch below is a warp-wide cooperative step
             const bool mine = stage == SG_FINISH;
             if (mine && have_item) {
+                float3 Lf = LGET();
                 if (escaped && a.p.show_environment > 0) {      // common.glsl:644-649
                     cnt.env();
                     const float3 Le = lookup_environment(a, dir);
                     const float pe = pdf_environment<MT>(a, Le);
                     const float mis_weight = n_paths > 0 ? MT::div(sqr(f_p), sqr(f_p) + sqr(pe)) : 1.f;
-                    L = L + thr * mis_weight * Le;
+                    Lf = Lf + thr * mis_weight * Le;
                 }
                 cnt.samp();                                     // pathtracer_brick.glsl:36: sanitize(L), folded by k_fold
                 VR_LBUF_STORE(a.lbuf + size_t(sj) * a.lbuf_stride + size_t(py) * W + px,
-                              make_float4(sanitize(L.x), sanitize(L.y), sanitize(L.z), sanitize(fminf(float(n_paths), 1.f))));
+                              make_float4(sanitize(Lf.x), sanitize(Lf.y), sanitize(Lf.z), sanitize(fminf(float(n_paths), 1.f))));
                 have_item = false;
                 if (a.tile_cost && ((px ^ py ^ sj) & 3) == 0) {   // a dithered quarter of the samples is enough to rank tiles
                     unsigned now;
@@ -522,7 +544,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
             if (mine && have_item) {
                 asm volatile("mov.u32 %0, %%clock;" : "=r"(t_item));
                 pos = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
-                thr = f3(1.f); L = f3(0.f); n_paths = 0; f_p = 0.f;
+                thr = f3(1.f); LSET(f3(0.f)); n_paths = 0; f_p = 0.f;
                 shadow = false; escaped = false;
                 rd = dir; start = true;
                 stage = SG_STEP;
@@ -548,6 +570,10 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         }
     }
     flush_counters(a, cnt);
+#undef LGET
+#undef LSET
+#undef PGET
+#undef PSET
 }
 
 // Folds the samples of one launch into the colour buffer in sample order (pathtracer_brick.glsl:36):
