@@ -302,6 +302,8 @@ class VoldataRef:
         L.ref_brick_from_grid.restype = C.c_void_p
         L.ref_brick_from_grid.argtypes = [C.c_void_p]
         L.ref_grid_free.argtypes = [C.c_void_p]
+        L.ref_brick_from_values.restype = C.c_void_p
+        L.ref_brick_from_values.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_uint32 * 3]
 
     def to_half(self, f):
         return int(self.lib.ref_to_half(float(f)))
@@ -351,6 +353,17 @@ class VoldataRef:
         self.lib.ref_grid_free(g)
         return dict(extent=tuple(ext), ibb_min=tuple(ibb), min_maj=(float(mm[0]), float(mm[1])),
                     transform=np.array(list(tr), np.float32).reshape(4, 4), n_bricks=nb, padded=padded, brick=brick)
+
+    def brick_build_values(self, padded_values, extent_whd, n_bricks):
+        """The unmodified BrickGrid(const Grid&) on a table-backed Grid (lookup() values on the padded lattice, [z][y][x])."""
+        val = np.ascontiguousarray(padded_values, np.float32)
+        assert val.shape == (n_bricks[2] * 8 + 4, n_bricks[1] * 8 + 4, n_bricks[0] * 8 + 4)
+        b = self.lib.ref_brick_from_values(_ptr(val), (C.c_uint32 * 3)(*extent_whd), (C.c_uint32 * 3)(*n_bricks))
+        if not b:
+            return None
+        out = self._brick_to_data(b)
+        self.lib.ref_brick_free(b)
+        return out
 
     def _brick_to_data(self, b) -> BrickGridData:
         nb = (C.c_uint32 * 3)()

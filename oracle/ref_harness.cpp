@@ -173,6 +173,23 @@ void ref_grid_lookup_padded(void* g, const uint32_t nb[3], float* out) {
     for (int z = -2; z < int(nb[2] * 8) + 2; ++z) for (int y = -2; y < int(nb[1] * 8) + 2; ++y) for (int x = -2; x < int(nb[0] * 8) + 2; ++x)
         out[i++] = gr->lookup(glm::uvec3(glm::ivec3(x, y, z)));
 }
+// A Grid whose lookup() reads a table on the padded lattice [-2, 8 nb + 2)^3 (x fastest, origin (-2, -2, -2)): lets the
+// UNMODIFIED BrickGrid(const Grid&) run on arbitrary float values (negative, -0, denormal, > fp16 range, NaN).
+struct TableGrid : public Grid {
+    const float* val; uint32_t px, py; glm::uvec3 extent;
+    float lookup(const glm::uvec3& ipos) const override {
+        return val[(size_t(int32_t(ipos.z) + 2) * py + size_t(int32_t(ipos.y) + 2)) * px + size_t(int32_t(ipos.x) + 2)];
+    }
+    std::pair<float, float> minorant_majorant() const override { return { 0.f, 0.f }; }
+    glm::uvec3 index_extent() const override { return extent; }
+    size_t num_voxels() const override { return size_t(extent.x) * extent.y * extent.z; }
+    size_t size_bytes() const override { return 0; }
+};
+void* ref_brick_from_values(const float* padded, const uint32_t extent[3], const uint32_t nb[3]) {
+    TableGrid t;
+    t.val = padded; t.px = nb[0] * 8 + 4; t.py = nb[1] * 8 + 4; t.extent = glm::uvec3(extent[0], extent[1], extent[2]);
+    try { return new BrickGrid(t); } catch (std::runtime_error&) { return nullptr; }
+}
 void* ref_brick_from_grid(void* g) {
     try { return new BrickGrid(*(Grid*)g); } catch (std::runtime_error&) { return nullptr; }
 }

@@ -219,16 +219,7 @@ def test_gpu_build_from_nvdb_matches_reference(ctx, nvdb_golden, name):
 def test_gpu_build_from_values_matches_oracle(ctx, oracle, extent):
     """Arbitrary float lattices: negative values, +-0 ties, constant bricks, huge and denormal ranges, values outside the
     extent (the constructor reads the whole brick lattice), NaN-free."""
-    import volren_b200 as vr
-    rng = np.random.default_rng(sum(extent))
-    nb, pd = vr._capi.brick_lattice(extent)
-    val = rng.standard_normal((pd[2], pd[1], pd[0])).astype(np.float32)
-    val[rng.random(val.shape) < 0.5] = 0.0
-    val[rng.random(val.shape) < 0.05] = -0.0
-    val[:, :, pd[0] // 2:] *= 1e-6
-    val[: pd[2] // 3] = np.float32(0.75)                        # constant region -> empty bricks
-    val[-5:, -5:, -5:] = np.float32(7e4)                        # above the fp16 range -> inf majorant
-    val[2:6, 2:6, 2:6] = np.float32(1e-41)                      # denormal
+    nb, val = _value_lattice(extent)                             # pinned against the reference in the CPU test of the same lattices
     ctx.grid_clear()
     ctx.grid_build_from_values(val, extent)
     got, want = ctx.grid_download(), oracle.brick_build_values(val, extent)
@@ -327,3 +318,38 @@ def test_gpu_nvdb_volume_renders_like_the_oracle(ctx, oracle, nvdb_golden, env_r
     ok = ~m
     assert ok.mean() > 0.8
     assert rmse(img[ok][:, :3], ref_a[ok][:, :3]) < rmse(ref_a[ok][:, :3], ref_b[ok][:, :3])
+
+
+def _value_lattice(extent, nan=False):
+    """The float lattices of test_gpu_build_from_values_matches_oracle (same seeds), optionally with NaN / inf voxels."""
+    import volren_b200 as vr
+    rng = np.random.default_rng(sum(extent))
+    nb, pd = vr._capi.brick_lattice(extent)
+    val = rng.standard_normal((pd[2], pd[1], pd[0])).astype(np.float32)
+    val[rng.random(val.shape) < 0.5] = 0.0
+    val[rng.random(val.shape) < 0.05] = -0.0
+    val[:, :, pd[0] // 2:] *= 1e-6
+    val[: pd[2] // 3] = np.float32(0.75)
+    val[-5:, -5:, -5:] = np.float32(7e4)
+    val[2:6, 2:6, 2:6] = np.float32(1e-41)
+    if nan:
+        val[rng.random(val.shape) < 0.01] = np.nan
+        val[rng.random(val.shape) < 0.002] = np.inf
+    return nb, val
+
+
+@pytest.mark.parametrize("extent,nan", [((1, 1, 1), False), ((9, 8, 8), False), ((30, 17, 41), False), ((64, 64, 64), False),
+                                        ((70, 33, 20), True), ((70, 33, 20), False)])
+def test_oracle_any_grid_build_equals_the_reference_on_arbitrary_floats(oracle, voldata_ref, extent, nan):
+    """vro_brick_build_values against the UNMODIFIED BrickGrid(const Grid&) run on a table-backed Grid subclass
+    (oracle/ref_harness.cpp TableGrid): negative values (encode_range's sign extension), +-0 ties, denormals, values beyond
+    the fp16 range, NaN and inf voxels (std::min / std::max order). These are the lattices the GPU test feeds the device
+    builder, so GPU == oracle (test_gpu_build_from_values_matches_oracle) and oracle == reference (here) close the chain."""
+    nb, val = _value_lattice(extent, nan)
+    got = oracle.brick_build_values(val, extent)
+    want = voldata_ref.brick_build_values(val, extent, nb)
+    assert want is not None and got.brick_count == want.brick_count and got.atlas_dim == want.atlas_dim
+    assert np.array_equal(got.range, want.range) and np.array_equal(got.indirection, want.indirection)
+    assert np.array_equal(got.atlas, want.atlas)
+    for i in range(3):
+        assert np.array_equal(got.mips[i], want.mips[i])
