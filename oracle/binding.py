@@ -294,6 +294,8 @@ class VoldataRef:
         L.ref_nvdb_build.restype = C.c_void_p
         L.ref_nvdb_build.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_float, C.c_double, C.c_double * 3]
         L.ref_nvdb_write.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p]
+        L.ref_nvdb_fog_sphere.restype = C.c_void_p
+        L.ref_nvdb_fog_sphere.argtypes = [C.c_double, C.c_double * 3, C.c_double, C.c_double, C.c_char_p]
         L.ref_nvdb_load.restype = C.c_void_p
         L.ref_nvdb_load.argtypes = [C.c_char_p, C.c_char_p]
         L.ref_nvdb_ibb_min.argtypes = [C.c_void_p, C.c_int32 * 3]
@@ -333,6 +335,11 @@ class VoldataRef:
             values = np.ascontiguousarray(values, np.float32)
             handles[i] = self.lib.ref_nvdb_build(_ptr(ijk), _ptr(values), len(values), name.encode(), background, voxel_size, (C.c_double * 3)(*origin))
         assert self.lib.ref_nvdb_write(handles, len(grids), path.encode()) == 0
+
+    def nvdb_write_fog_sphere(self, path, radius, center, voxel_size=1.0, half_width=3.0, name="density"):
+        """nanovdb::tools::createFogVolumeSphere -> one-grid .nvdb file (interior stored as active constant tiles)."""
+        h = (C.c_void_p * 1)(self.lib.ref_nvdb_fog_sphere(radius, (C.c_double * 3)(*center), voxel_size, half_width, name.encode()))
+        assert self.lib.ref_nvdb_write(h, 1, path.encode()) == 0
 
     def nvdb_load(self, path, gridname="density"):
         """voldata::NanoVDBGrid(path, gridname) -> dict with extent, ibb_min, min_maj, transform (rows = glm columns),

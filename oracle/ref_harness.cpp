@@ -24,6 +24,7 @@
 #include <nanovdb/io/IO.h>
 #include <nanovdb/tools/GridBuilder.h>
 #include <nanovdb/tools/CreateNanoGrid.h>
+#include <nanovdb/tools/CreatePrimitives.h>
 
 #include <cereal/types/utility.hpp>
 #include <cereal/types/atomic.hpp>
@@ -139,6 +140,13 @@ void* ref_nvdb_build(const int32_t* ijk, const float* values, size_t n, const ch
     auto acc = builder.getAccessor();
     for (size_t i = 0; i < n; ++i) acc.setValue(nanovdb::Coord(ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]), values[i]);
     auto* h = new nanovdb::GridHandle<nanovdb::HostBuffer>(nanovdb::tools::createNanoGrid(builder));
+    return h;
+}
+// NanoVDB's own fog-volume sphere (tools/CreatePrimitives.h): narrow-band ramp at the surface, the interior as ACTIVE
+// CONSTANT TILES of the internal nodes -- exercises the tile branches of the accessor with a grid the library built itself
+void* ref_nvdb_fog_sphere(double radius, const double center[3], double voxel_size, double half_width, const char* name) {
+    auto* h = new nanovdb::GridHandle<nanovdb::HostBuffer>(nanovdb::tools::createFogVolumeSphere<float>(
+        radius, nanovdb::Vec3d(center[0], center[1], center[2]), voxel_size, half_width, nanovdb::Vec3d(0.0), name));
     return h;
 }
 // writes the handles as consecutive file segments (io::writeGrids, uncompressed)

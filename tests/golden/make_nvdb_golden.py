@@ -64,6 +64,30 @@ def main():
             print(name, "extent", g["extent"], "ibb_min", g["ibb_min"], "min_maj", g["min_maj"], "bricks", b.n_bricks, b.brick_count,
                   "active", len(d_val if name == "density" else t_val))
         assert ref.nvdb_load(path, "nope") is None          # unknown grid name throws in the reference
+        # NanoVDB's own fog-volume sphere: the interior is stored as ACTIVE CONSTANT TILES of the lower internal nodes
+        spath = os.path.join(tmp, "sphere.nvdb")
+        ref.nvdb_write_fog_sphere(spath, 22.0, (3.0, -5.0, 60.0), voxel_size=1.0, half_width=3.0, name="density")
+        out["sphere_file"] = np.fromfile(spath, np.uint8)
+        g = ref.nvdb_load(spath, "density")
+        b = g["brick"]
+        name = "sphere"
+        out[name + ".extent"] = np.array(g["extent"], np.uint32)
+        out[name + ".ibb_min"] = np.array(g["ibb_min"], np.int32)
+        out[name + ".min_maj"] = np.array(g["min_maj"], np.float32)
+        out[name + ".transform"] = g["transform"]
+        out[name + ".padded"] = g["padded"]
+        out[name + ".n_bricks"] = np.array(b.n_bricks, np.uint32)
+        out[name + ".atlas_dim"] = np.array(b.atlas_dim, np.uint32)
+        out[name + ".brick_count"] = np.array([b.brick_count], np.uint64)
+        out[name + ".indirection"] = b.indirection
+        out[name + ".range"] = b.range
+        out[name + ".atlas"] = b.atlas
+        for i in range(3):
+            out[name + f".mip{i}"] = b.mips[i]
+        import struct
+        tiles = struct.unpack_from("<3I", out["sphere_file"].tobytes(), 16 + 176 + 8 + 672 + 44)
+        print("sphere extent", g["extent"], "ibb_min", g["ibb_min"], "min_maj", g["min_maj"], "bricks", b.n_bricks, b.brick_count, "active tiles (lower, upper, root)", tiles)
+        assert tiles[0] > 0
     np.savez_compressed(os.path.join(HERE, "nvdb_golden.npz"), **out)
     print("file bytes", raw.size, "npz bytes", os.path.getsize(os.path.join(HERE, "nvdb_golden.npz")))
 

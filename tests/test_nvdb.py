@@ -14,6 +14,13 @@ import pytest
 from conftest import GOLDEN
 
 NAMES = ("density", "temperature")
+# + NanoVDB's own fog-volume sphere (tools/CreatePrimitives.h): interior stored as active constant tiles of the lower nodes
+NAMES_ALL = NAMES + ("sphere",)
+
+
+def _source(g, name):
+    """(file bytes, grid name inside the file) of a golden entry."""
+    return (g["sphere_file"], "density") if name == "sphere" else (g["nvdb_file"], name)
 
 
 @pytest.fixture(scope="module")
@@ -51,10 +58,11 @@ def _golden_brick_equals(g, name, got):
 
 # ---- CPU: oracle pins ----------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("name", NAMES_ALL)
 def test_oracle_nvdb_restatement_matches_reference(nvdb_golden, name):
     from oracle.nvdb_np import Grid
-    g = Grid(nvdb_golden["nvdb_file"].tobytes(), name)
+    data, gridname = _source(nvdb_golden, name)
+    g = Grid(data.tobytes(), gridname)
     d = g.derived()
     assert d["extent"] == tuple(nvdb_golden[name + ".extent"]) and d["ibb_min"] == tuple(nvdb_golden[name + ".ibb_min"])
     assert np.array_equal(_bits(d["min_maj"]), _bits(nvdb_golden[name + ".min_maj"]))
@@ -62,7 +70,7 @@ def test_oracle_nvdb_restatement_matches_reference(nvdb_golden, name):
     assert np.array_equal(_bits(g.padded_lattice(tuple(nvdb_golden[name + ".n_bricks"]))), _bits(nvdb_golden[name + ".padded"]))
 
 
-@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("name", NAMES_ALL)
 def test_oracle_any_grid_brick_build_matches_reference(oracle, nvdb_golden, name):
     """vro_brick_build_values == the reference's BrickGrid(NanoVDBGrid), incl. the sign of a -0 minimum (first-seen std::min)."""
     got = oracle.brick_build_values(nvdb_golden[name + ".padded"], tuple(int(v) for v in nvdb_golden[name + ".extent"]))
@@ -79,21 +87,31 @@ def test_fixture_regenerates_from_the_reference(voldata_ref, nvdb_golden, tmp_pa
         assert np.array_equal(_bits(g["padded"]), _bits(nvdb_golden[name + ".padded"]))
         assert np.array_equal(g["brick"].atlas, nvdb_golden[name + ".atlas"])
     assert voldata_ref.nvdb_load(str(p), "nope") is None
+    p2 = tmp_path / "sphere.nvdb"
+    p2.write_bytes(nvdb_golden["sphere_file"].tobytes())
+    g = voldata_ref.nvdb_load(str(p2), "density")
+    assert np.array_equal(_bits(g["padded"]), _bits(nvdb_golden["sphere.padded"])) and np.array_equal(g["brick"].atlas, nvdb_golden["sphere.atlas"])
 
 
 # ---- CPU: the product's host-side reader and accessor ------------------------------------------------------------------
 
-@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("name", NAMES_ALL)
 def test_reader_matches_reference(nvdb_golden, name):
     import volren_b200 as vr
-    n = vr.NanoVDBGridData(nvdb_golden["nvdb_file"], name)
+    n = vr.NanoVDBGridData(*_source(nvdb_golden, name))
     assert n.extent == tuple(nvdb_golden[name + ".extent"]) and n.ibb_min == tuple(nvdb_golden[name + ".ibb_min"])
     assert np.array_equal(_bits(n.min_maj), _bits(nvdb_golden[name + ".min_maj"]))
     assert np.array_equal(_bits(n.transform), _bits(nvdb_golden[name + ".transform"]))
     assert np.array_equal(_bits(n.padded_lattice()), _bits(nvdb_golden[name + ".padded"]))
-    assert n.num_voxels == {"density": 43018, "temperature": 5050}[name]           # active voxels written by make_nvdb_golden.py
-    # far outside every root tile -> background
-    assert n.lookup([[1 << 20, 5, 5], [5, 1 << 22, 5]]).tolist() == [0.0, 0.0]
+    if name == "sphere":
+        import struct
+        tiles = struct.unpack_from("<3I", n.grid.tobytes(), 672 + 44)[0]
+        assert tiles > 0 and (nvdb_golden["sphere.padded"] == 1.0).sum() >= 512 * tiles        # the interior tiles are inside the lattice
+    else:
+        assert n.num_voxels == {"density": 43018, "temperature": 5050}[name]       # active voxels written by make_nvdb_golden.py
+    # far outside every root tile -> the root's background (the fog sphere keeps the level set's 3.0 there)
+    bg = 3.0 if name == "sphere" else 0.0
+    assert n.lookup([[1 << 20, 5, 5], [5, 1 << 22, 5]]).tolist() == [bg, bg]
 
 
 def test_reader_raw_buffer_files_tiles_and_background(nvdb_golden):
@@ -353,3 +371,15 @@ def test_oracle_any_grid_build_equals_the_reference_on_arbitrary_floats(oracle, 
     assert np.array_equal(got.atlas, want.atlas)
     for i in range(3):
         assert np.array_equal(got.mips[i], want.mips[i])
+
+
+@pytest.mark.gpu
+def test_gpu_build_from_nvdb_with_interior_tiles(ctx, nvdb_golden):
+    """NanoVDB's own fog-volume sphere: the device accessor takes the constant-tile branch of the lower internal nodes;
+    bricks == the reference's BrickGrid(NanoVDBGrid) of the same file. (The host accessor, which shares get_value() with
+    the device one, is checked against the same golden on the CPU.)"""
+    import volren_b200 as vr
+    n = vr.NanoVDBGridData(*_source(nvdb_golden, "sphere"))
+    ctx.grid_clear()
+    ctx.grid_build_from_nvdb(n)
+    _golden_brick_equals(nvdb_golden, "sphere", ctx.grid_download())
