@@ -383,3 +383,40 @@ def test_gpu_build_from_nvdb_with_interior_tiles(ctx, nvdb_golden):
     ctx.grid_clear()
     ctx.grid_build_from_nvdb(n)
     _golden_brick_equals(nvdb_golden, "sphere", ctx.grid_download())
+
+
+def test_reader_survives_corrupted_files(nvdb_golden, tmp_path):
+    """Random byte corruption anywhere in the file (headers, masks, child offsets, values): vrb_nvdb_open either rejects the
+    file or accepts a grid whose every link stays inside the buffer -- the accessor must then read the whole padded lattice
+    without faulting. Runs in a child process so that a fault shows up as a failed test, not as a dead test session."""
+    import subprocess
+    import sys
+    np.save(tmp_path / "file.npy", nvdb_golden["nvdb_file"])
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import volren_b200 as vr
+data = np.load(%r)
+rng = np.random.default_rng(11)
+accepted = rejected = 0
+for it in range(600):
+    bad = data.copy()
+    n = int(rng.integers(1, 6))
+    # a quarter each: file header + metadata + GridData + TreeData + root tiles | masks and child offsets of the first
+    # upper node | the first lower node | anywhere   (density grid: buffer at byte 200, upper nodes at +256, lower at +1081856)
+    lo, hi = ((0, 1400), (200 + 672 + 256, 200 + 672 + 256 + 12352), (200 + 672 + 1081856, 200 + 672 + 1081856 + 33856), (0, bad.size))[it % 4]
+    pos = rng.integers(lo, hi, n)
+    bad[pos] = rng.integers(0, 256, n).astype(np.uint8)
+    try:
+        g = vr.NanoVDBGridData(bad, "density")
+    except vr.VrbError:
+        rejected += 1
+        continue
+    accepted += 1
+    if all(0 < e <= 512 for e in g.extent):
+        g.padded_lattice()
+print("accepted", accepted, "rejected", rejected)
+assert accepted > 0 and rejected > 0
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "file.npy"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, (res.returncode, res.stdout[-300:], res.stderr[-800:])
