@@ -404,7 +404,7 @@ for it in range(600):
     n = int(rng.integers(1, 6))
     # a quarter each: file header + metadata + GridData + TreeData + root tiles | masks and child offsets of the first
     # upper node | the first lower node | anywhere   (density grid: buffer at byte 200, upper nodes at +256, lower at +1081856)
-    lo, hi = ((0, 1400), (200 + 672 + 256, 200 + 672 + 256 + 12352), (200 + 672 + 1081856, 200 + 672 + 1081856 + 33856), (0, bad.size))[it % 4]
+    lo, hi = ((0, 1400), (200 + 672 + 256, 200 + 672 + 256 + 12352), (200 + 672 + 1081856, 200 + 672 + 1081856 + 33856), (0, bad.size))[it %% 4]
     pos = rng.integers(lo, hi, n)
     bad[pos] = rng.integers(0, 256, n).astype(np.uint8)
     try:
