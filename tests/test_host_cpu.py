@@ -121,6 +121,49 @@ def test_hdr_loader_matches_python_loader(volpy, env_rgb):
     assert np.array_equal(top_down[::-1], env_rgb)
 
 
+def test_ldr_png_environment_maps(volpy, tmp_path):
+    """Environment(path) accepts LDR .png files like the reference (cppgl uploads them as GL_R8 / RG8 / RGB8 / RGBA8: the
+    shader samples u8 / 255, no gamma; image_load flips to bottom-up rows). Every PNG flavour an encoder produces here:
+    gray, gray+alpha, RGB, RGBA, 16-bit, palette, and all five scanline filters (cv2 / PIL choose them adaptively)."""
+    import cv2
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    H, W = 37, 53
+    smooth = (np.linspace(0, 255, W)[None, :, None] * np.ones((H, 1, 4)) * 0.5 + rng.integers(0, 128, (H, W, 4))).astype(np.uint8)
+    cases = {"rgb": smooth[..., :3], "rgba": smooth, "gray": smooth[..., 0], "ga": None, "rgb16": None, "pal": None}
+    for name in cases:
+        p = str(tmp_path / f"{name}.png")
+        if name == "ga":
+            Image.fromarray(smooth[..., :2], "LA").save(p)
+            want = np.zeros((H, W, 3), np.float32); want[..., 0] = smooth[..., 0] / np.float32(255); want[..., 1] = smooth[..., 1] / np.float32(255)
+        elif name == "rgb16":
+            img16 = (smooth[..., :3].astype(np.uint16) << 8) | rng.integers(0, 256, (H, W, 3)).astype(np.uint16)
+            cv2.imwrite(p, img16[..., ::-1])
+            want = (img16 >> 8).astype(np.float32) / np.float32(255)
+        elif name == "pal":
+            pimg = Image.fromarray(smooth[..., :3], "RGB").quantize(32)
+            pimg.save(p)
+            want = np.asarray(pimg.convert("RGB"), np.float32) / np.float32(255)
+        elif name == "gray":
+            cv2.imwrite(p, cases[name])
+            want = np.zeros((H, W, 3), np.float32); want[..., 0] = cases[name] / np.float32(255)
+        elif name == "rgba":
+            cv2.imwrite(p, cases[name][..., [2, 1, 0, 3]])
+            want = cases[name][..., :3].astype(np.float32) / np.float32(255)
+        else:
+            cv2.imwrite(p, cases[name][..., ::-1])
+            want = cases[name].astype(np.float32) / np.float32(255)
+        got = volpy.load_environment_image(p)
+        assert got.shape == (H, W, 3) and np.array_equal(got, want[::-1]), name        # bottom-up rows
+    env = volpy.Environment(str(tmp_path / "rgb.png"))                                    # and through the class the scripts use
+    assert env.strength == 1.0
+    with pytest.raises(RuntimeError):
+        volpy.Environment(str(tmp_path / "missing.png"))
+    (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff")
+    with pytest.raises(RuntimeError, match="hdr and .png"):
+        volpy.Environment(str(tmp_path / "x.jpg"))
+
+
 def _read_png(path):
     data = open(path, "rb").read()
     assert data[:8] == b"\x89PNG\r\n\x1a\n"

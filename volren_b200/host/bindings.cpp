@@ -73,6 +73,12 @@ void bind_volpy(py::module_& m) {
         std::copy(img.data.begin(), img.data.end(), out.mutable_data());
         return out;
     }, py::arg("path"), py::arg("flip") = true);
+    m.def("load_environment_image", [](const std::string& path) {      // what Environment(path) reads: .hdr or LDR .png, bottom-up RGB
+        ImageF img = load_environment_image(path);
+        py::array_t<float> out({ py::ssize_t(img.h), py::ssize_t(img.w), py::ssize_t(3) });
+        std::copy(img.data.begin(), img.data.end(), out.mutable_data());
+        return out;
+    }, py::arg("path"));
     m.def("save_ldr", [](const std::string& path, py::array_t<uint8_t, py::array::c_style | py::array::forcecast> px, bool flip) {
         if (px.ndim() != 3) throw std::runtime_error("save_ldr: expected an (h, w, c) uint8 array");
         store_ldr(path, px.data(), int(px.shape(1)), int(px.shape(0)), int(px.shape(2)), flip);

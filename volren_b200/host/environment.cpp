@@ -8,7 +8,7 @@
 static std::atomic<uint64_t> next_env_id{ 1 };
 
 Environment::Environment(const std::string& path) : transform(1.f), strength(1.f), width(0), height(0), id(next_env_id++) {
-    volren::ImageF img = volren::load_hdr(path, true);
+    volren::ImageF img = volren::load_environment_image(path);     // .hdr, or an LDR .png sampled as unorm (cppgl texture.cpp:27-60)
     width = img.w;
     height = img.h;
     pixels = std::move(img.data);

@@ -105,6 +105,86 @@ ImageF load_hdr(const std::string& path, bool flip) {
 
 namespace {
 
+uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
+int paeth(int a, int b, int c) {
+    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+}  // namespace
+
+ImageF load_png_rgb(const std::string& path, bool flip) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in.is_open()) throw std::runtime_error("Failed to load image file: " + path);
+    const std::vector<uint8_t> d((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    static const uint8_t sig[8] = { 0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a };
+    if (d.size() < 33 || memcmp(d.data(), sig, 8) != 0) throw std::runtime_error("Failed to load image file (not a PNG): " + path);
+    uint32_t w = 0, h = 0;
+    int depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte;
+    for (size_t pos = 8; pos + 12 <= d.size();) {
+        const uint32_t len = be32(&d[pos]);
+        if (pos + 12 + size_t(len) > d.size()) throw std::runtime_error("truncated PNG: " + path);
+        const uint8_t* c = &d[pos + 8];
+        if (!memcmp(&d[pos + 4], "IHDR", 4) && len >= 13) { w = be32(c); h = be32(c + 4); depth = c[8]; ctype = c[9]; interlace = c[12]; }
+        else if (!memcmp(&d[pos + 4], "PLTE", 4)) plte.assign(c, c + len);
+        else if (!memcmp(&d[pos + 4], "IDAT", 4)) idat.insert(idat.end(), c, c + len);
+        else if (!memcmp(&d[pos + 4], "IEND", 4)) break;
+        pos += 12 + size_t(len);
+    }
+    const int comps = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (!w || !h || !comps || (depth != 8 && depth != 16) || (ctype == 3 && depth != 8) || interlace)
+        throw std::runtime_error("unsupported PNG (need 8/16-bit, non-interlaced gray / RGB / palette / alpha variants): " + path);
+    const size_t bpp = size_t(comps) * (depth / 8), stride = size_t(w) * bpp;
+    std::vector<uint8_t> raw((stride + 1) * h);
+    uLongf raw_len = uLongf(raw.size());
+    if (uncompress(raw.data(), &raw_len, idat.data(), uLong(idat.size())) != Z_OK || raw_len != raw.size())
+        throw std::runtime_error("corrupt PNG data: " + path);
+    std::vector<uint8_t> px(stride * h);
+    for (uint32_t y = 0; y < h; ++y) {       // undo the scanline filters (PNG spec 9.2)
+        const uint8_t* src = &raw[(stride + 1) * y];
+        uint8_t* dst = &px[stride * y];
+        const uint8_t* up = y ? &px[stride * (y - 1)] : nullptr;
+        const int filter = src[0];
+        if (filter > 4) throw std::runtime_error("corrupt PNG filter: " + path);
+        for (size_t i = 0; i < stride; ++i) {
+            const int a = i >= bpp ? dst[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
+            const int pred = filter == 0 ? 0 : filter == 1 ? a : filter == 2 ? b : filter == 3 ? ((a + b) >> 1) : paeth(a, b, c);
+            dst[i] = uint8_t(src[1 + i] + pred);
+        }
+    }
+    ImageF img;
+    img.w = int(w); img.h = int(h); img.channels = 3;
+    img.data.assign(size_t(w) * h * 3, 0.f);
+    for (uint32_t y = 0; y < h; ++y) {
+        const uint32_t oy = flip ? h - 1 - y : y;
+        for (uint32_t x = 0; x < w; ++x) {
+            const uint8_t* s = &px[stride * y + size_t(x) * bpp];
+            uint8_t v[4] = { 0, 0, 0, 255 };
+            for (int k = 0; k < comps; ++k) v[k] = s[size_t(k) * (depth / 8)];      // 16-bit: the high (first) byte
+            float* o = &img.data[(size_t(oy) * w + x) * 3];
+            if (ctype == 3) {
+                if (size_t(v[0]) * 3 + 2 >= plte.size()) throw std::runtime_error("PNG palette index out of range: " + path);
+                for (int k = 0; k < 3; ++k) o[k] = plte[size_t(v[0]) * 3 + k] / 255.f;
+            } else {
+                const int n = std::min(comps, 3);
+                for (int k = 0; k < n; ++k) o[k] = v[k] / 255.f;
+            }
+        }
+    }
+    return img;
+}
+
+ImageF load_environment_image(const std::string& path) {
+    std::string ext = std::filesystem::path(path).extension().string();
+    std::transform(ext.begin(), ext.end(), ext.begin(), ::tolower);
+    if (ext == ".hdr") return load_hdr(path, true);
+    if (ext == ".png") return load_png_rgb(path, true);
+    throw std::runtime_error("Failed to load image file: " + path + " (environment maps are read from .hdr and .png)");
+}
+
+namespace {
+
 void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back(uint8_t(x >> 24)); v.push_back(uint8_t(x >> 16)); v.push_back(uint8_t(x >> 8)); v.push_back(uint8_t(x)); }
 
 void png_chunk(std::ofstream& out, const char tag[4], const std::vector<uint8_t>& payload) {
