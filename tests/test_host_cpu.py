@@ -121,6 +121,36 @@ def test_hdr_loader_matches_python_loader(volpy, env_rgb):
     assert np.array_equal(top_down[::-1], env_rgb)
 
 
+def test_colmap_helpers_against_numpy(volpy):
+    """colmap_view_trans / colmap_view_rot (bindings.cpp:196-203): GL_TO_COLMAP * view with view = lookAt(pos, pos + dir, up)
+    (cppgl camera.cpp:51-59), checked against an independent numpy / scipy evaluation for random poses."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(4)
+    R = volpy.Renderer
+    for _ in range(20):
+        pos = rng.standard_normal(3).astype(np.float32) * 2
+        d = rng.standard_normal(3).astype(np.float32)
+        d /= np.linalg.norm(d)
+        if abs(d[1]) > 0.95:
+            continue
+        R.cam_pos, R.cam_dir, R.cam_up = volpy.vec3(*map(float, pos)), volpy.vec3(*map(float, d)), volpy.vec3(0, 1, 0)
+        R.update_camera()
+        f = d.astype(np.float64)
+        s_ = np.cross(f, [0, 1, 0]); s_ /= np.linalg.norm(s_)
+        u = np.cross(s_, f)
+        view = np.eye(4)
+        view[0, :3], view[1, :3], view[2, :3] = s_, u, -f
+        view[:3, 3] = [-s_ @ pos, -u @ pos, f @ pos]
+        assert np.allclose(np.array(R.view_matrix).T, view, atol=2e-5)          # the binding exposes glm columns as rows
+        M = np.diag([1.0, -1.0, -1.0, 1.0]) @ view
+        assert np.allclose(np.array(R.colmap_view_trans()), M[:3, 3], atol=2e-5)
+        q = np.array(R.colmap_view_rot())                                        # buffer order x, y, z, w (SURVEY 8b)
+        want = Rotation.from_matrix(M[:3, :3]).as_quat()
+        assert abs(np.linalg.norm(q) - 1) < 1e-5 and min(np.abs(q - want).max(), np.abs(q + want).max()) < 5e-5
+    R.cam_pos, R.cam_dir = volpy.vec3(1, 0, 1), (-volpy.vec3(1, 0, 1)).normalize()
+    R.update_camera()
+
+
 def test_ldr_png_environment_maps(volpy, tmp_path):
     """Environment(path) accepts LDR .png files like the reference (cppgl uploads them as GL_R8 / RG8 / RGB8 / RGBA8: the
     shader samples u8 / 255, no gamma; image_load flips to bottom-up rows). Every PNG flavour an encoder produces here:

@@ -224,6 +224,8 @@ void bind_volpy(py::module_& m) {
         .def_readwrite_static("view_matrix", &current_camera()->view)
         .def_readwrite_static("proj_matrix", &current_camera()->proj)
         .def_static("cam_aspect", &CameraImpl::aspect_ratio)
+        // addition: the camera matrices are otherwise refreshed by render() / the main loops (CameraImpl::update)
+        .def_static("update_camera", []() { current_camera()->update(); })
         // colmap
         .def_static("colmap_view_trans", []() {
             const glm::mat4 GL_TO_COLMAP = glm::inverse(glm::mat4(1, 0, 0, 0, 0, -1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1));
