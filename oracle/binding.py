@@ -428,3 +428,54 @@ class VoldataRef:
         self.lib.ref_dense_set_range(g, vmin, vmax)
         self.lib.ref_dense_write(g, path.encode())
         self.lib.ref_dense_free(g)
+
+
+GLSL_REF_SO = os.path.join(HERE, "_ref", "libglsl_ref.so")
+
+
+class GlslRef:
+    """The reference's UNMODIFIED GLSL compute shaders compiled as C++ (oracle/glsl_ref/: glsl2cpp.py + glsl_shim.h over the
+    reference's own glm) -- "the reference compiled here" for the shader layer. Only built where /root/reference exists;
+    the prebuilt .so travels to the GPU box. Scenes and parameters are the oracle's (vro_scene / vrb_params)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(GLSL_REF_SO)
+
+    def __init__(self):
+        L = self.lib = C.CDLL(GLSL_REF_SO)
+        L.glslref_trace.argtypes = [C.POINTER(_Scene), C.POINTER(Params), C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.glslref_env_setup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.glslref_tonemap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.glslref_tea.restype = C.c_uint32
+        L.glslref_tea.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        L.glslref_rng.restype = C.c_float
+        L.glslref_rng.argtypes = [C.POINTER(C.c_uint32)]
+
+    def trace(self, scene, params: Params, first_sample, n_samples, color=None, n_threads=0):
+        W, H = params.resolution[0], params.resolution[1]
+        if color is None:
+            color = np.zeros((H, W, 4), np.float32)
+        self.lib.glslref_trace(C.byref(scene), C.byref(params), first_sample, n_samples, _ptr(color),
+                               n_threads or (os.cpu_count() or 1))
+        return color
+
+    def env_setup(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        h, w, _ = rgb.shape
+        out = np.empty((IMP_DIM, IMP_DIM), np.float32)
+        self.lib.glslref_env_setup(_ptr(rgb), w, h, _ptr(out))
+        return out
+
+    def tonemap(self, color, exposure, gamma):
+        color = np.ascontiguousarray(color, np.float32).copy()
+        self.lib.glslref_tonemap(_ptr(color), color.shape[1], color.shape[0], exposure, gamma)
+        return color
+
+    def tea(self, v0, v1, n=32):
+        return int(self.lib.glslref_tea(v0 & 0xFFFFFFFF, v1 & 0xFFFFFFFF, n))
+
+    def rng(self, state):
+        s = C.c_uint32(state & 0xFFFFFFFF)
+        v = self.lib.glslref_rng(C.byref(s))
+        return float(v), int(s.value)

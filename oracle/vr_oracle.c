@@ -52,7 +52,9 @@ static inline v3 mul3(v3 a, v3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); 
 static inline v3 scale3(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
 static inline float dot3(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static inline v3 cross3(v3 a, v3 b) { return V3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
-static inline v3 normalize3(v3 a) { const float l = sqrtf(dot3(a, a)); return V3(a.x / l, a.y / l, a.z / l); }
+/* normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x): GLSL 4.50 spec 8.5 as glm states it
+ * (glm/detail/func_geometric.inl compute_normalize, func_exponential.inl inversesqrt) -- pinned by oracle/_ref/libglsl_ref.so */
+static inline v3 normalize3(v3 a) { const float r = 1.f / sqrtf(dot3(a, a)); return V3(a.x * r, a.y * r, a.z * r); }
 static inline float gl_min(float x, float y) { return y < x ? y : x; }   /* GLSL 4.50 spec 8.3 */
 static inline float gl_max(float x, float y) { return x < y ? y : x; }
 static inline float gl_clamp(float x, float lo, float hi) { return gl_min(gl_max(x, lo), hi); }
@@ -77,9 +79,10 @@ static inline int f2i(float x) {
 static inline v3 m3mul(const float* m, v3 v) {
     return V3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z);
 }
+/* mat4 * vec4 sums the four column products pairwise, (c0 x + c1 y) + (c2 z + c3 w): glm/detail/type_mat4x4.inl operator* */
 static inline v3 m4mul_xyz(const float* m, v3 v, float w) {
-    return V3(m[0] * v.x + m[4] * v.y + m[8] * v.z + m[12] * w, m[1] * v.x + m[5] * v.y + m[9] * v.z + m[13] * w,
-              m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * w);
+    return V3((m[0] * v.x + m[4] * v.y) + (m[8] * v.z + m[12] * w), (m[1] * v.x + m[5] * v.y) + (m[9] * v.z + m[13] * w),
+              (m[2] * v.x + m[6] * v.y) + (m[10] * v.z + m[14] * w));
 }
 static void m4mul(const float* a, const float* b, float* out) { /* out = a * b */
     for (int c = 0; c < 4; ++c)
