@@ -202,11 +202,14 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
 /* deterministic transmittance-only mode (defined by this build, DESIGN.md "T1"): centre ray per pixel,
  * exact voxel DDA, color = (Tr * Le_env(dir), 1 - Tr) */
 int vrb_trace_deterministic(vrb_ctx* ctx, const vrb_params* params);
-/* kernel selection: 0 = persistent-thread kernel with MUFU fast math (default, production);
- * 1 = the straightforward one-thread-per-pixel kernel with IEEE math; 2 = the persistent kernel with IEEE math.
- * 1 and 2 are cross-checks: 2 must reproduce 1 (same paths, same counters), 0 is compared statistically.
- * 3 / 4 = the two-rays-per-lane schedule (vr_trace3.cuh) with fast / IEEE math: bit-identical to 0 / 2, measured within
- * a few percent of 0 (profiles/r01_v10_duo_and_steps_sweeps.txt). Environment variable VRB200_KERNEL sets the default. */
+/* kernel selection: 0 = ray-pool persistent kernel with MUFU fast math (default, production: every warp schedules a pool
+ * of 64 path states in shared memory, csrc/vr_trace_pool.cuh);
+ * 1 = the straightforward one-thread-per-pixel kernel with IEEE math and no FMA contraction; 2 = the lane-resident
+ * persistent kernel with the same IEEE math. 1 and 2 are cross-checks compiled in their own translation unit
+ * (csrc/vrb200_strict.cu, -fmad=false): they replay the CPU oracle -- and through it the reference's GLSL -- path for path
+ * up to the last bit of libm, and 2 must reproduce 1 exactly (same paths, same counters);
+ * 3 = the lane-resident persistent kernel with fast math (round 1's production schedule): bit-identical images to 0.
+ * Environment variable VRB200_KERNEL sets the default. */
 int vrb_set_kernel(vrb_ctx* ctx, int kind);
 /* scheduling options of the production kernel (none changes the image): "lpt" (heaviest tiles first, default 1),
  * "cull" (hidden environment only: pixels outside the screen rectangle of the volume's box and 8x4 tiles onto which no

@@ -306,6 +306,13 @@ class VoldataRef:
         L.ref_grid_free.argtypes = [C.c_void_p]
         L.ref_brick_from_values.restype = C.c_void_p
         L.ref_brick_from_values.argtypes = [C.c_void_p, C.c_uint32 * 3, C.c_uint32 * 3]
+        L.ref_colormap_lut.argtypes = [C.c_int, C.c_uint32, C.c_void_p]
+
+    def colormap_lut(self, type_index, n_bins=256):
+        """TransferFunction::colormap(type, n_bins) (src/transferfunc.cpp:69-77) with the reference's own tinycolormap."""
+        out = np.empty((n_bins, 4), np.float32)
+        self.lib.ref_colormap_lut(int(type_index), int(n_bins), _ptr(out))
+        return out
 
     def to_half(self, f):
         return int(self.lib.ref_to_half(float(f)))

@@ -31,6 +31,7 @@
 #include <cereal/types/vector.hpp>
 #include <cereal/archives/portable_binary.hpp>
 #include <glm/detail/type_half.hpp>
+#include <tinycolormap.hpp>    // the reference's colour-map submodule (src/transferfunc.cpp:69-77 samples it)
 
 namespace cereal {
     template <class Archive> void serialize(Archive& ar, glm::uvec3& v) { ar(v.x, v.y, v.z); }
@@ -50,6 +51,17 @@ namespace voldata {
 using namespace voldata;
 
 extern "C" {
+
+// ---- TransferFunction::colormap (src/transferfunc.cpp:69-77): the loop restated around the REAL tinycolormap::GetColor ----
+// (transferfunc.cpp itself needs the GL SSBO wrapper); out: n_bins x RGBA float, before upload_gpu
+void ref_colormap_lut(int type, uint32_t n_bins, float* out) {
+    for (uint32_t i = 0; i < n_bins; ++i) {
+        const float f = float(i) / n_bins;
+        const tinycolormap::Color color = tinycolormap::GetColor(f, tinycolormap::ColormapType(type));
+        const glm::vec4 v(color.r(), color.g(), color.b(), f);
+        out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+    }
+}
 
 // ---- glm half conversion (glm/detail/type_half.inl) ----
 uint16_t ref_to_half(float f) { return uint16_t(glm::detail::toFloat16(f)); }

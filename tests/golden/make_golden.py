@@ -75,6 +75,18 @@ def main():
     q2, mm2 = ref.dense_from_float(d2)
     out["dense_neg.input"], out["dense_neg.u8"], out["dense_neg.minmax"] = d2, q2, np.array(mm2, np.float32)
     np.savez_compressed(os.path.join(HERE, "voldata_golden.npz"), **out)
+    # files WRITTEN by the reference's own cereal serialisation (serialization.cpp:36-43,66-80) for the host / Python readers
+    os.makedirs(os.path.join(HERE, "ref_written"), exist_ok=True)
+    vox = (np.random.default_rng(77).random((6, 5, 7)) * 255).astype(np.uint8)
+    ref.dense_write(vox, -1.25, 3.5, os.path.join(HERE, "ref_written", "ref_7x5x6.dense"))
+    vb, lo, hi = synth_cases()["ragged_70x33x20"]
+    ref.brick_roundtrip_write(vb, lo, hi, os.path.join(HERE, "ref_written", "ref_ragged_70x33x20.brick"))
+    np.savez_compressed(os.path.join(HERE, "ref_written", "expected.npz"), dense_vox=vox, dense_minmax=np.array([-1.25, 3.5], np.float32))
+    # TransferFunction::colormap with the reference's tinycolormap: every type at 256 bins, Turbo / Viridis also at 7 and 1000
+    cm = {f"type{t}_256": ref.colormap_lut(t, 256) for t in range(14)}
+    for t in (3, 9):
+        cm[f"type{t}_7"], cm[f"type{t}_1000"] = ref.colormap_lut(t, 7), ref.colormap_lut(t, 1000)
+    np.savez_compressed(os.path.join(HERE, "colormap_golden.npz"), **cm)
     # smoke.brick as parsed by the reference's own cereal loader: hashes of every buffer
     s = ref.brick_load(os.path.join(HERE, "assets", "smoke.brick"))
     np.savez_compressed(

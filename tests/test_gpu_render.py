@@ -296,7 +296,7 @@ def test_persistent_kernel_equals_simple_kernel(smoke_ctx, oracle, smoke_grid, l
     p = default_scene(smoke_grid, W, H, bounces=128, use_tf=True) if use_tf else readme_scene(smoke_grid, W, H)
     smoke_ctx.resize(W, H)
     out, cnt = [], []
-    for kind in (1, 2):      # 1 = simple (IEEE math), 2 = persistent (IEEE math); 0 = persistent fast math is the default elsewhere
+    for kind in (1, 2):      # 1 = simple (IEEE math), 2 = lane-resident persistent (IEEE math); 0 = ray pool with fast math is the default elsewhere
         smoke_ctx.set_kernel(kind)
         smoke_ctx.clear()
         smoke_ctx.set_counting(True)
@@ -313,29 +313,66 @@ def test_persistent_kernel_equals_simple_kernel(smoke_ctx, oracle, smoke_grid, l
 
 
 @pytest.mark.parametrize("use_tf", [False, True])
-def test_two_rays_per_lane_kernel_is_bit_identical(smoke_ctx, oracle, smoke_grid, lut_raw, use_tf):
-    """k_trace_duo (vr_trace3.cuh: two rays per lane, event state in shared memory) is a different SCHEDULE of the same
-    per-path arithmetic: images and event counters equal those of the one-ray persistent kernel bit for bit, with fast
-    math (3 vs 0) and with IEEE math (4 vs 2)."""
+def test_ray_pool_kernel_is_bit_identical_to_the_lane_resident_kernel(smoke_ctx, oracle, smoke_grid, lut_raw, use_tf):
+    """k_trace_pool (vr_trace_pool.cuh: 64 path states per warp in shared memory, one stage per scheduler iteration) is a
+    different SCHEDULE of the same per-path arithmetic as the lane-resident persistent kernel (kind 3, round 1's production
+    kernel): images and event counters are equal bit for bit, counting and non-counting builds, odd image sizes, a sample
+    range that is not a power of two."""
     W, H, SPP = 150, 90, 6
     lut, _ = oracle.lut_upload(lut_raw)
     smoke_ctx.tf_upload(lut)
     p = default_scene(smoke_grid, W, H, bounces=128, use_tf=True) if use_tf else readme_scene(smoke_grid, W, H)
     smoke_ctx.resize(W, H)
     try:
-        for base, duo in ((0, 3), (2, 4)):
-            out, cnt = [], []
-            for kind in (base, duo):
-                smoke_ctx.set_kernel(kind)
-                smoke_ctx.clear()
-                smoke_ctx.set_counting(True)
-                smoke_ctx.trace(p, 3, SPP)
-                cnt.append(smoke_ctx.get_counters().as_dict())
-                smoke_ctx.set_counting(False)
-                smoke_ctx.trace(p, 3 + SPP, SPP)          # and the non-counting build on top
-                out.append(smoke_ctx.download_color())
-            assert cnt[0] == cnt[1], (base, duo)
-            assert np.array_equal(out[0], out[1]), (base, duo)
+        out, cnt = [], []
+        for kind in (3, 0):
+            smoke_ctx.set_kernel(kind)
+            smoke_ctx.clear()
+            smoke_ctx.set_counting(True)
+            smoke_ctx.trace(p, 3, SPP)
+            cnt.append(smoke_ctx.get_counters().as_dict())
+            smoke_ctx.set_counting(False)
+            smoke_ctx.trace(p, 3 + SPP, SPP)          # and the non-counting build on top
+            out.append(smoke_ctx.download_color())
+        assert cnt[0] == cnt[1]
+        assert cnt[0]["n_samples"] == W * H * SPP
+        assert np.array_equal(out[0], out[1])
+    finally:
+        smoke_ctx.set_kernel(0)
+
+
+IEEE_REPLAY_MIN = 0.999     # fraction of pixels within 1e-3 of the oracle, same seeds, 1 spp
+
+
+@pytest.mark.parametrize("use_tf,bounces", [(False, 3), (True, 3), (False, 128), (True, 128)], ids=["notf-b3", "tf-b3", "notf-b128", "tf-b128"])
+def test_ieee_kernels_replay_the_oracle(smoke_ctx, oracle, smoke_grid, env_rgb, env_pyramid, lut_raw, use_tf, bounces):
+    """Kernels 1 (one thread per pixel) and 2 (lane-resident persistent), IEEE math without FMA contraction
+    (csrc/vrb200_strict.cu), against the oracle -- which equals the reference's own GLSL compiled as C++ bit for bit
+    (tests/test_glsl_ref.py). Same TEA/LCG seeds, 1 spp: the device follows the oracle path for path except where the
+    last bit of a libm function (CUDA logf / sincosf / atan2f / acosf vs glibc) flips a comparison. Pass mark: >= 0.999 of
+    the pixels within 1e-3 (relative to max(|ref|, 1e-3)), for 3 and for 128 bounces."""
+    W, H = 128, 96
+    lut, _ = oracle.lut_upload(lut_raw)
+    smoke_ctx.tf_upload(lut)
+    p = default_scene(smoke_grid, W, H, bounces=bounces, use_tf=True) if use_tf else readme_scene(smoke_grid, W, H, bounces=bounces)
+    want, cnt_want = oracle.trace(oracle.make_scene(smoke_grid, env_rgb, env_pyramid, lut=lut), p, 1, 1)
+    smoke_ctx.resize(W, H)
+    try:
+        for kind in (1, 2):
+            smoke_ctx.set_kernel(kind)
+            smoke_ctx.clear()
+            smoke_ctx.set_counting(True)
+            smoke_ctx.trace(p, 1, 1)
+            got = smoke_ctx.download_color()
+            cnt = smoke_ctx.get_counters().as_dict()
+            smoke_ctx.set_counting(False)
+            ok = np.all(rel_err(got, want, eps=1e-3) < 1e-3, axis=-1)
+            exact = np.all(got == want, axis=-1).mean()
+            print(f"IEEE kernel {kind} vs oracle (tf={use_tf}, bounces={bounces}): within 1e-3 {ok.mean():.5f}, bit-identical {exact:.5f}")
+            assert ok.mean() >= IEEE_REPLAY_MIN, (kind, ok.mean())
+            w = cnt_want.as_dict()
+            for k in ("n_maj", "n_dens", "n_nee", "n_env", "n_real"):      # the event counts follow: a flipped path changes them by a few events
+                assert abs(cnt[k] - w[k]) <= 0.002 * max(w[k], 1) + 2, (kind, k, cnt[k], w[k])
     finally:
         smoke_ctx.set_kernel(0)
 

@@ -293,3 +293,52 @@ def test_cli_fails_loudly_without_a_device(volpy, tmp_path):
     assert r.returncode != 0 and "no usable CUDA device" in r.stderr
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         volpy.Renderer().init()
+
+
+def test_colormaps_equal_tinycolormap_bit_for_bit(volpy):
+    """TransferFunction::colormap (transferfunc.cpp:69-77): the host's tables / closed forms and the Python mirror against LUTs
+    produced by the reference's own tinycolormap header (tests/golden/colormap_golden.npz, make_golden.py): all 14 types."""
+    from volren_b200 import colormaps
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "colormap_golden.npz"))
+    for t, name in enumerate(colormaps.TYPES):
+        want = gold[f"type{t}_256"]
+        got_host = np.array([np.array(v) for v in volpy._colormap_lut(t, 256)], np.float32)
+        assert np.array_equal(got_host.view(np.uint32), want.view(np.uint32)), name
+        assert np.array_equal(colormaps.colormap_lut(name, 256).view(np.uint32), want.view(np.uint32)), name
+    for t in (3, 9):       # Turbo, Viridis: the two CLI flags, at bin counts that do not hit the table entries
+        for n in (7, 1000):
+            want = gold[f"type{t}_{n}"]
+            got_host = np.array([np.array(v) for v in volpy._colormap_lut(t, n)], np.float32)
+            assert np.array_equal(got_host.view(np.uint32), want.view(np.uint32))
+            assert np.array_equal(colormaps.colormap_lut(colormaps.TYPES[t], n).view(np.uint32), want.view(np.uint32))
+    with pytest.raises(Exception):
+        volpy._colormap_lut(99, 4)
+
+
+def test_files_written_by_the_reference_serialisation(volpy, golden):
+    """.dense / .brick files written by the reference's own cereal path (serialization.cpp:36-43, 66-80; make_golden.py through
+    oracle/_ref) are read by the C++ host and by the Python formats module."""
+    from volren_b200 import formats
+    d = os.path.join(ROOT, "tests", "golden", "ref_written")
+    exp = np.load(os.path.join(d, "expected.npz"))
+    vox, (lo, hi) = exp["dense_vox"], exp["dense_minmax"]
+    g = volpy.Volume.load_grid(os.path.join(d, "ref_7x5x6.dense"))
+    assert repr(g.index_extent()) == "uvec3(7, 5, 6)" and g.minorant_majorant() == (float(lo), float(hi))
+    for z in range(6):
+        for y in range(5):
+            for x in range(7):
+                assert g.lookup(volpy.uvec3(x, y, z)) == np.float32(lo) + (np.float32(vox[z, y, x]) / np.float32(255)) * (np.float32(hi) - np.float32(lo))
+    pd = formats.load_dense(os.path.join(d, "ref_7x5x6.dense"))
+    assert np.array_equal(pd.voxels, vox) and (pd.min_value, pd.max_value) == (float(lo), float(hi))
+    name = "ragged_70x33x20"
+    pb = formats.load_brick(os.path.join(d, "ref_ragged_70x33x20.brick"))
+    assert tuple(pb.n_bricks) == tuple(golden[name + ".n_bricks"]) and np.array_equal(pb.indirection, golden[name + ".indirection"])
+    assert np.array_equal(pb.range, golden[name + ".range"])
+    for i in range(3):
+        assert np.array_equal(pb.mips[i], golden[name + f".mip{i}"])
+    hb = volpy.Volume.load_grid(os.path.join(d, "ref_ragged_70x33x20.brick"))
+    dec = pb.decode_all()
+    rng = np.random.default_rng(4)
+    for _ in range(300):
+        x, y, z = int(rng.integers(0, 70)), int(rng.integers(0, 33)), int(rng.integers(0, 20))
+        assert hb.lookup(volpy.uvec3(x, y, z)) == dec[z, y, x]

@@ -1,7 +1,7 @@
 """Build several variants of libvrb200 with different -D tunables (here, on CPU) and time them (on the GPU box).
-    python tools/sweep.py build  name:"-DVR_K_NEE=8 -DVR_K_FINISH=16" ...
-    python tools/sweep.py run [--tf 0|1] [--spp 16]
-Variants live in gpurun_out/../build/sweep/*.so (they travel with the snapshot since *.so is not gpurun-ignored).
+    python tools/sweep.py build  name:"-DVR_POOL_SLOTS=96 -DVR_POOL_MIN_BLOCKS=4" ...
+    python tools/sweep.py run [--scenes c1,c2,c3] [--spp 32] [--scale 0.5]
+Variants live in tools/_sweep/*.so (they travel with the snapshot since *.so is not gpurun-ignored).
 """
 import glob
 import os
@@ -18,22 +18,28 @@ def build(specs):
     os.makedirs(OUT, exist_ok=True)
     for f in glob.glob(os.path.join(OUT, "*.so")):
         os.remove(f)
-    procs = []
-    for spec in specs:
+    for spec in specs:          # sequential: each build already runs its translation units in parallel
         name, _, flags = spec.partition(":")
-        cmd = [vb._nvcc()] + vb.NVCC_FLAGS + flags.split() + ["-o", os.path.join(OUT, name + ".so"), os.path.join(vb.CSRC, "vrb200.cu")]
-        procs.append((name, subprocess.Popen(cmd)))
-    for name, p in procs:
-        assert p.wait() == 0, name
+        os.environ["VRB200_NVCC_FLAGS"] = flags
+        vb.OBJ_DIR = os.path.join(OUT, "obj_" + name)
+        vb.build_cuda(force=True, lib=os.path.join(OUT, name + ".so"))
+        print("built", name, flags, flush=True)
 
 
 def run(argv):
+    scenes, rest = "c1,c2", []
+    it = iter(argv)
+    for x in it:
+        if x == "--scenes":
+            scenes = next(it)
+        else:
+            rest.append(x)
     for so in sorted(glob.glob(os.path.join(OUT, "*.so"))):
-        for tf in (1, 0):
-            env = dict(os.environ, VRB200_LIB=so)
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "profile_trace.py"), "--tf", str(tf), "--spp", "32", "--launches", "3"] + argv,
-                                 env=env, capture_output=True, text=True).stdout.strip().splitlines()
-            print(f"{os.path.basename(so):40s} tf={tf}  {out[-1] if out else 'FAILED'}", flush=True)
+        for sc in scenes.split(","):
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "profile_trace.py"), "--scene", sc, "--lib", so, "--json", "1"] + rest,
+                                 capture_output=True, text=True)
+            line = [l for l in out.stdout.splitlines() if l.startswith("JSON ")]
+            print(f"{os.path.basename(so):40s} {sc}  {line[-1][5:] if line else 'FAILED ' + out.stderr[-300:]}", flush=True)
 
 
 if __name__ == "__main__":

@@ -8,6 +8,7 @@ volpy*.so, volren (with --host): C++ host mirroring the reference Renderer/CLI/p
 from __future__ import annotations
 
 import os
+import shlex
 import shutil
 import subprocess
 import sys
@@ -21,8 +22,11 @@ LIB = os.path.join(PKG, "libvrb200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
+# translation units: (source, extra flags). The IEEE cross-check kernels are compiled without FMA contraction.
+UNITS = [("vrb200.cu", []), ("vrb200_strict.cu", ["-fmad=false"])]
+OBJ_DIR = os.path.join(PKG, "csrc", "_build")
 
 
 def _newer(target, sources):
@@ -36,13 +40,23 @@ def _nvcc():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def build_cuda(force=False, verbose=False):
-    sources = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "vrb200.h")]
-    if not force and not _newer(LIB, sources):
+def build_cuda(force=False, verbose=False, lib=None):
+    sources = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [os.path.join(ROOT, "include", "vrb200.h")]
+    if not force and lib is None and not _newer(LIB, sources):
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "vrb200.cu")]
-    subprocess.run(cmd, check=True)
-    return LIB
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    extra = shlex.split(os.environ.get("VRB200_NVCC_FLAGS", ""))          # e.g. -DVR_POOL_SLOTS=96 for sweep builds
+    jobs = []
+    for src, flags in UNITS:
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        jobs.append((obj, subprocess.Popen(cmd)))
+    for obj, proc in jobs:
+        if proc.wait() != 0:
+            raise subprocess.CalledProcessError(proc.returncode, "nvcc -c " + obj)
+    out = lib or LIB
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + [o for o, _ in jobs], check=True)
+    return out
 
 
 def host_targets():

@@ -8,6 +8,13 @@
 
 #define VR_DEV __device__ __forceinline__
 #define VR_HD __host__ __device__ __forceinline__
+// Non-template kernels defined in headers: the strict translation unit (vrb200_strict.cu, compiled with -fmad=false for the
+// IEEE cross-check kernels) includes the same headers, so there they get internal linkage and are dropped when unused.
+#ifdef VR_STRICT_TU
+#define VR_GLOBAL static __global__
+#else
+#define VR_GLOBAL __global__
+#endif
 
 namespace vr {
 
@@ -25,7 +32,7 @@ VR_HD float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s)
 VR_HD float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
 VR_HD float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 VR_HD float3 cross(float3 a, float3 b) { return f3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
-VR_DEV float3 normalize(float3 a) { return a / sqrtf(dot(a, a)); }
+VR_DEV float3 normalize(float3 a) { return a * (1.f / sqrtf(dot(a, a))); }   // v * inversesqrt(dot(v, v)), as glm states GLSL's normalize
 VR_HD float sqr(float x) { return x * x; }
 VR_HD float luma(float3 c) { return dot(c, f3(0.212671f, 0.715160f, 0.072169f)); }            // common.glsl:21
 VR_DEV float sanitize(float x) { return (isnan(x) || isinf(x)) ? 0.f : x; }                    // common.glsl:17
@@ -40,13 +47,16 @@ VR_HD float3 mul(const Mat3& M, float3 v) {
     return f3(M.m[0] * v.x + M.m[3] * v.y + M.m[6] * v.z, M.m[1] * v.x + M.m[4] * v.y + M.m[7] * v.z,
               M.m[2] * v.x + M.m[5] * v.y + M.m[8] * v.z);
 }
+// mat4 * vec4(v, 1) and mat4 * vec4(v, 0): the four column products are summed pairwise, (c0 x + c1 y) + (c2 z + c3 w), the
+// order of glm's operator* (glm/detail/type_mat4x4.inl) that the compiled-GLSL reference, which the compiled-GLSL reference of the test suite pins
 VR_HD float3 mul_point(const Mat4& M, float3 v) {
-    return f3(M.m[0] * v.x + M.m[4] * v.y + M.m[8] * v.z + M.m[12], M.m[1] * v.x + M.m[5] * v.y + M.m[9] * v.z + M.m[13],
-              M.m[2] * v.x + M.m[6] * v.y + M.m[10] * v.z + M.m[14]);
+    return f3((M.m[0] * v.x + M.m[4] * v.y) + (M.m[8] * v.z + M.m[12]), (M.m[1] * v.x + M.m[5] * v.y) + (M.m[9] * v.z + M.m[13]),
+              (M.m[2] * v.x + M.m[6] * v.y) + (M.m[10] * v.z + M.m[14]));
 }
 VR_HD float3 mul_dir(const Mat4& M, float3 v) {
-    return f3(M.m[0] * v.x + M.m[4] * v.y + M.m[8] * v.z, M.m[1] * v.x + M.m[5] * v.y + M.m[9] * v.z,
-              M.m[2] * v.x + M.m[6] * v.y + M.m[10] * v.z);
+    // (c3 * 0 is kept: its signed zero decides the sign of an exactly-zero component, hence of 1 / idir)
+    return f3((M.m[0] * v.x + M.m[4] * v.y) + (M.m[8] * v.z + M.m[12] * 0.f), (M.m[1] * v.x + M.m[5] * v.y) + (M.m[9] * v.z + M.m[13] * 0.f),
+              (M.m[2] * v.x + M.m[6] * v.y) + (M.m[10] * v.z + M.m[14] * 0.f));
 }
 
 constexpr float PI_F = 3.14159265358979323846f;  // common.glsl:4

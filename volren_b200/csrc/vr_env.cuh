@@ -45,13 +45,13 @@ VR_DEV float3 env_texture(const EnvView& e, float u, float v) {
               mixf(mixf(t00.z, t10.z, ax), mixf(t01.z, t11.z, ax), ay));
 }
 
-__global__ void k_env_pad(const float* __restrict__ rgb, float4* __restrict__ out, size_t n) {
+VR_GLOBAL void k_env_pad(const float* __restrict__ rgb, float4* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
         out[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.f);
 }
 
 // env_setup.glsl:18-34 with num_samples = (8,8), output_size_samples = 4096, inv_samples = 1/64
-__global__ void __launch_bounds__(256) k_env_impmap(EnvView e, float* __restrict__ impmap) {
+VR_GLOBAL void __launch_bounds__(256) k_env_impmap(EnvView e, float* __restrict__ impmap) {
     const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
     if (px >= IMP_DIM || py >= IMP_DIM) return;
     float importance = 0.f;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_env_impmap(EnvView e, float* __restrict
 
 // glGenerateMipmap on the R32F importance map: 2x2 box filter, pinned as 0.25f*((a+b)+(c+d)).
 // One warp reduces a 2x2 quad per lane; levels are produced one launch per level (tiny, one-off).
-__global__ void k_env_mip(const float* __restrict__ src, int sdim, float* __restrict__ dst, int ddim) {
+VR_GLOBAL void k_env_mip(const float* __restrict__ src, int sdim, float* __restrict__ dst, int ddim) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= ddim || y >= ddim) return;
     const float2 r0 = *reinterpret_cast<const float2*>(src + size_t(2 * y) * sdim + 2 * x);
@@ -88,7 +88,7 @@ VR_DEV uint32_t to_unorm8(float x) {  // GL float -> unorm8 conversion
 }
 
 // shader/tonemap.glsl:29-36 (in place on the RGBA32F colour buffer)
-__global__ void k_tonemap_inplace(float4* __restrict__ color, size_t n, float exposure, float inv_gamma) {
+VR_GLOBAL void k_tonemap_inplace(float4* __restrict__ color, size_t n, float exposure, float inv_gamma) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         float4 c = color[i];
         c.x = sanitize(powf(hable_tonemap(c.x, exposure), inv_gamma));
@@ -99,7 +99,7 @@ __global__ void k_tonemap_inplace(float4* __restrict__ color, size_t n, float ex
     }
 }
 // RendererOpenGL::draw (renderer.cpp:147-153): tonemap.fs or blit.fs into the RGBA8 framebuffer
-__global__ void k_draw(const float4* __restrict__ color, uchar4* __restrict__ fb, size_t n, float exposure, float inv_gamma, int tonemapping) {
+VR_GLOBAL void k_draw(const float4* __restrict__ color, uchar4* __restrict__ fb, size_t n, float exposure, float inv_gamma, int tonemapping) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         float4 c = color[i];
         if (tonemapping) {
@@ -110,25 +110,25 @@ __global__ void k_draw(const float4* __restrict__ color, uchar4* __restrict__ fb
         fb[i] = make_uchar4((unsigned char)to_unorm8(c.x), (unsigned char)to_unorm8(c.y), (unsigned char)to_unorm8(c.z), (unsigned char)to_unorm8(c.w));
     }
 }
-__global__ void k_color_to_ldr(const float4* __restrict__ color, uchar4* __restrict__ out, size_t n) {
+VR_GLOBAL void k_color_to_ldr(const float4* __restrict__ color, uchar4* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         const float4 c = color[i];
         out[i] = make_uchar4((unsigned char)to_unorm8(c.x), (unsigned char)to_unorm8(c.y), (unsigned char)to_unorm8(c.z), (unsigned char)to_unorm8(c.w));
     }
 }
 // packed tile coordinates (ty << 16 | tx) in raster order
-__global__ void k_tile_coords(uint32_t* __restrict__ out, size_t n, uint32_t tiles_x) {
+VR_GLOBAL void k_tile_coords(uint32_t* __restrict__ out, size_t n, uint32_t tiles_x) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
         out[i] = (uint32_t(i / tiles_x) << 16) | uint32_t(i % tiles_x);
 }
-__global__ void k_scale(float4* __restrict__ color, size_t n, float s) {
+VR_GLOBAL void k_scale(float4* __restrict__ color, size_t n, float s) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         float4 c = color[i];
         c.x *= s; c.y *= s; c.z *= s; c.w *= s;
         color[i] = c;
     }
 }
-__global__ void k_add(float4* __restrict__ dst, const float4* __restrict__ src, size_t n) {
+VR_GLOBAL void k_add(float4* __restrict__ dst, const float4* __restrict__ src, size_t n) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         float4 a = dst[i];
         const float4 b = src[i];

@@ -29,7 +29,7 @@ struct StrictMath {
     static VR_DEV float sqrt(float a) { return sqrtf(a); }
     static VR_DEV float log(float a) { return logf(a); }
     static VR_DEV void sincos(float a, float* s, float* c) { sincosf(a, s, c); }
-    static VR_DEV float3 normalize(float3 v) { return v / sqrtf(dot(v, v)); }
+    static VR_DEV float3 normalize(float3 v) { return v * (1.f / sqrtf(dot(v, v))); }   // glm: v * inversesqrt(dot(v, v))
 };
 struct FastMath {
     static constexpr bool fast = true;
@@ -91,17 +91,11 @@ struct TraceArgs {
 template <bool COUNT> struct Cnt;
 template <> struct Cnt<false> {
     VR_DEV void maj() {} VR_DEV void dens() {} VR_DEV void emis() {} VR_DEV void nee() {} VR_DEV void env() {} VR_DEV void real() {} VR_DEV void samp() {}
-    VR_DEV void maj(bool) {} VR_DEV void spec_begin() {} VR_DEV void spec_rollback() {}
 };
 template <> struct Cnt<true> {
     uint32_t n_samp = 0, n_maj = 0, n_dens = 0, n_emis = 0, n_nee = 0, n_env = 0, n_real = 0;
     VR_DEV void maj() { ++n_maj; } VR_DEV void dens() { ++n_dens; } VR_DEV void emis() { ++n_emis; } VR_DEV void nee() { ++n_nee; }
     VR_DEV void env() { ++n_env; } VR_DEV void real() { ++n_real; } VR_DEV void samp() { ++n_samp; }
-    // speculative DDA steps (vr_trace2.cuh) count only once their outstanding collision is confirmed null
-    uint32_t n_spec = 0;
-    VR_DEV void maj(bool speculative) { ++n_maj; if (speculative) ++n_spec; }
-    VR_DEV void spec_begin() { n_spec = 0; }
-    VR_DEV void spec_rollback() { n_maj -= n_spec; n_spec = 0; }
 };
 VR_DEV void flush_counters(const TraceArgs&, const Cnt<false>&) {}
 VR_DEV void flush_counters(const TraceArgs& a, const Cnt<true>& c) {
@@ -129,7 +123,11 @@ VR_DEV float brick_value(const GridView& g, int x, int y, int z) {
     float unorm = 0.f;
     if (r.x != 0xffffffffu)
         unorm = unorm8_to_float(__ldg(g.atlas_lin + size_t(r.x) * 512u + uint32_t(((z & 7) << 6) | ((y & 7) << 3) | (x & 7))));
+#ifdef VR_STRICT_TU
+    return lo + unorm * (hi - lo);        // -fmad=false: two roundings, the arithmetic of the oracle / the compiled GLSL
+#else
     return fmaf(unorm, hi - lo, lo);      // explicit: the same rounding at every call site (tracer, decoded apron blocks)
+#endif
 }
 
 // lookup_majorant (common.glsl:278-281) without the density_scale factor
@@ -282,7 +280,7 @@ VR_DEV float decoded_value(const GridView& g, int x, int y, int z) {
 
 // ---- building the decoded apron bricks -----------------------------------------------------------------
 // flags[cell] = 1 when any of the cell's 8 bricks (b + {0,1}^3) lies in the grid with a range other than (0, 0)
-__global__ void k_cell_flags(const uint2* __restrict__ rec, uint3 nb, uint32_t* __restrict__ flags) {
+VR_GLOBAL void k_cell_flags(const uint2* __restrict__ rec, uint3 nb, uint32_t* __restrict__ flags) {
     const uint32_t cx = nb.x + 1, cy = nb.y + 1, cz = nb.z + 1;
     const size_t n = size_t(cx) * cy * cz;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
@@ -300,11 +298,11 @@ __global__ void k_cell_flags(const uint2* __restrict__ rec, uint3 nb, uint32_t* 
     }
 }
 // cslot = 1 + (number of flagged cells before this one) for flagged cells, 0 (the shared zero block) otherwise
-__global__ void k_cell_slots(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ excl, size_t n, uint32_t* __restrict__ cslot) {
+VR_GLOBAL void k_cell_slots(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ excl, size_t n, uint32_t* __restrict__ cslot) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) cslot[i] = flags[i] ? excl[i] + 1u : 0u;
 }
 // one warp per cell with a block of its own: 729 decoded voxels
-__global__ void __launch_bounds__(256) k_decode_cells(const GridView g, const uint32_t* __restrict__ cslot, float* __restrict__ datlas) {
+VR_GLOBAL void __launch_bounds__(256) k_decode_cells(const GridView g, const uint32_t* __restrict__ cslot, float* __restrict__ datlas) {
     const uint32_t cx = g.nb.x + 1, cy = g.nb.y + 1, cz = g.nb.z + 1;
     const size_t n = size_t(cx) * cy * cz;
     const int lane = threadIdx.x & 31;
@@ -421,7 +419,7 @@ VR_DEV float pdf_environment(const TraceArgs& a, float3 Le_dir) {
 // The per-level quantities dsplit, e and the reciprocals the remaps multiply with depend on the quad only: k_env_split
 // evaluates them once per environment with these very expressions (FastMath: a * rcp.approx(b)), so the table path
 // returns the same bits with 2 dependent 16-byte loads and no MUFU per level instead of 2 loads + 4 MUFU.RCP.
-__global__ void k_env_split(const float* __restrict__ impmap, float4* __restrict__ split) {
+VR_GLOBAL void k_env_split(const float* __restrict__ impmap, float4* __restrict__ split) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < SPLIT_QUADS; i += gridDim.x * blockDim.x) {
         int mip = 8;
         while (mip > 0 && i >= split_offset(mip - 1)) --mip;
@@ -659,7 +657,7 @@ VR_DEV float mix_rn(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, _
 // sample order (so the running mean is evaluated exactly like n successive dispatches).
 // Warps cover 8x4 pixel tiles for ray coherence. Cross-check kernel (StrictMath), not the production path.
 template <bool TF, bool COUNT>
-__global__ void __launch_bounds__(256) k_trace_pixels(const __grid_constant__ TraceArgs a) {
+VR_GLOBAL void __launch_bounds__(256) k_trace_pixels(const __grid_constant__ TraceArgs a) {
     using MT = StrictMath;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = a.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -691,7 +689,7 @@ __global__ void __launch_bounds__(256) k_trace_pixels(const __grid_constant__ Tr
 // ------------------------------------------------------------------------------------------------
 // deterministic transmittance-only mode ("T1"): centre ray, exact voxel DDA with empty-brick
 // skipping, color = (Tr * Le_env(dir), 1 - Tr). fp32 on the device; the oracle evaluates it in fp64.
-__global__ void __launch_bounds__(256) k_trace_deterministic(const __grid_constant__ TraceArgs a) {
+VR_GLOBAL void __launch_bounds__(256) k_trace_deterministic(const __grid_constant__ TraceArgs a) {
     using MT = StrictMath;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);

@@ -39,7 +39,7 @@ enum : int { SG_STEP = 0, SG_COLLIDE = 1, SG_NEE = 2, SG_SCATTER = 3, SG_FINISH 
 
 // fills one level of the majorant table: exactly majorant_at() of vr_trace.cuh, hoisted out of the DDA loop
 template <bool TF>
-__global__ void k_majorant_table(const __grid_constant__ TraceArgs a, int level, float* __restrict__ out, size_t n) {
+VR_GLOBAL void k_majorant_table(const __grid_constant__ TraceArgs a, int level, float* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         const uint32_t w = level == 0 ? a.density.rec[i].y : a.density.mips[level - 1][i];
         const float m = a.p.vol_density_scale * range_hi(w);
@@ -63,8 +63,7 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #endif
 #ifndef VR_TRACE_MIN_BLOCKS
 #define VR_TRACE_MIN_BLOCKS 7     // CTAs per SM: 7 -> 72 registers without spills (28 warps/SM). B200, TF / non-TF Gsamples/s:
-                                  // 6 (80 regs) 40.8 / 4.36, 7 (72) 44.1 / 4.41, 8 (64, spills) 41.9 / 4.32,
-                                  // 8 with VR_COLD_SMEM (64, no spills) 44.0 / 4.47 (profiles/r01_v10_duo_and_steps_sweeps.txt)
+                                  // 6 (80 regs) 40.8 / 4.36, 7 (72) 44.1 / 4.41, 8 (64, spills) 41.9 / 4.32 (profiles/r01_v10_duo_and_steps_sweeps.txt)
 #endif
 // Queue thresholds, tuned on B200 (tools/sweep.py, profiles/r01_sweep*.txt): a queue's stage runs once this many lanes
 // wait in it. The TF variant has cheap events and an expensive 8-tap collision; the non-TF variant a cheap 1-tap
@@ -93,39 +92,9 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #ifndef VR_MIN_STEP
 #define VR_MIN_STEP 24    // fewer stepping lanes than this: drain the fullest queue even below its threshold
 #endif
-// Speculative null collisions (VR_SPECULATE): 92-94 % of the tentative collisions of the bench scenes are null, and the
-// number of random draws a null collision consumes is fixed (density filter 9 | 0, emission filter 9 on camera segments,
-// 1 for the test, then the new tau). A lane that hits a tentative collision therefore records it (t, seed, majorant,
-// mip), jumps its stream ahead, draws the new tau and KEEPS STEPPING; the recorded collision is evaluated later, when
-// many lanes hold one (the 8-tap / tricubic lookup then runs with most lanes active instead of ~14). A null result
-// confirms the speculation; a real collision rolls the lane back to the recorded point (t, seed) and discards the
-// speculative steps. One collision may be outstanding per lane: a second one, or the end of the ray, parks the lane until
-// the first is resolved. Same paths, same draws, same sums in the same order as the non-speculative schedule.
-// MEASURED SLOWER on B200 (profiles/r01_v9_speculate_sweep.txt: TF 1.01 -> 1.07-1.15 ms, non-TF 8.47 -> 8.84-9.21 ms for
-// every threshold pair tried): a lane meets its next tentative collision ~2.5 steps later and parks anyway, so the
-// resolve batches grow little while ~7 % of the steps are thrown away. Off by default; bit-identical images and
-// counters with it on (the GPU test-suite passes either way).
-#ifndef VR_SPECULATE
-#define VR_SPECULATE 0
-#endif
-#ifndef VR_K_BLOCKED_TF
-#define VR_K_BLOCKED_TF 8     // resolve when this many lanes are parked behind their outstanding collision ...
-#endif
-#ifndef VR_K_BLOCKED
-#define VR_K_BLOCKED 8
-#endif
-#ifndef VR_K_PENDING_TF
-#define VR_K_PENDING_TF 24    // ... or this many lanes hold one
-#endif
-#ifndef VR_K_PENDING
-#define VR_K_PENDING 24
-#endif
 #ifndef VR_STEPS_PER_PASS
 #define VR_STEPS_PER_PASS 3       // DDA steps per scheduler pass: the five ballots + queue logic are 7 % of the issued instructions at 32 lanes;
                                   // B200 (TF / non-TF Gsamples/s): 1 -> 37.0 / 4.01, 2 -> 39.0 / 4.19, 3 -> 38.8 / 4.26, 4 -> 38.2 / 4.16, 6 -> 36.6 / 3.88
-#endif
-#ifndef VR_COLD_SMEM
-#define VR_COLD_SMEM 0            // 1: radiance + pending NEE term of the lane's path live in shared memory
 #endif
 #ifndef VR_LBUF_STREAM
 #define VR_LBUF_STREAM 1          // sample-buffer stores are streaming (evict-first): written once, read once by k_fold
@@ -135,18 +104,10 @@ VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
 #else
 #define VR_LBUF_STORE(ptr, v) (*(ptr) = (v))
 #endif
-#ifndef VR_STEP_PREFETCH
-#define VR_STEP_PREFETCH 0        // 1: fetch the majorants of all steps of a pass before consuming the first (bit-identical;
-                                  // measured: TF 41.0 -> 41.2, non-TF 4.37 -> 4.06 Gsamples/s: the discarded geometry costs more than the
-                                  // overlapped loads save, profiles/r01_v10_duo_and_steps_sweeps.txt)
-#endif
-#ifndef VR_REP_MIN
-#define VR_REP_MIN 0              // repeat a step only while this many lanes are still stepping (0: always)
-#endif
 constexpr int MAX_RAY_STEPS = 1 << 20;  // hang guard only: no finite ray takes this many DDA steps
 
 template <bool TF, bool COUNT, class MT>
-__global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_persistent(const __grid_constant__ TraceArgs a) {
+VR_GLOBAL void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_persistent(const __grid_constant__ TraceArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int W = a.p.resolution[0];
@@ -161,37 +122,9 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
     unsigned t_item = 0;           // clock at which this lane took its sample
     uint32_t seed = 0, n_paths = 0;
     float3 pos = f3(0.f), dir = f3(0.f, 0.f, -1.f), thr = f3(1.f);
-    // radiance so far and the pending NEE term are touched by the rare events only (NEE, end of a shadow ray, emission,
-    // finish): with VR_COLD_SMEM they live in shared memory (one conflict-free column per thread) instead of 6 registers
-#if VR_COLD_SMEM
-    __shared__ float s_cold[6][VR_TRACE_BLOCK];
-#define LGET() f3(s_cold[0][threadIdx.x], s_cold[1][threadIdx.x], s_cold[2][threadIdx.x])
-#define LSET(v) do { const float3 v_ = (v); s_cold[0][threadIdx.x] = v_.x; s_cold[1][threadIdx.x] = v_.y; s_cold[2][threadIdx.x] = v_.z; } while (0)
-#define PGET() f3(s_cold[3][threadIdx.x], s_cold[4][threadIdx.x], s_cold[5][threadIdx.x])
-#define PSET(v) do { const float3 v_ = (v); s_cold[3][threadIdx.x] = v_.x; s_cold[4][threadIdx.x] = v_.y; s_cold[5][threadIdx.x] = v_.z; } while (0)
-    LSET(f3(0.f)); PSET(f3(0.f));
-#else
-    float3 L = f3(0.f), pend = f3(0.f);
-#define LGET() L
-#define LSET(v) L = (v)
-#define PGET() pend
-#define PSET(v) pend = (v)
-#endif
+    float3 L = f3(0.f), pend = f3(0.f);    // radiance so far; NEE term waiting for its shadow ray
     float3 ipos = f3(0.f), idir = f3(1.f), ri = f3(1.f);
     float t = 0.f, tfar = -1.f, tau = 0.f, mip = 3.f, f_p = 0.f, Tr = 1.f, majorant = 0.f;
-    // outstanding (speculated-null) tentative collision of this lane
-    constexpr bool SPEC = VR_SPECULATE != 0;
-    bool pending = false, second = false;     // second: parked AT another tentative collision (else: parked at the ray's end)
-    float t_c = 0.f, maj_c = 0.f, mip_c = 0.f;
-    uint32_t seed_c = 0;
-    // records the tentative collision at the lane's current state and continues as if it were null (common.glsl:451-452 / 497-498)
-    auto speculate = [&]() {
-        t_c = t; seed_c = seed; maj_c = majorant; mip_c = mip; pending = true;
-        if (shadow) rng_skip<TF ? 1 : 10>(seed); else rng_skip<TF ? 10 : 19>(seed);
-        tau = -MT::log(1.f - rng(seed));
-        mip = fmaxf(0.f, mip - 2.f);
-        cnt.spec_begin();
-    };
     // ---- warp state: the current block of 32 samples (one tile, one sample index), prepared in shared memory ----
     __shared__ float4 s_prep[VR_TRACE_BLOCK / 32][32];     // {view dir, seed after the two jitter draws}
     float4* prep = s_prep[threadIdx.x >> 5];
@@ -204,62 +137,13 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
 
     while (true) {
         // ================= STEP: one brick-DDA step (common.glsl:423-435 / 470-482) =================
-#if VR_STEP_PREFETCH && !VR_SPECULATE
-        // The geometry of the next R steps (positions, step lengths, mip levels) does not depend on the majorants, only on
-        // whether a tentative collision interrupts the walk: fetch all R majorants first (R loads in flight instead of a
-        // load -> use chain per step), then consume them in order; after a collision or the end of the ray the remaining
-        // ones are dropped. Same arithmetic per step, hence the same t / tau / mip sequence bit for bit.
-        if (stage == SG_STEP) {
-            constexpr int R = VR_STEPS_PER_PASS;
-            float dts[R], majs[R];
-            {
-                float tk = t, mk = mip;
-#pragma unroll
-                for (int k = 0; k < R; ++k) {
-                    const float3 curr = ipos + tk * idir;
-                    const int m = round_mip(mk);
-                    majs[k] = (tk < tfar) ? table_majorant(a, curr, m) : 0.f;
-                    dts[k] = step_dda(curr, ri, m);
-                    tk += dts[k];
-                    mk = fminf(mk + 0.25f, 3.f);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-                if (stage == SG_STEP && t < tfar) {
-                    cnt.maj();
-                    majorant = majs[k];
-                    const float dt = dts[k];
-                    t += dt;
-                    tau -= majorant * dt;
-                    mip = fminf(mip + 0.25f, 3.f);
-                    if (!(tau > 0.f)) {
-                        t += MT::div(tau, majorant);
-                        if (!(t >= tfar)) { stage = SG_COLLIDE; second = true; }   // `if (t >= far) break;` (a NaN t goes on to the lookup)
-                    }
-                    if (++steps > MAX_RAY_STEPS) { t = INFINITY; stage = SG_STEP; }
-                }
-            }
-            if (stage == SG_STEP && !(t < tfar)) {   // the ray left the volume
-                if (shadow) {
-                    if (Tr != 0.f) LSET(LGET() + PGET() * Tr);     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
-                    stage = SG_SCATTER;
-                } else {
-                    escaped = true;
-                    stage = SG_FINISH;
-                }
-            }
-        }
-#else
 #pragma unroll
         for (int rep = 0; rep < VR_STEPS_PER_PASS; ++rep) {
-        // a further step only while enough lanes still step (one vote instead of the full scheduler)
-        if (VR_REP_MIN > 0 && rep > 0 && __popc(__ballot_sync(FULL, stage == SG_STEP)) < VR_REP_MIN) break;
         if (stage == SG_STEP) {
             if (t < tfar) {
                 const float3 curr = ipos + t * idir;
                 const int m = round_mip(mip);
-                cnt.maj(SPEC && pending);
+                cnt.maj();
                 majorant = table_majorant(a, curr, m);
                 const float dt = step_dda(curr, ri, m);
                 t += dt;
@@ -267,18 +151,13 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 mip = fminf(mip + 0.25f, 3.f);
                 if (!(tau > 0.f)) {
                     t += MT::div(tau, majorant);
-                    if (!(t >= tfar)) {                     // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
-                        if (SPEC && !pending) speculate();  // stays in STEP
-                        else { stage = SG_COLLIDE; second = true; }
-                    }
+                    if (!(t >= tfar)) stage = SG_COLLIDE;   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
                 }
                 if (++steps > MAX_RAY_STEPS) { t = INFINITY; stage = SG_STEP; }
             }
             if (stage == SG_STEP && !(t < tfar)) {   // the ray left the volume
-                if (SPEC && pending) {                // ... if the outstanding collision turns out null: wait for it
-                    stage = SG_COLLIDE; second = false;
-                } else if (shadow) {
-                    if (Tr != 0.f) LSET(LGET() + PGET() * Tr);     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
+                if (shadow) {
+                    if (Tr != 0.f) L = L + pend * Tr;     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
                     stage = SG_SCATTER;
                 } else {
                     escaped = true;
@@ -286,14 +165,11 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 }
             }
         }
-
         }
-#endif
 
         // ================= scheduler =================
         const unsigned m_step = __ballot_sync(FULL, stage == SG_STEP);
         const unsigned m_col = __ballot_sync(FULL, stage == SG_COLLIDE);
-        const unsigned m_pend = SPEC ? __ballot_sync(FULL, pending) : 0u;
         const unsigned m_nee = __ballot_sync(FULL, stage == SG_NEE);
         const unsigned m_scat = __ballot_sync(FULL, stage == SG_SCATTER);
         const unsigned m_fin = __ballot_sync(FULL, stage == SG_FINISH);
@@ -301,8 +177,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         const int n_step = __popc(m_step), n_col = __popc(m_col), n_nee = __popc(m_nee), n_scat = __popc(m_scat), n_fin = __popc(m_fin);
         constexpr int KF = TF ? VR_K_FINISH_TF : VR_K_FINISH;
         constexpr int K = TF ? VR_K_EVENT_TF : VR_K_EVENT, KC = TF ? VR_K_COLLIDE_TF : VR_K_COLLIDE, MIN_STEP = TF ? VR_MIN_STEP_TF : VR_MIN_STEP;
-        constexpr int KB = TF ? VR_K_BLOCKED_TF : VR_K_BLOCKED, KP = TF ? VR_K_PENDING_TF : VR_K_PENDING;
-        bool run_col = SPEC ? (n_col >= KB || __popc(m_pend) >= KP) : n_col >= KC;
+        bool run_col = n_col >= KC;
         bool run_nee = n_nee >= K, run_scat = n_scat >= K, run_fin = n_fin >= KF;
         if (!(run_col | run_nee | run_scat | run_fin)) {
             if (n_step >= MIN_STEP) continue;                  // keep stepping
@@ -314,64 +189,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         }
 
         // ================= COLLIDE: tentative collision (common.glsl:436-452 / 483-498) =================
-        if (SPEC) {
-            // resolves the outstanding collision of EVERY lane that holds one (parked or still stepping)
-            if (run_col && pending) {
-                cnt.dens();
-                pending = false;
-                uint32_t sd = seed_c;
-                const float3 at = ipos + t_c * idir;
-                float d;
-                float3 tf_rgb = f3(1.f);
-                if (TF) {
-                    const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * (MT::decoded ? density_trilinear_decoded(a.density, at) : density_trilinear(a.density, at)) * a.p.vol_inv_majorant);
-                    d = a.p.vol_majorant * rgba.w;
-                    tf_rgb = f3(rgba.x, rgba.y, rgba.z);
-                } else {
-                    const int3 tap = stochastic_tricubic_filter<MT>(at, sd);
-                    d = a.p.vol_density_scale * brick_value(a.density, tap.x, tap.y, tap.z);
-                }
-                bool real = false;
-                if (!shadow) {
-                    bool fetched;
-                    const float3 em = lookup_emission<MT>(a, at, sd, fetched);
-                    if (fetched) {
-                        cnt.emis();
-                        const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-                        LSET(LGET() + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant);
-                    }
-                    if (rng(sd) * maj_c < d) {               // real collision: the segment ends here (common.glsl:490-496)
-                        thr = thr * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-                        if (TF) thr = thr * tf_rgb;
-                        real = true;
-                        stage = SG_NEE;
-                    }
-                } else {
-                    if (rng(sd) * maj_c < d) {               // common.glsl:442-451
-                        real = true;
-                        stage = SG_STEP;
-                        Tr *= fmaxf(0.f, 1.f - MT::div(a.p.vol_majorant, maj_c));
-                        if (Tr < .1f) {
-                            const float prob = 1 - Tr;
-                            if (rng(sd) < prob) { Tr = 0.f; stage = SG_SCATTER; }   // absorbed: `return 0.f`, nothing is added to L
-                            else Tr = MT::div(Tr, 1 - prob);
-                        }
-                        if (stage == SG_STEP) {              // the shadow ray goes on from the collision with the shifted stream
-                            tau = -MT::log(1.f - rng(sd));
-                            mip = fmaxf(0.f, mip_c - 2.f);
-                        }
-                    }
-                }
-                if (real) {                                  // roll back to the collision: the speculative steps never happened
-                    t = t_c;
-                    seed = sd;
-                    cnt.spec_rollback();
-                } else if (stage == SG_COLLIDE) {            // confirmed null and the lane was parked behind it
-                    stage = SG_STEP;                         // at the ray's end: the next STEP pass finishes the ray
-                    if (second) speculate();                 // at another tentative collision: that one is outstanding now
-                }
-            }
-        } else if (run_col && stage == SG_COLLIDE) {
+        if (run_col && stage == SG_COLLIDE) {
             cnt.dens();
             stage = SG_STEP;
             const float3 at = ipos + t * idir;
@@ -392,7 +210,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 if (fetched) {
                     cnt.emis();
                     const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-                    LSET(LGET() + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant);
+                    L = L + thr * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant;
                 }
                 if (rng(seed) * majorant < d) {          // real collision: the segment ends here (common.glsl:490-496)
                     thr = thr * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
@@ -432,7 +250,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
                 const float mis_weight = a.p.show_environment > 0 ? MT::div(sqr(Le_pdf.w), sqr(Le_pdf.w) + sqr(f_p)) : 1.f;
                 // L += throughput * mis_weight * f_p * Tr * Le / pdf, with Tr applied when the shadow ray is done
                 const float3 c = thr * mis_weight * f_p * f3(Le_pdf.x, Le_pdf.y, Le_pdf.z);
-                PSET(f3(MT::div(c.x, Le_pdf.w), MT::div(c.y, Le_pdf.w), MT::div(c.z, Le_pdf.w)));
+                pend = f3(MT::div(c.x, Le_pdf.w), MT::div(c.y, Le_pdf.w), MT::div(c.z, Le_pdf.w));
                 Tr = 1.f;
                 shadow = true;
                 rd = w_i; start = true;
@@ -472,7 +290,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         if (run_fin) {     // warp-uniform: the block switch below is a warp-wide cooperative step
             const bool mine = stage == SG_FINISH;
             if (mine && have_item) {
-                float3 Lf = LGET();
+                float3 Lf = L;
                 if (escaped && a.p.show_environment > 0) {      // common.glsl:644-649
                     cnt.env();
                     const float3 Le = lookup_environment(a, dir);
@@ -544,7 +362,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
             if (mine && have_item) {
                 asm volatile("mov.u32 %0, %%clock;" : "=r"(t_item));
                 pos = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
-                thr = f3(1.f); LSET(f3(0.f)); n_paths = 0; f_p = 0.f;
+                thr = f3(1.f); L = f3(0.f); n_paths = 0; f_p = 0.f;
                 shadow = false; escaped = false;
                 rd = dir; start = true;
                 stage = SG_STEP;
@@ -570,10 +388,6 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
         }
     }
     flush_counters(a, cnt);
-#undef LGET
-#undef LSET
-#undef PGET
-#undef PSET
 }
 
 // Folds the samples of one launch into the colour buffer in sample order (pathtracer_brick.glsl:36):
@@ -585,7 +399,7 @@ __global__ void __launch_bounds__(VR_TRACE_BLOCK, VR_TRACE_MIN_BLOCKS) k_trace_p
 // majorant projects yields exactly (0, 0, 0, 0) for every sample, whatever the seed. One thread per brick marks the
 // tiles under the screen bounding rectangle of its 8 corners (+ 1 pixel); a brick with a corner beside or behind the
 // camera sets `info[1]` (mask unusable: every tile is live).
-__global__ void k_tile_mask(const __grid_constant__ TraceArgs a, const float* __restrict__ maj0, unsigned int* __restrict__ tile_live,
+VR_GLOBAL void k_tile_mask(const __grid_constant__ TraceArgs a, const float* __restrict__ maj0, unsigned int* __restrict__ tile_live,
                             unsigned int* __restrict__ info, int tiles_y) {
     const uint32_t nbx = a.density.nb.x, nby = a.density.nb.y, nbz = a.density.nb.z;
     const size_t n = size_t(nbx) * nby * nbz;
@@ -618,7 +432,7 @@ __global__ void k_tile_mask(const __grid_constant__ TraceArgs a, const float* __
 
 // sort keys of the tile slots: dead tiles 0 (they sort behind every live tile), live tiles max(cost, 1) (cost = 0 everywhere
 // when the view has not been measured yet: the stable sort keeps raster order); info[0] = number of live tiles
-__global__ void k_tile_keys(const unsigned int* __restrict__ tile_live, const unsigned int* __restrict__ cost, unsigned int* __restrict__ key,
+VR_GLOBAL void k_tile_keys(const unsigned int* __restrict__ tile_live, const unsigned int* __restrict__ cost, unsigned int* __restrict__ key,
                             unsigned int* __restrict__ info, int n_tiles) {
     const bool all_live = info[1] != 0u;
     unsigned int mine = 0;
@@ -634,7 +448,7 @@ __global__ void k_tile_keys(const unsigned int* __restrict__ tile_live, const un
 // Pixels of the region [x0, x1) x [y0, y1) outside the traced rectangle [tx0, tx1) x [ty0, ty1) were culled on the host (no
 // ray of theirs can reach the volume's box and the environment is hidden), pixels of dead tiles by k_tile_mask: each of
 // their samples is exactly (0, 0, 0, 0).
-__global__ void __launch_bounds__(256) k_fold(float4* __restrict__ color, const float4* __restrict__ lbuf, size_t lbuf_stride, int W, int x0, int y0, int x1, int y1,
+VR_GLOBAL void __launch_bounds__(256) k_fold(float4* __restrict__ color, const float4* __restrict__ lbuf, size_t lbuf_stride, int W, int x0, int y0, int x1, int y1,
                                               int tx0, int ty0, int tx1, int ty1, int first_sample, int n_samples, int accum_mode,
                                               const unsigned int* __restrict__ tile_live, const unsigned int* __restrict__ info, int tiles_x) {
     // block = 64 x 4 pixels (grid covers the region): coalesced 1 KiB rows, no integer division

@@ -1,0 +1,427 @@
+// Ray-pool tracking kernel (production path of vrb_trace since round 2).
+//
+// Per path it executes exactly the arithmetic and the random-number order of k_trace_persistent (vr_trace2.cuh) -- the images
+// are bit-identical -- but the lanes of a warp no longer OWN a ray. The lane-resident kernel ran its stages at 12-17 of 32
+// active lanes (profiles/r01_v11_trace_*_summary.txt: the other lanes were parked in a queue or idled through the rest of a
+// multi-step pass), and every threshold / occupancy / two-rays-per-lane variant ended within a few percent, because 32 rays
+// simply are asynchronous. Here every warp keeps a POOL of VR_POOL_SLOTS (64) path states in shared memory, struct-of-arrays
+// so that 32 lanes touching 32 different slots are (at worst two-way) bank-conflict free. One scheduler iteration
+//   1. reads the stage word of every slot and counts the slots per stage (ballots),
+//   2. picks the stage with the most waiting slots (STEP at once when it can fill the warp),
+//   3. hands the first 32 slots of that stage to the lanes (rank by popcount -> slot list in shared memory),
+//   4. runs that ONE stage: the lanes load just the fields the stage reads, run the same code as the lane-resident
+//      kernel, and store what changed. STEP keeps stepping its rays until fewer than VR_POOL_STEP_MIN of them are left or
+//      VR_POOL_MAX_STEPS steps were taken, so the 10 loads / 4 stores are paid once per several DDA steps.
+// A stage therefore runs with min(32, waiting slots) lanes instead of "whoever happens to be there".
+// Costs: ~25 instructions of scheduling per iteration, the loads/stores, and shared memory instead of registers as the
+// occupancy limit (36 words x 64 slots = 9 KiB per warp).
+// FINISH also regenerates: finished slots take the next samples of the warp's current block of 32 (tile, sample index)
+// exactly like the lane-resident kernel (all 32 lanes prepare a block together: TEA seed, jitter, view direction).
+#pragma once
+
+#include "vr_trace2.cuh"
+
+namespace vr {
+
+#ifndef VR_POOL_SLOTS
+#define VR_POOL_SLOTS 64          // path states per warp (multiple of 32)
+#endif
+#ifndef VR_POOL_WARPS
+#define VR_POOL_WARPS 4           // warps per CTA
+#endif
+#ifndef VR_POOL_MIN_BLOCKS
+#define VR_POOL_MIN_BLOCKS 5      // CTAs per SM the register allocation must allow (shared memory: 5 x 37.5 KiB at 64 slots)
+#endif
+#ifndef VR_POOL_MAX_STEPS
+#define VR_POOL_MAX_STEPS 8       // DDA steps per STEP visit at most
+#endif
+#ifndef VR_POOL_STEP_MIN
+#define VR_POOL_STEP_MIN 20       // leave the STEP loop when fewer of its rays are still stepping
+#endif
+#ifndef VR_POOL_STEP_FULL
+#define VR_POOL_STEP_FULL 32      // STEP runs at once when this many slots wait for it
+#endif
+
+// fields of a slot (one 32-bit word each; PF_COUNT words per slot)
+enum : int {
+    PF_STAGE = 0,   // stage | flags
+    PF_PIX, PF_SJ, PF_TILE, PF_TITEM, PF_SEED, PF_NPATHS,
+    PF_POS, PF_DIR = PF_POS + 3, PF_THR = PF_DIR + 3, PF_L = PF_THR + 3, PF_PEND = PF_L + 3,
+    PF_FP = PF_PEND + 3, PF_TR,
+    PF_IPOS, PF_IDIR = PF_IPOS + 3, PF_T = PF_IDIR + 3, PF_TFAR, PF_TAU, PF_MIP, PF_MAJ, PF_STEPS,
+    PF_COUNT
+};
+// flags in the stage word
+enum : uint32_t { PL_STAGE = 7u, PL_SHADOW = 8u, PL_ESCAPED = 16u, PL_ITEM = 32u, PL_LIT = 64u };
+
+constexpr size_t pool_warp_words() { return size_t(PF_COUNT) * VR_POOL_SLOTS + 32 /* slot list */ + 128 /* prepared block: 32 x float4 */; }
+constexpr size_t pool_smem_bytes() { return pool_warp_words() * 4 * VR_POOL_WARPS; }
+
+template <bool TF, bool COUNT, class MT>
+__global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trace_pool(const __grid_constant__ TraceArgs a) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int SL = VR_POOL_SLOTS, NS = VR_POOL_SLOTS / 32;
+    static_assert(VR_POOL_SLOTS % 32 == 0 && VR_POOL_SLOTS >= 32, "whole rows of 32 slots");
+    static_assert((pool_warp_words() * 4) % 16 == 0, "float4 alignment of the prepared block");
+    extern __shared__ float4 pool_smem[];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int W = a.p.resolution[0];
+    Cnt<COUNT> cnt;
+
+    float* sf = reinterpret_cast<float*>(pool_smem) + size_t(threadIdx.x >> 5) * pool_warp_words();
+    uint32_t* su = reinterpret_cast<uint32_t*>(sf);
+    uint32_t* sel = su + size_t(PF_COUNT) * SL;
+    float4* prep = reinterpret_cast<float4*>(sf + size_t(PF_COUNT) * SL + 32);
+#define PF(f, s) sf[(f) * SL + (s)]
+#define PU(f, s) su[(f) * SL + (s)]
+#define PLOAD3(f, s) f3(PF((f), s), PF((f) + 1, s), PF((f) + 2, s))
+#define PSTORE3(f, s, v) do { const float3 v_ = (v); PF((f), s) = v_.x; PF((f) + 1, s) = v_.y; PF((f) + 2, s) = v_.z; } while (0)
+
+#pragma unroll
+    for (int k = 0; k < NS; ++k) PU(PF_STAGE, k * 32 + lane) = SG_FINISH;      // every slot starts by asking for a sample
+
+    // ---- warp state: the current block of 32 samples (one tile, one sample index), prepared in shared memory ----
+    int blk_x0 = 0, blk_y0 = 0, blk_sj = 0;
+    int blk_next = 32;             // next sample of the block to hand out (>= 32: block used up)
+    bool blk_done = false;         // the counter is exhausted
+    unsigned nxt_block = 0;        // lane 0: id of the prefetched next block
+    if (lane == 0) nxt_block = atomicAdd(a.job_counter, 1u);
+    const unsigned n_jobs = a.n_live ? (__ldg(a.n_live) << a.sample_bits) : unsigned(a.n_jobs);
+
+    while (true) {
+        __syncwarp();
+        // ================= scheduler: count the slots per stage, pick one stage, hand its slots to the lanes =================
+        uint32_t st[NS];
+        unsigned bal[5][NS];
+        int n[5] = { 0, 0, 0, 0, 0 };
+#pragma unroll
+        for (int k = 0; k < NS; ++k) st[k] = PU(PF_STAGE, k * 32 + lane) & PL_STAGE;
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+#pragma unroll
+            for (int k = 0; k < NS; ++k) { bal[s][k] = __ballot_sync(FULL, st[k] == uint32_t(s)); n[s] += __popc(bal[s][k]); }
+        if ((n[0] | n[1] | n[2] | n[3] | n[4]) == 0) break;      // every slot idle
+        int S = SG_STEP;
+        if (n[SG_STEP] < VR_POOL_STEP_FULL) {
+            int best = n[SG_STEP];
+#pragma unroll
+            for (int s = 1; s < 5; ++s) if (n[s] > best) { best = n[s]; S = s; }
+        }
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            unsigned b = bal[0][k];
+#pragma unroll
+            for (int s = 1; s < 5; ++s) if (S == s) b = bal[s][k];
+            if (st[k] == uint32_t(S)) {
+                const int r = base + __popc(b & lt);
+                if (r < 32) sel[r] = uint32_t(k * 32 + lane);
+            }
+            base += __popc(b);
+        }
+        __syncwarp();
+        const bool act = lane < min(base, 32);
+        const int slot = act ? int(sel[lane]) : 0;
+
+        bool start = false;            // this lane starts a new ray from (spos, rd) with the stream `seed` below
+        float3 spos = f3(0.f), rd = f3(0.f, 0.f, -1.f);
+        uint32_t seed = 0, fl = 0;
+
+        if (S == SG_STEP) {
+            // ================= STEP: brick-DDA steps (common.glsl:423-435 / 470-482) =================
+            float3 ipos = f3(0.f), idir = f3(1.f), ri = f3(1.f);
+            float t = 0.f, tfar = -1.f, tau = 0.f, mip = 3.f, majorant = 0.f;
+            uint32_t steps = 0;
+            bool stepping = act;
+            int ns = SG_STEP;
+            if (act) {
+                fl = PU(PF_STAGE, slot);
+                ipos = PLOAD3(PF_IPOS, slot); idir = PLOAD3(PF_IDIR, slot);
+                t = PF(PF_T, slot); tfar = PF(PF_TFAR, slot); tau = PF(PF_TAU, slot); mip = PF(PF_MIP, slot);
+                steps = PU(PF_STEPS, slot);
+                ri = f3(MT::rcp(idir.x), MT::rcp(idir.y), MT::rcp(idir.z));
+            }
+#pragma unroll 1
+            for (int rep = 0; rep < VR_POOL_MAX_STEPS; ++rep) {
+                if (stepping) {
+                    if (t < tfar) {
+                        const float3 curr = ipos + t * idir;
+                        const int m = round_mip(mip);
+                        cnt.maj();
+                        majorant = table_majorant(a, curr, m);
+                        const float dt = step_dda(curr, ri, m);
+                        t += dt;
+                        tau -= majorant * dt;
+                        mip = fminf(mip + 0.25f, 3.f);
+                        if (!(tau > 0.f)) {
+                            t += MT::div(tau, majorant);
+                            if (!(t >= tfar)) { ns = SG_COLLIDE; stepping = false; }   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
+                        }
+                        if (++steps > uint32_t(MAX_RAY_STEPS)) { t = INFINITY; ns = SG_STEP; stepping = true; }
+                    }
+                    if (stepping && !(t < tfar)) {       // the ray left the volume
+                        stepping = false;
+                        ns = (fl & PL_SHADOW) ? SG_SCATTER : SG_FINISH;
+                    }
+                }
+                if (__popc(__ballot_sync(FULL, stepping)) < VR_POOL_STEP_MIN) break;
+            }
+            if (act) {
+                PF(PF_T, slot) = t; PF(PF_TAU, slot) = tau; PF(PF_MIP, slot) = mip;
+                PU(PF_STEPS, slot) = steps;
+                if (ns == SG_COLLIDE) PF(PF_MAJ, slot) = majorant;
+                if (ns != SG_STEP) {
+                    uint32_t f = (fl & ~(PL_STAGE | PL_LIT | PL_ESCAPED)) | uint32_t(ns);
+                    if (ns == SG_SCATTER) f |= PL_LIT;           // shadow ray got through: SCATTER adds pend * Tr first
+                    if (ns == SG_FINISH) f |= PL_ESCAPED;        // camera segment left the volume: environment on escape
+                    PU(PF_STAGE, slot) = f;
+                }
+            }
+        } else if (S == SG_COLLIDE) {
+            // ================= COLLIDE: tentative collision (common.glsl:436-452 / 483-498) =================
+            if (act) {
+                cnt.dens();
+                fl = PU(PF_STAGE, slot);
+                const bool shadow = (fl & PL_SHADOW) != 0u;
+                const float t = PF(PF_T, slot), majorant = PF(PF_MAJ, slot);
+                seed = PU(PF_SEED, slot);
+                const float3 at = PLOAD3(PF_IPOS, slot) + t * PLOAD3(PF_IDIR, slot);
+                int ns = SG_STEP;
+                float d;
+                float3 tf_rgb = f3(1.f);
+                if (TF) {
+                    const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * (MT::decoded ? density_trilinear_decoded(a.density, at) : density_trilinear(a.density, at)) * a.p.vol_inv_majorant);
+                    d = a.p.vol_majorant * rgba.w;
+                    tf_rgb = f3(rgba.x, rgba.y, rgba.z);
+                } else {
+                    const int3 tap = stochastic_tricubic_filter<MT>(at, seed);
+                    d = a.p.vol_density_scale * ((MT::decoded && VR_DECODED_TAP) ? decoded_value(a.density, tap.x, tap.y, tap.z) : brick_value(a.density, tap.x, tap.y, tap.z));
+                }
+                if (!shadow) {
+                    bool fetched;
+                    const float3 em = lookup_emission<MT>(a, at, seed, fetched);
+                    if (fetched) {
+                        cnt.emis();
+                        const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                        PSTORE3(PF_L, slot, PLOAD3(PF_L, slot) + PLOAD3(PF_THR, slot) * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant);
+                    }
+                    if (rng(seed) * majorant < d) {          // real collision: the segment ends here (common.glsl:490-496)
+                        float3 thr = PLOAD3(PF_THR, slot) * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                        if (TF) thr = thr * tf_rgb;
+                        PSTORE3(PF_THR, slot, thr);
+                        ns = SG_NEE;
+                    }
+                } else {
+                    if (rng(seed) * majorant < d) {          // common.glsl:442-450
+                        float Tr = PF(PF_TR, slot);
+                        Tr *= fmaxf(0.f, 1.f - MT::div(a.p.vol_majorant, majorant));
+                        if (Tr < .1f) {
+                            const float prob = 1 - Tr;
+                            if (rng(seed) < prob) { Tr = 0.f; ns = SG_SCATTER; }   // absorbed: `return 0.f`, nothing is added to L
+                            else Tr = MT::div(Tr, 1 - prob);
+                        }
+                        PF(PF_TR, slot) = Tr;
+                    }
+                }
+                if (ns == SG_STEP) {
+                    PF(PF_TAU, slot) = -MT::log(1.f - rng(seed));
+                    PF(PF_MIP, slot) = fmaxf(0.f, PF(PF_MIP, slot) - 2.f);
+                }
+                PU(PF_SEED, slot) = seed;
+                PU(PF_STAGE, slot) = (fl & ~(PL_STAGE | PL_LIT)) | uint32_t(ns);
+            }
+        } else if (S == SG_NEE) {
+            // ================= NEE: real collision -> next-event estimation (common.glsl:611-626) =================
+            if (act) {
+                cnt.real();
+                fl = PU(PF_STAGE, slot);
+                seed = PU(PF_SEED, slot);
+                const float3 dir = PLOAD3(PF_DIR, slot);
+                spos = PLOAD3(PF_POS, slot) + PF(PF_T, slot) * dir;
+                PSTORE3(PF_POS, slot, spos);
+                float3 w_i;
+                const float r0 = rng(seed), r1 = rng(seed);
+                cnt.nee();
+                const float4 Le_pdf = sample_environment<MT>(a, r0, r1, w_i);
+                if (Le_pdf.w > 0) {
+                    const float f_p = phase_hg<MT>(dot(-dir, w_i), a.p.vol_phase_g);
+                    const float mis_weight = a.p.show_environment > 0 ? MT::div(sqr(Le_pdf.w), sqr(Le_pdf.w) + sqr(f_p)) : 1.f;
+                    // L += throughput * mis_weight * f_p * Tr * Le / pdf, with Tr applied when the shadow ray is done
+                    const float3 c = PLOAD3(PF_THR, slot) * mis_weight * f_p * f3(Le_pdf.x, Le_pdf.y, Le_pdf.z);
+                    PSTORE3(PF_PEND, slot, f3(MT::div(c.x, Le_pdf.w), MT::div(c.y, Le_pdf.w), MT::div(c.z, Le_pdf.w)));
+                    PF(PF_FP, slot) = f_p;
+                    PF(PF_TR, slot) = 1.f;
+                    fl = (fl & ~(PL_STAGE | PL_LIT)) | PL_SHADOW | uint32_t(SG_STEP);
+                    rd = w_i; start = true;
+                } else {
+                    PU(PF_SEED, slot) = seed;
+                    fl = (fl & ~(PL_STAGE | PL_LIT)) | uint32_t(SG_SCATTER);
+                }
+                PU(PF_STAGE, slot) = fl;
+            }
+        } else if (S == SG_SCATTER) {
+            // ================= SCATTER: bounce limit, Russian roulette, phase sampling (common.glsl:628-641) =================
+            if (act) {
+                fl = PU(PF_STAGE, slot);
+                if (fl & PL_LIT) {                               // the shadow ray reached the environment (deferred from STEP)
+                    const float Tr = PF(PF_TR, slot);
+                    if (Tr != 0.f) PSTORE3(PF_L, slot, PLOAD3(PF_L, slot) + PLOAD3(PF_PEND, slot) * Tr);     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
+                }
+                seed = PU(PF_SEED, slot);
+                uint32_t n_paths = PU(PF_NPATHS, slot);
+                bool end = false;
+                if (++n_paths >= uint32_t(a.p.bounces)) end = true;
+                else {
+                    float3 thr = PLOAD3(PF_THR, slot);
+                    const float rr_val = luma(thr);
+                    if (rr_val < .1f) {
+                        const float prob = 1 - rr_val;
+                        if (rng(seed) < prob) end = true;
+                        else { const float k = 1 - prob; PSTORE3(PF_THR, slot, f3(MT::div(thr.x, k), MT::div(thr.y, k), MT::div(thr.z, k))); }
+                    }
+                }
+                PU(PF_NPATHS, slot) = n_paths;
+                if (end) {
+                    PU(PF_SEED, slot) = seed;
+                    fl = (fl & ~(PL_STAGE | PL_LIT | PL_ESCAPED | PL_SHADOW)) | uint32_t(SG_FINISH);
+                } else {
+                    const float3 dir = PLOAD3(PF_DIR, slot);
+                    const float s0 = rng(seed), s1 = rng(seed);
+                    const float3 scatter_dir = sample_phase_hg<MT>(dir, a.p.vol_phase_g, s0, s1);
+                    PF(PF_FP, slot) = phase_hg<MT>(dot(-dir, scatter_dir), a.p.vol_phase_g);
+                    PSTORE3(PF_DIR, slot, scatter_dir);
+                    fl = (fl & ~(PL_STAGE | PL_LIT | PL_SHADOW)) | uint32_t(SG_STEP);
+                    spos = PLOAD3(PF_POS, slot);
+                    rd = scatter_dir; start = true;
+                }
+                PU(PF_STAGE, slot) = fl;
+            }
+        } else {
+            // ================= FINISH: environment on escape, store the sample, take the next one =================
+            bool want = act;
+            if (act) {
+                fl = PU(PF_STAGE, slot);
+                if (fl & PL_ITEM) {
+                    float3 Lf = PLOAD3(PF_L, slot);
+                    const uint32_t n_paths = PU(PF_NPATHS, slot);
+                    if ((fl & PL_ESCAPED) && a.p.show_environment > 0) {      // common.glsl:644-649
+                        cnt.env();
+                        const float3 Le = lookup_environment(a, PLOAD3(PF_DIR, slot));
+                        const float pe = pdf_environment<MT>(a, Le);
+                        const float f_p = PF(PF_FP, slot);
+                        const float mis_weight = n_paths > 0 ? MT::div(sqr(f_p), sqr(f_p) + sqr(pe)) : 1.f;
+                        Lf = Lf + PLOAD3(PF_THR, slot) * mis_weight * Le;
+                    }
+                    cnt.samp();                                     // pathtracer_brick.glsl:36: sanitize(L), folded by k_fold
+                    const uint32_t sj = PU(PF_SJ, slot);
+                    VR_LBUF_STORE(a.lbuf + size_t(sj) * a.lbuf_stride + PU(PF_PIX, slot),
+                                  make_float4(sanitize(Lf.x), sanitize(Lf.y), sanitize(Lf.z), sanitize(fminf(float(n_paths), 1.f))));
+                    const uint32_t tile = PU(PF_TILE, slot);
+                    if (a.tile_cost && !(tile & 0x80000000u)) {     // a dithered quarter of the samples is enough to rank tiles
+                        unsigned now;
+                        asm volatile("mov.u32 %0, %%clock;" : "=r"(now));
+                        atomicAdd(a.tile_cost + tile, (now - PU(PF_TITEM, slot)) >> 8);
+                    }
+                }
+            }
+            int px = 0, py = 0;
+            bool have_item = false;
+            float3 dir = f3(0.f, 0.f, -1.f);
+            while (true) {
+                const unsigned m_want = __ballot_sync(FULL, want);
+                if (m_want == 0u) break;
+                if (blk_next >= 32) {                              // warp-uniform: switch to the prefetched block
+                    unsigned b = 0xffffffffu;
+                    if (!blk_done) {
+                        b = __shfl_sync(FULL, nxt_block, 0);
+                        if (lane == 0) nxt_block = atomicAdd(a.job_counter, 1u);
+                    }
+                    if (b >= n_jobs) {                             // no blocks left
+                        blk_done = true;
+                        want = false;
+                        break;
+                    }
+                    // tile-major: the blocks of a tile slot are consecutive (sample index in the low bits); the slot's tile
+                    // comes from the order array (natural or heaviest-first), packed as (tile y << 16 | tile x)
+                    blk_sj = int(b & ((1u << a.sample_bits) - 1u));
+                    if (blk_sj >= a.n_samples) continue;           // padding of a non-power-of-two sample count
+                    const unsigned txy = __ldg(a.tile_order + (b >> a.sample_bits));
+                    blk_x0 = a.x0 + int(txy & 0xffffu) * 8;
+                    blk_y0 = a.y0 + int(txy >> 16) * 4;
+                    const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
+                    // all 32 lanes prepare the block: lane i seeds sample (pixel i of the tile, sample blk_sj)
+                    // (pathtracer_brick.glsl:28-30: TEA seed, two jitter draws, view direction)
+                    uint32_t sd = tea32(uint32_t(a.p.seed) * uint32_t(iy * W + ix), uint32_t(a.first_sample + blk_sj));
+                    const float jx = rng(sd), jy = rng(sd);
+                    const float3 vd = view_dir<MT>(a, ix, iy, jx, jy);
+                    __syncwarp();
+                    prep[lane] = make_float4(vd.x, vd.y, vd.z, __uint_as_float(sd));
+                    __syncwarp();
+                    blk_next = 0;
+                }
+                // the r-th wanting lane takes the r-th remaining sample of the block (samples of a border tile that fall
+                // outside the image are dropped and the lane asks again)
+                const int i = blk_next + __popc(m_want & lt);
+                if (want && i < 32) {
+                    px = blk_x0 + (i & 7);
+                    py = blk_y0 + (i >> 3);
+                    if (px < a.x1 && py < a.y1) {
+                        const float4 pr = prep[i];
+                        seed = __float_as_uint(pr.w);
+                        dir = f3(pr.x, pr.y, pr.z);
+                        have_item = true;
+                        want = false;
+                    }
+                }
+                blk_next += __popc(m_want);
+            }
+            if (act) {
+                if (have_item) {                                   // new sample: camera ray of the prepared sample
+                    unsigned now;
+                    asm volatile("mov.u32 %0, %%clock;" : "=r"(now));
+                    PU(PF_TITEM, slot) = now;
+                    PU(PF_PIX, slot) = uint32_t(py) * uint32_t(W) + uint32_t(px);
+                    PU(PF_SJ, slot) = uint32_t(blk_sj);
+                    PU(PF_TILE, slot) = (((px ^ py ^ blk_sj) & 3) == 0 ? 0u : 0x80000000u) | uint32_t(((py - a.y0) >> 2) * a.tiles_x + ((px - a.x0) >> 3));
+                    PU(PF_NPATHS, slot) = 0u;
+                    spos = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
+                    PSTORE3(PF_POS, slot, spos);
+                    PSTORE3(PF_DIR, slot, dir);
+                    PSTORE3(PF_THR, slot, f3(1.f));
+                    PSTORE3(PF_L, slot, f3(0.f));
+                    PF(PF_FP, slot) = 0.f;
+                    PU(PF_STAGE, slot) = PL_ITEM | uint32_t(SG_STEP);
+                    rd = dir; start = true;
+                } else {
+                    PU(PF_STAGE, slot) = uint32_t(SG_IDLE);        // the counter is exhausted
+                }
+            }
+        }
+
+        // ================= start the new rays: clip + world->index + first free-flight draw (common.glsl:459-468 / 413-421) =================
+        if (start) {
+            float tn, tf;
+            PU(PF_STEPS, slot) = 0u;
+            if (intersect_box<MT>(spos, rd, a.p.vol_bb_min, a.p.vol_bb_max, tn, tf)) {
+                const Mat4& M = *reinterpret_cast<const Mat4*>(a.p.vol_density_inv_transform);
+                PSTORE3(PF_IPOS, slot, mul_point(M, spos));
+                PSTORE3(PF_IDIR, slot, mul_dir(M, rd));
+                PF(PF_T, slot) = tn + 1e-6f;
+                PF(PF_TFAR, slot) = tf;
+                PF(PF_TAU, slot) = -MT::log(1.f - rng(seed));
+                PF(PF_MIP, slot) = 3.f;
+            } else {
+                PF(PF_T, slot) = 0.f; PF(PF_TFAR, slot) = -1.f;   // missed the box: the ray "ends" at once (Tr = 1 / escape)
+            }
+            PU(PF_SEED, slot) = seed;
+        }
+    }
+    flush_counters(a, cnt);
+#undef PF
+#undef PU
+#undef PLOAD3
+#undef PSTORE3
+}
+
+}  // namespace vr

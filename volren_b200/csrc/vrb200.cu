@@ -8,7 +8,7 @@
 #include "vr_env.cuh"
 #include "vr_trace.cuh"
 #include "vr_trace2.cuh"
-#include "vr_trace3.cuh"
+#include "vr_trace_pool.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -24,6 +24,11 @@
 #include <vector>
 
 using namespace vr;
+
+namespace vr {   // vrb200_strict.cu (-fmad=false): the IEEE cross-check kernels
+cudaError_t launch_trace_pixels(const TraceArgs& a, bool tf, bool count, dim3 grid, cudaStream_t stream);
+const void* strict_persistent_kernel(bool tf, bool count);
+}
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -448,7 +453,7 @@ int vrb_create(int device, vrb_ctx** out) {
     if (const char* e = getenv("VRB200_LPT")) ctx->lpt = atoi(e) != 0;
     if (const char* e = getenv("VRB200_CULL")) ctx->cull = atoi(e) != 0;
     if (const char* e = getenv("VRB200_PASS")) ctx->pass_samples = std::max(1, atoi(e));
-    if (const char* e = getenv("VRB200_KERNEL")) ctx->kernel = std::min(4, std::max(0, atoi(e)));
+    if (const char* e = getenv("VRB200_KERNEL")) ctx->kernel = std::min(3, std::max(0, atoi(e)));
     cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream);
     *out = ctx;
     return VRB_OK;
@@ -999,14 +1004,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     const bool tf = params->use_transferfunc != 0;
     if (ctx->kernel == 1) {   // cross-check kernel: one thread per pixel, no regeneration
         const dim3 grid((a.x1 - a.x0 + 15) / 16, (a.y1 - a.y0 + 15) / 16);
-        if (ctx->counting) {
-            if (tf) k_trace_pixels<true, true><<<grid, 256, 0, ctx->stream>>>(a);
-            else k_trace_pixels<false, true><<<grid, 256, 0, ctx->stream>>>(a);
-        } else {
-            if (tf) k_trace_pixels<true, false><<<grid, 256, 0, ctx->stream>>>(a);
-            else k_trace_pixels<false, false><<<grid, 256, 0, ctx->stream>>>(a);
-        }
-        CK_LAUNCH();
+        CK(launch_trace_pixels(a, tf, ctx->counting, grid, ctx->stream));
         return VRB_OK;
     }
     // ---- production path: persistent kernel ----
@@ -1091,7 +1089,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     a.tiles_x = std::max(1, (a.x1 - a.x0 + 7) / 8);
     const int n_tiles = std::max(1, a.tiles_x * ((a.y1 - a.y0 + 3) / 4));
     // ---- heaviest tiles first: order the blocks by the per-tile cost the previous launch of this view measured ----
-    const bool lpt = ctx->lpt && !ctx->counting && (ctx->kernel == 0 || ctx->kernel == 3);
+    const bool lpt = ctx->lpt && !ctx->counting && (ctx->kernel == 0 || ctx->kernel == 3);    // the fast-math production schedules
     uint64_t vkey = key;
     if (a.tiles_x >= 65536 || n_tiles / a.tiles_x >= 65536) return fail(ctx, VRB_ERR_INVALID, "image too large");
     {
@@ -1125,30 +1123,31 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             ctx->tile_coords_tx = a.tiles_x;
         }
     }
-    const bool duo = ctx->kernel == 3 || ctx->kernel == 4;
-    const int variant = (tf ? 1 : 0) | (ctx->counting ? 2 : 0) | ((ctx->kernel == 2 || ctx->kernel == 4) ? 4 : 0) | (duo ? 8 : 0);
+    // kernel kinds on this path: 0 = ray-pool kernel (production), 2 = lane-resident kernel with IEEE math (cross-check,
+    // vrb200_strict.cu), 3 = lane-resident kernel with fast math (round 1's production schedule, kept for A/B runs)
+    const bool pool = ctx->kernel == 0;
+    const int variant = (tf ? 1 : 0) | (ctx->counting ? 2 : 0) | (ctx->kernel == 2 ? 4 : 0) | (pool ? 8 : 0);
     const void* fn = nullptr;
     switch (variant) {
-        case 8: fn = (const void*)k_trace_duo<false, false, FastMath>; break;
-        case 9: fn = (const void*)k_trace_duo<true, false, FastMath>; break;
-        case 10: fn = (const void*)k_trace_duo<false, true, FastMath>; break;
-        case 11: fn = (const void*)k_trace_duo<true, true, FastMath>; break;
-        case 12: fn = (const void*)k_trace_duo<false, false, StrictMath>; break;
-        case 13: fn = (const void*)k_trace_duo<true, false, StrictMath>; break;
-        case 14: fn = (const void*)k_trace_duo<false, true, StrictMath>; break;
-        case 15: fn = (const void*)k_trace_duo<true, true, StrictMath>; break;
+        case 8: fn = (const void*)k_trace_pool<false, false, FastMath>; break;
+        case 9: fn = (const void*)k_trace_pool<true, false, FastMath>; break;
+        case 10: fn = (const void*)k_trace_pool<false, true, FastMath>; break;
+        case 11: fn = (const void*)k_trace_pool<true, true, FastMath>; break;
         case 0: fn = (const void*)k_trace_persistent<false, false, FastMath>; break;
         case 1: fn = (const void*)k_trace_persistent<true, false, FastMath>; break;
         case 2: fn = (const void*)k_trace_persistent<false, true, FastMath>; break;
         case 3: fn = (const void*)k_trace_persistent<true, true, FastMath>; break;
-        case 4: fn = (const void*)k_trace_persistent<false, false, StrictMath>; break;
-        case 5: fn = (const void*)k_trace_persistent<true, false, StrictMath>; break;
-        case 6: fn = (const void*)k_trace_persistent<false, true, StrictMath>; break;
-        default: fn = (const void*)k_trace_persistent<true, true, StrictMath>; break;
+        default: fn = strict_persistent_kernel(tf, ctx->counting); break;
     }
+    const int block_threads = pool ? VR_POOL_WARPS * 32 : VR_TRACE_BLOCK;
+    const size_t dyn_smem = pool ? pool_smem_bytes() : 0;
     if (!ctx->trace_blocks[variant]) {
+        if (pool) {
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, VR_TRACE_BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block_threads, dyn_smem));
         ctx->trace_blocks[variant] = ctx->sm_count * (per_sm > 0 ? per_sm : 1);   // one resident wave: grid = 148 x blocks/SM
     }
     const int first_end = first_sample + n_samples;
@@ -1203,10 +1202,11 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, ctx->stream));
             a.tile_cost = ctx->tile_cost;
         }
-        const int needed = (n_tiles * a.n_samples + (VR_TRACE_BLOCK / 32) - 1) / (VR_TRACE_BLOCK / 32);
+        const int per_block = pool ? VR_POOL_WARPS * (VR_POOL_SLOTS / 32) : VR_TRACE_BLOCK / 32;     // blocks of 32 samples one CTA holds at a time
+        const int needed = (n_tiles * a.n_samples + per_block - 1) / per_block;
         const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
         void* kargs[] = { (void*)&a };
-        CK(cudaLaunchKernel(fn, dim3(blocks), dim3(VR_TRACE_BLOCK), kargs, 0, ctx->stream));
+        CK(cudaLaunchKernel(fn, dim3(blocks), dim3(block_threads), kargs, dyn_smem, ctx->stream));
         ctx->trace_launches += 2;          // the tracking kernel + k_fold below
         k_fold<<<dim3((fold_x1 - fold_x0 + 63) / 64, (fold_y1 - fold_y0 + 3) / 4), 256, 0, ctx->stream>>>(
             ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode,
@@ -1238,7 +1238,7 @@ int vrb_get_stat(vrb_ctx* ctx, const char* name, uint64_t* out) {
 
 int vrb_set_kernel(vrb_ctx* ctx, int kind) {
     if (!ctx) return VRB_ERR_INVALID;
-    if (kind < 0 || kind > 4) return fail(ctx, VRB_ERR_INVALID, "kernel kind must be 0 (persistent, fast math), 1 (simple, strict math), 2 (persistent, strict math), 3 (two rays per lane, fast math) or 4 (two rays per lane, strict math)");
+    if (kind < 0 || kind > 3) return fail(ctx, VRB_ERR_INVALID, "kernel kind must be 0 (ray pool, fast math), 1 (one thread per pixel, IEEE math), 2 (lane-resident persistent, IEEE math) or 3 (lane-resident persistent, fast math)");
     ctx->kernel = kind;
     return VRB_OK;
 }

@@ -144,6 +144,13 @@ void bind_volpy(py::module_& m) {
         .def_readwrite("window_left", &TransferFunction::window_left)
         .def_readwrite("window_width", &TransferFunction::window_width)
         .def_readonly("lut", &TransferFunction::lut);
+    // test hook (not part of the reference surface): the LUT of TransferFunction::colormap(type, n_bins) -- what `--turbo` /
+    // `--viridis` upload (main.cpp:385-392); type = index into tinycolormap::ColormapType
+    m.def("_colormap_lut", [](int type, size_t n_bins) {
+        TransferFunction tf;
+        tf.colormap(static_cast<colormap::ColormapType>(type), n_bins);
+        return tf.lut;
+    }, py::arg("type"), py::arg("n_bins") = 256);
 
     // ---- renderer (bindings.cpp:118-209) ----
     py::class_<RendererOpenGL, std::shared_ptr<RendererOpenGL>>(m, "Renderer")

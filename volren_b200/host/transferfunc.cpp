@@ -1,6 +1,7 @@
 #include "transferfunc.h"
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <filesystem>
@@ -13,29 +14,57 @@ using vmath::vec4;
 
 namespace colormap {
 
-// Turbo: A. Mikhailov's polynomial fit (Google, Apache-2.0); Viridis: M. Zucker's degree-6 fit (public domain).
-// The reference samples tinycolormap's 256-entry tables; these fits stay within ~1e-2 of them in the interior.
-vec3 GetColor(float x, ColormapType type) {
-    x = std::fmin(std::fmax(x, 0.f), 1.f);
-    auto sat = [](float v) { return std::fmin(std::fmax(v, 0.f), 1.f); };
+#include "colormap_tables.inc"
+
+// tinycolormap::GetColor (tinycolormap.hpp:200-237) in double precision, as TransferFunction::colormap calls it
+// (reference src/transferfunc.cpp:69-77). Table maps: internal::CalcLerp (:160-170) -- a = clamp01(x) * (N - 1),
+// (1 - t) * data[floor(a)] + t * data[ceil(a)]; Hot and Gray are closed forms (:806-834).
+static void lerp_table(double x, const unsigned int* data, size_t n, double out[3]) {
+    const double xc = (x < 0.0) ? 0.0 : (x > 1.0) ? 1.0 : x;
+    const double a = xc * double(n - 1);
+    const double i = std::floor(a);
+    const double t = a - i;
+    const unsigned int* c0 = data + 3 * static_cast<size_t>(i);
+    const unsigned int* c1 = data + 3 * static_cast<size_t>(std::ceil(a));
+    for (int k = 0; k < 3; ++k) out[k] = (1.0 - t) * (double(c0[k]) / 1e6) + t * (double(c1[k]) / 1e6);
+}
+
+void GetColor(double x, ColormapType type, double out[3]) {
+#define VR_TABLE(name) lerp_table(x, colormap_##name, sizeof(colormap_##name) / sizeof(unsigned int) / 3, out); return
     switch (type) {
-        case ColormapType::Turbo: {
-            const float x2 = x * x, x3 = x2 * x, x4 = x2 * x2, x5 = x4 * x;
-            return vec3(sat(0.13572138f + 4.61539260f * x - 42.66032258f * x2 + 132.13108234f * x3 - 152.94239396f * x4 + 59.28637943f * x5),
-                        sat(0.09140261f + 2.19418839f * x + 4.84296658f * x2 - 14.18503333f * x3 + 4.27729857f * x4 + 2.82956604f * x5),
-                        sat(0.10667330f + 12.64194608f * x - 60.58204836f * x2 + 110.36276771f * x3 - 89.90310912f * x4 + 27.34824973f * x5));
+        case ColormapType::Parula: VR_TABLE(parula);
+        case ColormapType::Heat: VR_TABLE(heat);
+        case ColormapType::Jet: VR_TABLE(jet);
+        case ColormapType::Turbo: VR_TABLE(turbo);
+        case ColormapType::Magma: VR_TABLE(magma);
+        case ColormapType::Inferno: VR_TABLE(inferno);
+        case ColormapType::Plasma: VR_TABLE(plasma);
+        case ColormapType::Viridis: VR_TABLE(viridis);
+        case ColormapType::Cividis: VR_TABLE(cividis);
+        case ColormapType::Github: VR_TABLE(github);
+        case ColormapType::Cubehelix: VR_TABLE(cubehelix);
+        case ColormapType::HSV: VR_TABLE(hsv);
+        case ColormapType::Hot: {
+            const double xc = (x < 0.0) ? 0.0 : (x > 1.0) ? 1.0 : x;
+            if (xc < 0.4) { out[0] = xc / 0.4 * 1.0; out[1] = xc / 0.4 * 0.0; out[2] = xc / 0.4 * 0.0; }
+            else if (xc < 0.8) { const double t = (xc - 0.4) / (0.8 - 0.4); out[0] = 1.0 + t * 0.0; out[1] = 0.0 + t * 1.0; out[2] = 0.0 + t * 0.0; }
+            else { const double t = (xc - 0.8) / (1.0 - 0.8); out[0] = 1.0 + 0.0 + t * 0.0; out[1] = 0.0 + 1.0 + t * 0.0; out[2] = 0.0 + 0.0 + t * 1.0; }
+            return;
         }
-        case ColormapType::Viridis: {
-            const vec3 c0(0.2777273272234177f, 0.005407344544966578f, 0.3340998053353061f), c1(0.1050930431085774f, 1.404613529898575f, 1.384590162594685f),
-                c2(-0.3308618287255563f, 0.214847559468213f, 0.09509516302823659f), c3(-4.634230498983486f, -5.799100973351585f, -19.33244095627987f),
-                c4(6.228269936347081f, 14.17993336680509f, 56.69055260068105f), c5(4.776384997670288f, -13.74514537774601f, -65.35303263337234f),
-                c6(-5.435455855934631f, 4.645852612178535f, 26.3124352495832f);
-            const vec3 c = c0 + x * (c1 + x * (c2 + x * (c3 + x * (c4 + x * (c5 + x * c6)))));
-            return vec3(sat(c.x), sat(c.y), sat(c.z));
+        case ColormapType::Gray: {
+            const double xc = (x < 0.0) ? 0.0 : (x > 1.0) ? 1.0 : x;
+            out[0] = out[1] = out[2] = 1.0 - xc;
+            return;
         }
-        case ColormapType::Heat: return vec3(sat(3.f * x), sat(3.f * x - 1.f), sat(3.f * x - 2.f));
-        default: return vec3(x);
     }
+#undef VR_TABLE
+    throw std::invalid_argument("unknown ColormapType");
+}
+
+vec3 GetColor(float x, ColormapType type) {
+    double c[3];
+    GetColor(double(x), type, c);
+    return vec3(float(c[0]), float(c[1]), float(c[2]));
 }
 
 }  // namespace colormap

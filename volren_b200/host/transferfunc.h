@@ -10,8 +10,11 @@
 #include "vmath.h"
 
 namespace colormap {
-enum class ColormapType { Turbo, Viridis, Heat, Gray };
-vmath::vec3 GetColor(float x, ColormapType type);   // polynomial fits of the published maps (see transferfunc.cpp)
+// tinycolormap::ColormapType, same names and order (tinycolormap.hpp:78-81)
+enum class ColormapType { Parula, Heat, Jet, Turbo, Hot, Gray, Magma, Inferno, Plasma, Viridis, Cividis, Github, Cubehelix, HSV };
+// tinycolormap::GetColor: exact tables / closed forms, double precision (transferfunc.cpp; tables in colormap_tables.inc)
+void GetColor(double x, ColormapType type, double out[3]);
+vmath::vec3 GetColor(float x, ColormapType type);
 }  // namespace colormap
 
 class TransferFunction {
