@@ -1,24 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- path samples/s of the B200 volume path tracer on BASELINE.json's metric config.
+"""bench.py -- path samples/s of the B200 volume path tracer on BASELINE.json's configs.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--configs C1,C3,C4,C5 | none]
 
-Workload at every N: BASELINE.json configs[1] -- data/smoke.brick + data/lut.txt transfer function
-(pathtracer_brick_tf), 1920x1080, 128 bounces. One "step" = one batch of --spp-per-step samples for every
-pixel (the full config is 1024 spp = 1024/spp-per-step such steps; samples are independent).
-N > 1: spp-sliced weak scaling -- every rank traces its own --spp-per-step slice of sample indices for all
-pixels into a SUM buffer, the float4 buffers are reduced to rank 0 with NCCL (the one real exchange step).
+Headline workload at every N: BASELINE.json configs[1] (C2) -- data/smoke.brick + data/lut.txt transfer function
+(pathtracer_brick_tf), 1920x1080, 128 bounces, 1024 spp. One STEP = one full frame of the config on every GPU
+(--spp-per-step = 1024 samples per pixel and rank; internally 32 launches of the tracking kernel + fold of 32 spp each).
 
-value  : whole-job samples/s with volume/env/LUT resident in HBM (CUDA events around the K steps, max over ranks)
-e2e    : same metric through the C ABI with HOST buffers: per step the brick grid, environment and LUT are
-         uploaded from pinned host memory, traced, and the RGBA32F image is read back (H2D/D2H inside the timed region);
-         steps rotate over four contexts with asynchronous uploads so that read-backs, uploads and traces overlap
-roofline: algorithmic bytes (event counters x per-event bytes) / kernel time vs the measured HBM peak
-cpu_baseline: the CPU oracle (port of the reference shaders) on a bounded sample of the same workload
+value     whole-job samples/s with volume/env/LUT resident in HBM: CUDA events around the K steps, max over ranks.
+          N > 1: weak scaling -- every rank traces its own 1024-spp slice of sample indices of an N*1024-spp frame into a SUM
+          buffer and EVERY step ends with the one exchange of the path, the NCCL reduce(SUM) of the float4 images to rank 0
+          (inside the timed region; its own duration is reported as collective_ms).
+e2e       the same metric through the C ABI with HOST buffers: per step (= per frame) the brick grid, environment and LUT are
+          uploaded from pinned host memory, the frame is traced and the RGBA32F image is read back, all inside the timed region.
+roofline  headline kernel (C2 is L2-resident by nature: 27 MB working set): EXECUTED algorithmic bytes (event counters of the
+          launch the timed region runs) / kernel time against the L2 random-sector-gather ceiling measured in
+          this run (vrb_probe_bandwidth); the HBM numbers are next to it. C3 / C4 (HBM-resident atlases) report against HBM.
+configs   C1, C3, C4 (samples/s, roofline, counters) and C5 (frames/s) measured in the same run; at N > 1 they are split the way
+          BASELINE.json names (spp slices + reduce per frame for C1/C3/C4, frames dealt to the ranks for C5): strong scaling.
+strong    N > 1: ONE 1024-spp frame of the headline config split over the N ranks with its per-frame reduce.
+cpu_baseline / --impl reference: the CPU port of the reference shaders (oracle/vr_oracle.c, pinned bit for bit against the
+          reference's GLSL compiled as C++) on all host threads, bounded sample of the same frame.
 """
 from __future__ import annotations
 
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -31,43 +39,51 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-ASSETS = os.path.join(ROOT, "tests", "golden", "assets")
 W, H, BOUNCES, FULL_SPP = 1920, 1080, 128, 1024
 METRIC = "path samples/sec (1080p, 128 bounces)"
 UNIT = "samples/s"
+WORKLOAD = "configs[1]: smoke.brick + lut.txt TF (pathtracer_brick_tf), 1920x1080, 128 bounces, 1024 spp"
+CPU_W, CPU_H = W // 4, H // 4     # CPU legs: the SAME frame (camera, fov, aspect) at 1/4 resolution per axis
 
 
 def load_workload(w=W, h=H):
-    from volren_b200 import formats
-    from helpers import default_scene
-    grid = formats.load_brick(os.path.join(ASSETS, "smoke.brick"))
-    env = formats.load_hdr(os.path.join(ASSETS, "table_mountain_2_puresky_1k.hdr"))
-    lut = formats.lut_for_upload(formats.load_lut_txt(os.path.join(ASSETS, "lut.txt")))
+    import workloads as wl
+    grid, env, lut = wl.load_assets()
     # `./volren data/smoke.brick <hdr> data/lut.txt -w 1920 -h 1080 --render --bounces 128`
-    params = default_scene(grid, w, h, bounces=BOUNCES, use_tf=True)
-    return grid, env, lut, params
-
-
-# CPU legs: the SAME frame (camera, fov, aspect -> the same mix of empty and dense pixels) at 1/4 resolution per axis
-CPU_W, CPU_H = W // 4, H // 4
-
-
-def algorithmic_bytes(c: dict, use_tf: bool) -> float:
-    """bytes the algorithm must touch, from the event counters (per launch)."""
-    if use_tf:
-        per_maj, per_dens = 4 + 32, 8 * 9 + 32
-    else:
-        per_maj, per_dens = 4, 9
-    return (per_maj * c["n_maj"] + per_dens * c["n_dens"] + 9 * c["n_emis"] + 200 * c["n_nee"] + 100 * c["n_env"]
-            + 32 * c["n_samples"])
+    return grid, env, lut, wl.default_params(grid, w, h, bounces=BOUNCES, use_tf=True)
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return json.load(open(p)), "measured"
-    return {"hbm_gbs": 6650.0}, "fallback"
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def source_hash():
+    """sha256 over the CUDA sources: ncu captures under profiles/ are stamped with it and ignored when the kernels changed."""
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "volren_b200", "csrc", "*.cu*"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(key):
+    """DRAM bytes per launch of the tracking kernel on workload `key` from the committed ncu capture -- only when the capture
+    was taken from the sources this run uses."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+    except Exception:
+        return None, "no capture committed"
+    if tj.get("source_sha16") != source_hash():
+        return None, f"stale capture ignored (taken at source hash {tj.get('source_sha16')}, this run is {source_hash()})"
+    e = tj.get(key)
+    if not e:
+        return None, "no capture for this workload"
+    return e["dram_read_bytes"] + e["dram_write_bytes"], e.get("source", "profiles/traffic_latest.json")
 
 
 class ClockSampler:
@@ -82,13 +98,10 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # CUDA_VISIBLE_DEVICES may remap indices: match by PCI bus id of the torch device when possible
             import torch
-            try:
-                bus = torch.cuda.get_device_properties(index).pci_bus_id
-                dom = getattr(torch.cuda.get_device_properties(index), "pci_domain_id", 0)
-                dev = getattr(torch.cuda.get_device_properties(index), "pci_device_id", 0)
-                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+            try:        # CUDA_VISIBLE_DEVICES may remap indices: match by PCI bus id of the torch device when possible
+                pr = torch.cuda.get_device_properties(index)
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{getattr(pr, 'pci_domain_id', 0):08x}:{pr.pci_bus_id:02x}:{getattr(pr, 'pci_device_id', 0):02x}.0".encode())
             except Exception:
                 self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.nvml = pynvml
@@ -131,64 +144,57 @@ class ClockSampler:
                 "reasons": sorted(k for k, bit in self.REASONS.items() if self.mask & bit), "samples": len(self.sm), "how": "NVML poll every 2 ms during the timed region"}
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path. The GLSL renderer needs a GL context that
-    neither this container nor the GPU box has, so this is the oracle port of the shaders with all host threads
-    (kind = "port"); each step is a bounded crop of the same workload."""
-    if rank != 0:
-        return
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs
+
+def _cpu_trace_rate(spp_budget_s, steps, warmup):
+    """The oracle on the headline frame at 480x270 with all host threads -> (samples/s, cores, sample description, dt per step)."""
     from oracle.binding import Oracle
     grid, env, lut, params = load_workload(CPU_W, CPU_H)
     o = Oracle()
     pyr = o.env_build(env)
     sc = o.make_scene(grid, env, pyr, lut=lut)
     cores = len(os.sched_getaffinity(0))     # all host threads, whatever OMP_NUM_THREADS torchrun exported
-    # bounded sample: the whole frame at 480x270, spp per step sized for ~3 s per step
     color = np.zeros((CPU_H, CPU_W, 4), np.float32)
     o.trace(sc, params, 1, 1, color=color, n_threads=cores)
     t0 = time.perf_counter()
     o.trace(sc, params, 1, 4, color=color, n_threads=cores)
     probe = (time.perf_counter() - t0) / 4
-    spp = max(1, int(min(3.0, 90.0 / max(args.steps, 1)) / max(probe, 1e-4)))      # ~3 s per step, the whole run <= ~90 s
-    for i in range(args.warmup):
+    spp = max(1, int(spp_budget_s / max(probe, 1e-4)))
+    for i in range(warmup):
         o.trace(sc, params, 1 + i, 1, color=color, n_threads=cores)
     t0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         o.trace(sc, params, 1 + k * spp, spp, color=color, n_threads=cores)
     dt = time.perf_counter() - t0
-    samples = CPU_W * CPU_H * spp * args.steps
-    v = samples / dt
-    sample = f"the 1080p frame rendered at {CPU_W}x{CPU_H} (same camera), {spp} spp per step, {args.steps} steps"
+    sample = f"the 1080p frame rendered at {CPU_W}x{CPU_H} (same camera), {spp} spp per step, {steps} step(s); oracle/vr_oracle.c, OpenMP"
+    return CPU_W * CPU_H * spp * steps / dt, cores, sample, dt / steps
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path. The GLSL renderer needs a GL context that neither
+    this container nor the GPU box has, so this is the oracle port of the shaders with all host threads (kind = "port");
+    each step is a bounded sample of the same frame."""
+    if rank != 0:
+        return
+    v, cores, sample, dt = _cpu_trace_rate(min(3.0, 90.0 / max(args.steps, 1)), args.steps, args.warmup)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "reference assets (smoke.brick, lut.txt, hdr) committed under tests/golden/assets",
-        "config": {"workload": "configs[1]: smoke.brick + lut.txt TF (pathtracer_brick_tf), 1920x1080, 128 bounces", "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def cpu_baseline_worker():
-    """cpu_baseline leg: the oracle (port of the reference shaders) on a bounded sample of the bench workload."""
-    from oracle.binding import Oracle
-    grid, env, lut, params = load_workload(CPU_W, CPU_H)
-    o = Oracle()
-    pyr = o.env_build(env)
-    sc = o.make_scene(grid, env, pyr, lut=lut)
-    img = np.zeros((CPU_H, CPU_W, 4), np.float32)
-    cores = len(os.sched_getaffinity(0))
-    o.trace(sc, params, 1, 1, color=img, n_threads=cores)
-    t0 = time.perf_counter()
-    o.trace(sc, params, 1, 4, color=img, n_threads=cores)
-    probe = (time.perf_counter() - t0) / 4
-    spp = max(1, int(12.0 / max(probe, 1e-4)))
-    t0 = time.perf_counter()
-    o.trace(sc, params, 2, spp, color=img, n_threads=cores)
-    dt = time.perf_counter() - t0
-    print(json.dumps({"value": CPU_W * CPU_H * spp / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                      "sample": f"the 1080p frame rendered at {CPU_W}x{CPU_H} (same camera), {spp} spp (oracle/vr_oracle.c, OpenMP)"}))
+    v, cores, sample, _ = _cpu_trace_rate(12.0, 1, 0)
+    print(json.dumps({"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}))
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
 
 def main():
     if "--cpu-baseline-worker" in sys.argv:
@@ -199,7 +205,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=32)
+    ap.add_argument("--spp-per-step", type=int, default=FULL_SPP, help="samples per pixel, rank and step (default: the config's full 1024-spp frame)")
+    ap.add_argument("--configs", default="C1,C3,C4,C5", help="other BASELINE configs measured into the `configs` object ('none' to skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -213,6 +220,8 @@ def main():
     import torch
     import torch.distributed as dist
     import volren_b200 as vr
+    import workloads as wl
+    from volren_b200.multigpu import PartitionedRenderer
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: volren_b200 has no CPU fallback")
@@ -227,12 +236,6 @@ def main():
     ctx = vr.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)          # kernels run on torch's current stream: torch.cuda.Event sees them
-    ctx.resize(W, H)
-    color = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
-    ctx.bind_color(color.data_ptr())            # NCCL reduces this tensor in place
-    ctx.grid_upload_brick(grid)
-    ctx.env_upload(env)
-    ctx.tf_upload(lut)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -240,73 +243,119 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    from volren_b200.multigpu import PartitionedRenderer
-    kev_cur = [None]
+    def ev_pair():
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def trace_fn(first, n, tile, accum):
-        if kev_cur[0] is not None:
-            kev_cur[0][0].record()
-        ctx.trace(params, first, n, tile=tile, accum_mode=accum)
-        if kev_cur[0] is not None:
-            kev_cur[0][1].record()
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # spp slices: rank r traces S of the S*world samples of a step into a SUM buffer, one NCCL reduce(SUM) to rank 0
-    pr = PartitionedRenderer(color, trace_fn, partition="spp")
+    def counters_of(c, p, spp, culled):
+        """event counters of one launch of `spp` samples per pixel (the counting build of the same kernel)"""
+        c.set_option("count_culled", 1 if culled else 0)
+        c.set_counting(True)
+        c.clear()
+        c.trace(p, 1, spp)
+        out = c.get_counters().as_dict()
+        c.set_counting(False)
+        c.set_option("count_culled", 0)
+        c.clear()
+        return out
 
-    def step(last=True):
-        """one step: S more samples per pixel on every rank (weak scaling). The float4 accumulation buffers are reduced to
-        rank 0 ONCE per frame: by the last step of the frame, inside the timed region."""
-        pr.render(S * world, reduce=last)
+    class Timed:
+        """Runs `frames` of `spp_total` samples on a context partitioned over the ranks by spp slices, one reduce per frame."""
 
-    # ---- counting pass (defines the algorithmic bytes of one launch) ----
-    ctx.set_counting(True)
-    ctx.trace(params, 1, S)
-    counters = ctx.get_counters().as_dict()
-    alg_bytes = algorithmic_bytes(counters, use_tf=True)
-    # the same with the production launch's exact culling kept (hidden environment: pixels / tiles that cannot produce a
-    # non-zero sample are not traced): the events -- and bytes -- the timed kernel really executes
-    ctx.set_option("count_culled", 1)
-    ctx.set_counting(True)                      # resets the counters
-    ctx.clear()
-    ctx.trace(params, 1, S)
-    counters_exec = ctx.get_counters().as_dict()
-    ctx.set_option("count_culled", 0)
-    ctx.set_counting(False)
-    exec_bytes = algorithmic_bytes(counters_exec, use_tf=True) + 32 * (counters["n_samples"] - counters_exec["n_samples"])   # folded zeros still cost the RMW
+        def __init__(self, c, p, w, h):
+            self.c, self.p, self.w, self.h = c, p, w, h
+            c.resize(w, h)
+            self.color = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+            c.bind_color(self.color.data_ptr())
+            self.kev = None
+            self.coll = []
+            self.pr = PartitionedRenderer(self.color, self._trace, partition="spp")
 
-    # ---- device-resident throughput ----
-    pr.reset()
-    for i in range(args.warmup):
-        step()
+        def _trace(self, first, n, tile, accum):
+            if self.kev is not None:
+                self.kev[0].record()
+            self.c.trace(self.p, first, n, tile=tile, accum_mode=accum)
+            if self.kev is not None:
+                self.kev[1].record()
+
+        def frame(self, spp_total, kev=None):
+            """one frame: spp_total samples split over the ranks, then the reduce (timed separately as the collective)"""
+            self.pr.reset()
+            self.kev = kev
+            self.pr.render(spp_total, reduce=False)
+            self.kev = None
+            if world > 1:
+                a, b = ev_pair()
+                a.record()
+                self.pr.finish()
+                b.record()
+                self.coll.append((a, b))
+
+        def run(self, spp_total, frames, warm_spp):
+            """-> (samples/s whole job, ms per frame (max over ranks), kernel ms per frame on this rank, collective ms per frame)"""
+            self.frame(warm_spp)
+            barrier()
+            self.coll = []
+            launches0 = self.c.get_stat("trace_launches")
+            ev, kev = [ev_pair() for _ in range(frames)], [ev_pair() for _ in range(frames)]
+            for k in range(frames):
+                flush.fill_(k & 0xFF)               # L2 flush between timed iterations (not timed)
+                barrier()
+                ev[k][0].record()
+                self.frame(spp_total, kev[k])
+                ev[k][1].record()
+                barrier()
+            self.launches = self.c.get_stat("trace_launches") - launches0     # this rank's own kernels inside the timed region
+            ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+            kms = sum(a.elapsed_time(b) for a, b in kev) / frames
+            cms = sum(a.elapsed_time(b) for a, b in self.coll) / max(len(self.coll), 1) if self.coll else 0.0
+            return self.w * self.h * spp_total * frames / (ms * 1e-3), ms / frames, kms, cms
+
+    # ---- ceilings measured in this run, on this device (SURVEY 8(d): "must be micro-benchmarked on the box") ----
+    peaks, peak_kind = measured_peaks()
+    probes = None
+    if rank == 0:
+        probes = {"l2_gather_gbs": ctx.probe_bandwidth(32 << 20, 1), "l2_stream_gbs": ctx.probe_bandwidth(32 << 20, 0),
+                  "hbm_gather_gbs": ctx.probe_bandwidth(1 << 30, 1), "hbm_stream_gbs": ctx.probe_bandwidth(1 << 30, 0),
+                  "how": "vrb_probe_bandwidth: 32 MiB (L2-resident) and 1 GiB working sets; random 32-B sector gathers counted at 32 B each, 16-B streaming loads; best of 5"}
+
+    # ---- headline: C2 resident in HBM ----
+    ctx.grid_upload_brick(grid)
+    ctx.env_upload(env)
+    ctx.tf_upload(lut)
+    head = Timed(ctx, params, W, H)
+    PASS = 32
+    counters = counters_of(ctx, params, PASS, culled=False)         # the reference algorithm's events for this image
+    counters_exec = counters_of(ctx, params, PASS, culled=True)     # the events the production launch executes (exact culling kept)
+    n_all = counters["n_samples"]
+    alg_bytes = wl.algorithmic_bytes(counters, True)
+    exec_bytes = wl.algorithmic_bytes(counters_exec, True) + 32 * (n_all - counters_exec["n_samples"])   # folded zeros still cost the RMW
+
+    for _ in range(max(0, args.warmup - 1)):        # W warm-up steps in total: run() does the last one itself
+        head.frame(S * world)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = ctx.get_stat("trace_launches")
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)                   # L2 flush between timed iterations (not timed)
-        barrier()
-        kev_cur[0] = kev[k]
-        ev[k][0].record()
-        step(last=(k == args.steps - 1))        # the K timed steps are one frame of K * S * N samples: one NCCL reduce at its end
-        ev[k][1].record()
-        kev_cur[0] = None
-        barrier()
-    launches = ctx.get_stat("trace_launches") - launches0      # counted by the library at its launch sites
+    value, ms_per_step, kms, coll_ms = head.run(S * world, args.steps, S * world)
+    launches = head.launches
     clocks = sampler.stop() if rank == 0 else None
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    kms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    launches_per_step = -(-S // PASS)
+    k_launch_ms = kms / launches_per_step                            # tracking kernel + its fold, per 32-spp launch
+
+    # ---- strong scaling of the headline frame: 1024 spp split over the ranks, reduce per frame ----
+    strong = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    samples_per_step = W * H * S * world
-    value = samples_per_step * args.steps / (ms_total * 1e-3)
+        sv, sms, skms, scms = head.run(FULL_SPP, max(3, min(args.steps, 10)), FULL_SPP)
+        strong = {"value": sv, "unit": UNIT, "ms_per_frame": sms, "kernel_ms_per_frame": skms, "collective_ms": scms,
+                  "frame": f"{FULL_SPP} spp split into {world} slices of {FULL_SPP // world}, one NCCL reduce(SUM) of the 33 MB float4 image per frame"}
 
     # ---- end to end through the C ABI with host buffers ----
-    # pinned host buffers for everything that crosses PCIe inside the timed region
     pinned = []
 
     def pin(arr):
@@ -315,26 +364,22 @@ def main():
         return t.numpy()
 
     import copy
-    grid = copy.copy(grid)
-    grid.indirection, grid.range, grid.atlas, grid.mips = pin(grid.indirection), pin(grid.range), pin(grid.atlas), [pin(m) for m in grid.mips]
-    env, lut = pin(env), pin(lut)
-    h2d = grid.indirection.nbytes + grid.range.nbytes + grid.atlas.nbytes + sum(m.nbytes for m in grid.mips) + env.nbytes + lut.nbytes
+    hgrid = copy.copy(grid)
+    hgrid.indirection, hgrid.range, hgrid.atlas, hgrid.mips = pin(grid.indirection), pin(grid.range), pin(grid.atlas), [pin(m) for m in grid.mips]
+    henv, hlut = pin(env), pin(lut)
+    h2d = hgrid.indirection.nbytes + hgrid.range.nbytes + hgrid.atlas.nbytes + sum(m.nbytes for m in hgrid.mips) + henv.nbytes + hlut.nbytes
     d2h = H * W * 16 if rank == 0 else 0
 
-    # Four contexts on this GPU, each with its own stream, colour buffer and pinned read-back image (a ring of in-flight
-    # frames through the public API): step k runs on lane k % 4 with asynchronous uploads ("async_upload": the pinned inputs
-    # outlive the step), so the host enqueues upload + trace of the next steps while it waits for the device->host read of
-    # an older one, and the tracking kernels run back to back. Measured on B200: 2 lanes with blocking uploads 21.6 G,
-    # 2 / 3 / 4 lanes with asynchronous uploads 20.9 / 25.1 / 29.5 Gsamples/s (the persistent tracking kernel fills every
-    # SM, so another lane's small upload kernels only run between two traces; a blocking upload stalls the host on them).
-    # Every step still uploads its own inputs and its image is read back inside the timed region.
+    # Two contexts on this GPU, each with its own stream, colour buffer and pinned read-back image: step k runs on lane k % 2
+    # with asynchronous uploads (the pinned inputs outlive the step), so the host enqueues the next frame while it waits for
+    # the read-back of the previous one. Every step uploads its own inputs and its image is read back inside the timed region.
     class Lane:
         def __init__(self):
             self.stream = torch.cuda.Stream(device=dev)
             self.ctx = vr.Context(local_rank)
             self.ctx.set_stream(self.stream.cuda_stream)
             self.ctx.resize(W, H)
-            self.ctx.set_option("async_upload", 1)      # the pinned inputs outlive every step: uploads only enqueue
+            self.ctx.set_option("async_upload", 1)
             self.color = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
             self.ctx.bind_color(self.color.data_ptr())
             self.host_img = pin(np.empty((H, W, 4), np.float32))
@@ -352,72 +397,181 @@ def main():
 
         def submit(self):
             with torch.cuda.stream(self.stream):
-                self.ctx.grid_upload_brick(grid)        # host -> device: indirection, range, atlas, mips
-                self.ctx.env_upload(env)                # host -> device + importance pyramid rebuild
-                self.ctx.tf_upload(lut)
-                self.pr.render(S * world)
+                self.ctx.grid_upload_brick(hgrid)       # host -> device: indirection, range, atlas, mips
+                self.ctx.env_upload(henv)               # host -> device + importance pyramid rebuild
+                self.ctx.tf_upload(hlut)
+                self.pr.reset()
+                self.pr.render(S * world)               # incl. the per-frame reduce at N > 1
             self.pending = True
 
-    lanes = [Lane() for _ in range(max(2, int(os.environ.get("VRB_E2E_LANES", "4"))))]
-    n_lanes = len(lanes)
-    # the pipeline needs a few steps to fill and one read-back to drain: time at least 40 steps so that the number is the
-    # steady state whatever --steps is (reported as e2e.steps)
-    e2e_steps = max(args.steps, 40)
-
-    def e2e_step(k):
-        lane = lanes[k % n_lanes]
-        lane.finish()                                   # the image of step k - 2 (normally long done)
-        lane.submit()
-
-    for k in range(4):
-        e2e_step(k)
+    lanes = [Lane() for _ in range(max(2, int(os.environ.get("VRB_E2E_LANES", "2"))))]
+    e2e_steps = max(args.steps, 8)
+    for k in range(len(lanes)):
+        lanes[k].submit()
     for lane in lanes:
         lane.finish()
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        e2e_step(k)
+        lane = lanes[k % len(lanes)]
+        lane.finish()
+        lane.submit()
     for lane in lanes:
         lane.finish()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = samples_per_step * e2e_steps / float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = W * H * S * world * e2e_steps / e2e_s
+    for lane in lanes:
+        lane.ctx.close()
+    del lanes
+
+    # ---- the other BASELINE configs ----
+    cfg_out = {}
+    wanted = [] if args.configs.lower() == "none" else [c.strip().upper() for c in args.configs.split(",") if c.strip()]
+
+    def roofline_of(c, p, tf, kernel_ms_per_launch, spp_launch, bound, traffic_key):
+        cs = counters_of(c, p, 2, culled=False)
+        ce = counters_of(c, p, 2, culled=True)
+        n = cs["n_samples"]
+        per_sample = wl.algorithmic_bytes(ce, tf) / n + 32.0 * (n - ce["n_samples"]) / n
+        bytes_launch = per_sample * p.resolution[0] * p.resolution[1] * spp_launch
+        achieved = bytes_launch / (kernel_ms_per_launch * 1e-3) / 1e9
+        peak = probes["l2_gather_gbs"] if bound == "l2" else peaks["hbm_gbs"]
+        traffic, src = committed_traffic(traffic_key)
+        return {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_kind": "L2 random 32-B sector gather ceiling measured in this run (vrb_probe_bandwidth)" if bound == "l2" else peak_kind,
+                "traffic": traffic, "traffic_source": src, "algorithmic_bytes_per_sample": per_sample,
+                "reference_algorithm_bytes_per_sample": wl.algorithmic_bytes(cs, tf) / n, "traced_fraction": ce["n_samples"] / n,
+                "counters_per_sample": {k: v / n for k, v in cs.items()}}
+
+    def run_config(name):
+        c2 = vr.Context(local_rank)
+        c2.set_stream(stream.cuda_stream)
+        c2.env_upload(env)
+        try:
+            if name == "C1":
+                w, h, spp, tf, bound = 1024, 1024, 64, False, "l2"
+                c2.grid_upload_brick(grid)
+                p = wl.readme_params(grid, w, h)
+                label, extra = "configs[0]: smoke.brick + hdr, README command (non-TF, environment visible), 1024x1024, 64 spp", {}
+            else:
+                w, h = W, H
+                if name == "C3":
+                    n = 1024
+                    vox, dims, tf, spp, bound = wl.fbm_cloud(n), (n, n, n), False, 4096, "hbm"
+                    label = "configs[2]: synthetic 1024^3 fBm cloud -> GPU brick build, density 100, albedo .8 (non-TF), 1920x1080, 4096 spp"
+                else:
+                    vox, dims, tf, spp, bound = wl.ct_phantom(512, 512, 1800), (512, 512, 1800), True, 1024, "hbm"
+                    c2.tf_upload(wl.turbo_lut())
+                    label = "configs[3]: synthetic 512x512x1800 CT phantom + 256-entry Turbo LUT (TF), 1920x1080, 1024 spp"
+                torch.cuda.synchronize()
+                torch.cuda.empty_cache()
+                c2.grid_build_from_dense_device(vox.data_ptr(), dims, 0.0, 1.0)       # first build grows the memory pool
+                a, b = ev_pair()
+                a.record()
+                c2.grid_build_from_dense_device(vox.data_ptr(), dims, 0.0, 1.0)
+                b.record()
+                torch.cuda.synchronize()
+                build_ms = a.elapsed_time(b)
+                nb, _, count = c2.grid_info()
+                n_vox = dims[0] * dims[1] * dims[2]
+                build_bytes = n_vox + count * 512 + 8 * nb[0] * nb[1] * nb[2]
+                extra = {"grid": list(dims), "n_bricks": list(nb), "bricks_allocated": int(count), "atlas_MiB": count * 512 / 2 ** 20,
+                         "brick_build": {"ms": build_ms, "algorithmic_GBps": build_bytes / (build_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                         "frac": build_bytes / (build_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                         "bytes": "1 B/voxel read + 1 B/allocated voxel written + 8 B/brick (SURVEY 8(d))"}}
+                del vox
+                torch.cuda.empty_cache()
+                p = wl.synthetic_params(dims, w, h, tf)
+            t = Timed(c2, p, w, h)
+            v, ms, kms_c, cms = t.run(spp, 1 if spp >= 1024 else 4, min(spp, 64))
+            out = {"workload": label, "value": v, "unit": UNIT, "resolution": [w, h], "spp": spp, "ms_per_frame": ms, "collective_ms": cms,
+                   "partition": f"{world} spp slices + one NCCL reduce per frame" if world > 1 else "single GPU", **extra}
+            if rank == 0:
+                per_rank_spp = spp // world if world > 1 else spp
+                out["roofline"] = roofline_of(c2, p, tf, kms_c / max(1, -(-per_rank_spp // PASS)), min(PASS, per_rank_spp), bound, name.lower())
+            return out
+        finally:
+            c2.close()
+
+    def run_c5(frames=8, clean_spp=256, n=256, w=1024, h=1024):
+        """datagen_denoise.py:60-130 on synthetic animated frames: per frame GPU brick build, noisy + clean render, two read-backs
+        to fp16 (N, 3, H, W); frames are dealt round-robin to the ranks (independent jobs: no exchange)."""
+        c5 = vr.Context(local_rank)
+        c5.set_stream(stream.cuda_stream)
+        c5.env_upload(env)
+        c5.resize(w, h)
+        vols = wl.fbm_frames(n, frames)
+        plist = wl.c5_parameters(frames)
+        inputs = np.zeros((frames, 3, h, w), np.float16)
+        targets = np.zeros((frames, 3, h, w), np.float16)
+        samples = 0
+        barrier()
+        t0 = time.perf_counter()
+        for i, q in enumerate(plist):
+            if i % world != rank:
+                continue
+            c5.grid_build_from_dense_device(vols[i].data_ptr(), (n, n, n), 0.0, 1.0)
+            for seed, spp, dst in ((q["seed_input"], q["samples"], inputs), (q["seed_target"], clean_spp, targets)):
+                c5.clear()
+                c5.trace(wl.c5_frame_params(q, n, w, h, seed), 1, spp)
+                rgb = c5.download_color(3)                                             # fbo_data(): linear RGB fp32
+                dst[i] = np.transpose(np.flip(rgb, axis=0).astype(np.float16), [2, 1, 0])  # datagen_denoise.py:113-114
+                samples += w * h * spp
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        tot = torch.tensor([float(samples)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        c5.close()
+        return {"workload": f"configs[4]: {frames} animated {n}^3 fBm frames, datagen_denoise-style pairs (noisy 1..33 spp, clean {clean_spp} spp; named: 64 frames x 4096 spp), 1024x1024, fp16 (N,3,H,W) out",
+                "value": frames / dt, "unit": "frames/s", "samples_per_s": float(tot.item()) / dt, "wall_s": dt,
+                "partition": f"frames dealt round-robin to {world} ranks, no exchange" if world > 1 else "single GPU",
+                "finite": bool(np.isfinite(inputs.astype(np.float32)).all() and np.isfinite(targets.astype(np.float32)).all())}
+
+    for name in wanted:
+        try:
+            cfg_out[name] = run_c5() if name == "C5" else run_config(name)
+        except Exception as e:      # a failing side config must not take the headline line down
+            cfg_out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
-        peaks, peak_kind = measured_peaks()
-        traffic, traffic_src = None, "no capture committed"
-        try:        # DRAM bytes of one launch of the same kernel on the same workload, from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
-            traffic, traffic_src = tj["dram_read_bytes"] + tj["dram_write_bytes"], tj["source"]
-        except Exception:
-            pass
-        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        traffic, traffic_src = committed_traffic("c2")
+        achieved = exec_bytes / (k_launch_ms * 1e-3) / 1e9       # executed algorithmic bytes of one 32-spp launch / its duration
+        l2_peak = probes["l2_gather_gbs"]
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "reference assets (smoke.brick, lut.txt, hdr) committed under tests/golden/assets",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "reference assets (smoke.brick, lut.txt, hdr) committed under tests/golden/assets; synthetic grids (seed 42) for C3-C5",
             "config": {
-                "workload": "configs[1]: smoke.brick + lut.txt TF (pathtracer_brick_tf), 1920x1080, 128 bounces",
-                "spp_per_step": S, "full_config_spp": FULL_SPP, "partition": "spp slices, one NCCL reduce(SUM) of the float4 buffers at the end of the K-step frame (inside the timed region)" if world > 1 else "single GPU",
-                "l2": "flushed between timed iterations (256 MiB fill); the 1.9 MB volume is L2-resident by nature",
+                "workload": WORKLOAD, "spp_per_step": S, "full_config_spp": FULL_SPP,
+                "step": "one full frame of the config per GPU (32 launches of the tracking kernel + fold, 32 spp each)",
+                "partition": (f"weak scaling: {world} spp slices of {S} spp, one NCCL reduce(SUM) of the float4 images per step (inside the timed region)" if world > 1 else "single GPU"),
+                "l2": "flushed between timed iterations (256 MiB fill); the 1.9 MB volume / 27 MB decoded working set is L2-resident by nature",
             },
             "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, " + traffic_src + ")",
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_kind": peak_kind, "kernel": "k_trace_persistent<TF, FastMath>", "kernel_ms": kms,
-                "algorithmic_bytes_per_sample": alg_bytes / counters["n_samples"], "counters_per_sample": {k: v / counters["n_samples"] for k, v in counters.items()},
-                "executed": {"bytes_per_sample": exec_bytes / counters["n_samples"], "achieved": exec_bytes / (kms * 1e-3) / 1e9,
-                             "traced_fraction": counters_exec["n_samples"] / counters["n_samples"],
-                             "note": "events the production launch executes after its exact screen-space culling; `achieved` above uses the reference algorithm's bytes for the same image"},
-                "note": "latency/issue-bound gather workload on an L2-resident volume: see DESIGN.md for the L2 roofline",
+                "bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
+                "peak_kind": "L2 random 32-B sector gather ceiling measured in this run (vrb_probe_bandwidth, 32 MiB working set)",
+                "hbm": {"peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "frac": achieved / peaks["hbm_gbs"],
+                        "note": "C2's working set never leaves L2: DRAM moves <1 % of the algorithmic bytes, so HBM does not bound this workload; C3 / C4 in `configs` are the HBM-resident ones"},
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": exec_bytes, "algorithmic_bytes_per_sample": exec_bytes / n_all,
+                "bytes_definition": "EXECUTED events of one 32-spp launch (counting build with the production culling kept) x SURVEY 8(d) bytes per event; culled samples still pay their 32 B accumulate",
+                "reference_algorithm_bytes_per_sample": alg_bytes / n_all, "traced_fraction": counters_exec["n_samples"] / n_all,
+                "kernel": "k_trace_pool<TF, FastMath> + k_fold", "kernel_ms": k_launch_ms, "launches_per_step": launches_per_step,
+                "counters_per_sample": {k: v / n_all for k, v in counters.items()},
+                "probes": probes,
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "lanes": n_lanes},
-            "gpu_launches": int(launches),      # rank 0's own kernels in the timed region (tracking kernel + k_fold per step, brick mask + tile keys when the cached order is rebuilt)
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "note": "per step: upload grid + env + LUT from pinned host memory, trace the frame, read the RGBA32F image back"},
+            "collective_ms": coll_ms,
+            "gpu_launches": int(launches),      # rank 0's own kernels in the timed region (tracking kernel + k_fold per pass; brick mask + tile keys when the cached order is rebuilt)
             "clocks": clocks,
+            "configs": cfg_out,
+            "source_sha16": source_hash(),
         }
+        if strong is not None:
+            out["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
             # separate process: no torch / CUDA runtime (and no second OpenMP runtime) next to the OpenMP oracle
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker"], capture_output=True, text=True)
@@ -426,8 +580,6 @@ def main():
             except Exception:
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: " + (r.stderr or "")[-300:]}
         print(json.dumps(out))
-    for lane in lanes:
-        lane.ctx.close()
     if world > 1:
         dist.destroy_process_group()
     ctx.close()

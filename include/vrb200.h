@@ -222,6 +222,11 @@ int vrb_set_kernel(vrb_ctx* ctx, int kind);
  * or download on this context; pass pinned memory so that the copies really are asynchronous. A pipelined caller can
  * then enqueue the uploads and the trace of the next frame while the previous one is still running. */
 int vrb_set_option(vrb_ctx* ctx, const char* name, int value);
+/* measurement aid (new; SURVEY 8(d): the L2 roofline "must be micro-benchmarked on the box"): read bandwidth of this device over
+ * a working set of `bytes` (1 MiB ... 8 GiB; below the 126 MB L2 it measures L2, 1 GiB measures HBM), best of 5 launches timed
+ * with CUDA events on the context's stream. mode 0 = streaming 16-byte loads, mode 1 = random 32-byte sector gathers
+ * (4-byte load per sector, the tracer's access pattern; GB/s counted at 32 B per sector). */
+int vrb_probe_bandwidth(vrb_ctx* ctx, size_t bytes, int mode, double* gbytes_per_s);
 /* counters of the context: "trace_launches" = hand-written kernels vrb_trace has launched so far on the production path
  * (majorant tables, brick mask, tile keys, tracking kernel, fold; library sorts and memsets are not counted) */
 int vrb_get_stat(vrb_ctx* ctx, const char* name, uint64_t* out);

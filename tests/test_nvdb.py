@@ -420,3 +420,26 @@ assert accepted > 0 and rejected > 0
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "file.npy"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, (res.returncode, res.stdout[-300:], res.stderr[-800:])
+
+
+def test_reader_rejects_wrapping_size_fields(nvdb_golden):
+    """Sizes read from the file must not wrap the 64-bit offset arithmetic: 0, 2^64 - 256 and 2^63 in every
+    size field of the container (FileMetaData.fileSize, GridData.mGridSize) -- of the segment file and of the raw grid buffer
+    inside it. The reader rejects the file or finds the grid; it never reads out of bounds or spins."""
+    import volren_b200 as vr
+    data = nvdb_golden["nvdb_file"]
+    first = vr.NanoVDBGridData(data, "density")
+    off = int(first.info.grid_offset)
+    raw = data[off:].copy()                                     # raw grid buffers back to back (GridHandle::read path)
+    assert vr.NanoVDBGridData(raw, "density").extent == first.extent
+    fields = [(data, 16 + 8), (data, off + 32), (raw, 32)]      # FileMetaData.fileSize of entry 0; mGridSize (GridData + 32)
+    for src, pos in fields:
+        for val in (0, 0xFFFFFFFFFFFFFF00, 1 << 63, 8):
+            bad = src.copy()
+            bad[pos:pos + 8] = np.frombuffer(np.uint64(val).tobytes(), np.uint8)
+            for name in ("density", "temperature", "nope"):
+                try:
+                    g = vr.NanoVDBGridData(bad, name)
+                except vr.VrbError:
+                    continue
+                assert g.extent == first.extent or name != "density"

@@ -20,7 +20,7 @@ SYMBOLS = [
     "vrb_create", "vrb_destroy", "vrb_last_error", "vrb_status_string", "vrb_abi_version", "vrb_set_stream", "vrb_sync",
     "vrb_resize", "vrb_grid_clear", "vrb_grid_free", "vrb_grid_upload_brick", "vrb_grid_build_from_dense",
     "vrb_grid_build_from_dense_device", "vrb_brick_lattice", "vrb_grid_build_from_values", "vrb_nvdb_open", "vrb_nvdb_lookup", "vrb_grid_build_from_nvdb", "vrb_grid_info", "vrb_grid_download", "vrb_debug_sample_density", "vrb_dense_from_float",
-    "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_set_option", "vrb_get_stat", "vrb_scale",
+    "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_set_option", "vrb_get_stat", "vrb_probe_bandwidth", "vrb_scale",
     "vrb_clear", "vrb_set_counting", "vrb_get_counters", "vrb_tonemap", "vrb_download_color", "vrb_download_color_ldr",
     "vrb_download_framebuffer", "vrb_upload_color", "vrb_color_device_ptr", "vrb_bind_color", "vrb_reduce", "vrb_copy_rows",
 ]
@@ -128,6 +128,7 @@ def load_library(path: str = LIB_PATH):
     L.vrb_set_kernel.argtypes = [vp, ci]
     L.vrb_set_option.argtypes = [vp, C.c_char_p, ci]
     L.vrb_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
+    L.vrb_probe_bandwidth.argtypes = [vp, C.c_size_t, ci, C.POINTER(C.c_double)]
     L.vrb_scale.argtypes = [vp, cf]
     L.vrb_clear.argtypes = [vp]
     L.vrb_set_counting.argtypes = [vp, ci]
@@ -244,6 +245,8 @@ class Context:
 
     def grid_upload_brick(self, grid, slot=SLOT_DENSITY, frame=0):
         """grid: any object with n_bricks, atlas_dim, brick_count, indirection, range, atlas, mips (numpy)."""
+        from .formats import check_brick_layout
+        check_brick_layout(grid)          # the library copies n_bricks-sized blocks out of these arrays
         v = BrickView()
         v.n_bricks[:] = grid.n_bricks
         v.atlas_dim[:] = grid.atlas_dim
@@ -333,6 +336,12 @@ class Context:
 
     def trace_deterministic(self, params: Params):
         self._ck(self.lib.vrb_trace_deterministic(self.handle, C.byref(params)))
+
+    def probe_bandwidth(self, nbytes, mode=0):
+        """GB/s of streaming (mode 0) or random 32-B sector gather (mode 1) reads over a working set of nbytes on this device."""
+        out = C.c_double()
+        self._ck(self.lib.vrb_probe_bandwidth(self.handle, C.c_size_t(nbytes), int(mode), C.byref(out)))
+        return float(out.value)
 
     def set_kernel(self, kind):
         self._ck(self.lib.vrb_set_kernel(self.handle, kind))

@@ -39,7 +39,8 @@ enum : int { SG_STEP = 0, SG_COLLIDE = 1, SG_NEE = 2, SG_SCATTER = 3, SG_FINISH 
 
 // fills one level of the majorant table: exactly majorant_at() of vr_trace.cuh, hoisted out of the DDA loop
 template <bool TF>
-VR_GLOBAL void k_majorant_table(const __grid_constant__ TraceArgs a, int level, float* __restrict__ out, size_t n) {
+VR_GLOBAL void k_majorant_table      // (internal linkage in the strict unit: the two units instantiate DIFFERENT arithmetic under one name)
+    (const __grid_constant__ TraceArgs a, int level, float* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         const uint32_t w = level == 0 ? a.density.rec[i].y : a.density.mips[level - 1][i];
         const float m = a.p.vol_density_scale * range_hi(w);

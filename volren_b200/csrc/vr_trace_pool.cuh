@@ -1,20 +1,25 @@
 // Ray-pool tracking kernel (production path of vrb_trace since round 2).
 //
 // Per path it executes exactly the arithmetic and the random-number order of k_trace_persistent (vr_trace2.cuh) -- the images
-// are bit-identical -- but the lanes of a warp no longer OWN a ray. The lane-resident kernel ran its stages at 12-17 of 32
-// active lanes (profiles/r01_v11_trace_*_summary.txt: the other lanes were parked in a queue or idled through the rest of a
-// multi-step pass), and every threshold / occupancy / two-rays-per-lane variant ended within a few percent, because 32 rays
-// simply are asynchronous. Here every warp keeps a POOL of VR_POOL_SLOTS (64) path states in shared memory, struct-of-arrays
-// so that 32 lanes touching 32 different slots are (at worst two-way) bank-conflict free. One scheduler iteration
-//   1. reads the stage word of every slot and counts the slots per stage (ballots),
-//   2. picks the stage with the most waiting slots (STEP at once when it can fill the warp),
-//   3. hands the first 32 slots of that stage to the lanes (rank by popcount -> slot list in shared memory),
-//   4. runs that ONE stage: the lanes load just the fields the stage reads, run the same code as the lane-resident
-//      kernel, and store what changed. STEP keeps stepping its rays until fewer than VR_POOL_STEP_MIN of them are left or
-//      VR_POOL_MAX_STEPS steps were taken, so the 10 loads / 4 stores are paid once per several DDA steps.
-// A stage therefore runs with min(32, waiting slots) lanes instead of "whoever happens to be there".
-// Costs: ~25 instructions of scheduling per iteration, the loads/stores, and shared memory instead of registers as the
-// occupancy limit (36 words x 64 slots = 9 KiB per warp).
+// are bit-identical -- but the lanes of a warp no longer OWN a path. The lane-resident kernel ran its stages at 12-17 of 32
+// active lanes (profiles/r01_v11_trace_*_summary.txt): a lane whose path waited for a rare event (NEE, scatter, finish +
+// regeneration) was lost to the hot brick-DDA loop, and every threshold / occupancy / two-rays-per-lane variant ended within
+// a few percent, because 32 paths simply are asynchronous. Here every warp keeps a POOL of VR_POOL_SLOTS (64) path states in
+// shared memory, struct-of-arrays so that 32 lanes touching 32 different slots are (at worst two-way) bank-conflict free, and
+// a scheduler iteration
+//   1. picks the stage class with the most waiting slots -- SEGMENT (a ray that steps or sits at a tentative collision), NEE,
+//      SCATTER or FINISH -- from per-class counts that every stage keeps up to date with a few ballots,
+//   2. hands the first 32 slots of that class to the lanes (rank by popcount -> slot list in shared memory),
+//   3. runs that ONE stage with up to 32 lanes: the lanes load the fields the stage reads, run the code of the lane-resident
+//      kernel, and store what changed.
+// SEGMENT is the hot loop and stays in REGISTERS: the 32 lanes step their rays (brick DDA) and resolve tentative collisions
+// in batches (a lane at a collision waits until VR_SEG_K_COLLIDE lanes are, like the in-warp queues of round 1) until fewer
+// than VR_SEG_EXIT lanes still have a live ray -- lanes only drop out at a REAL collision or at the end of a ray, ~10x rarer
+// than a step or a null collision -- and only then is the state written back and the next class scheduled. So the pool pays
+// its ~25 instructions of scheduling + ~20 loads/stores once per many DDA events, the event stages run with a full warp, and
+// the hot loop starts every visit with 32 live rays. History: v1 scheduled every DDA visit through the pool and recounted
+// the stages with ten ballots per iteration (29 % of the issued instructions, 27 active lanes but no faster:
+// profiles/r02_pool_v1_*); v2 kept the counts incrementally (-6 %); v3 is the register-resident SEGMENT loop.
 // FINISH also regenerates: finished slots take the next samples of the warp's current block of 32 (tile, sample index)
 // exactly like the lane-resident kernel (all 32 lanes prepare a block together: TEA seed, jitter, view direction).
 #pragma once
@@ -30,29 +35,44 @@ namespace vr {
 #define VR_POOL_WARPS 4           // warps per CTA
 #endif
 #ifndef VR_POOL_MIN_BLOCKS
-#define VR_POOL_MIN_BLOCKS 5      // CTAs per SM the register allocation must allow (shared memory: 5 x 37.5 KiB at 64 slots)
+#define VR_POOL_MIN_BLOCKS 6      // CTAs per SM the register allocation must allow (shared memory: 6 x 34.5 KiB at 64 slots)
 #endif
-#ifndef VR_POOL_MAX_STEPS
-#define VR_POOL_MAX_STEPS 8       // DDA steps per STEP visit at most
+#ifndef VR_SEG_FULL
+#define VR_SEG_FULL 32            // SEGMENT runs at once when this many slots wait for it
 #endif
-#ifndef VR_POOL_STEP_MIN
-#define VR_POOL_STEP_MIN 20       // leave the STEP loop when fewer of its rays are still stepping
+#ifndef VR_SEG_EXIT
+#define VR_SEG_EXIT 20            // leave the SEGMENT loop when fewer of its lanes still have a live ray
 #endif
-#ifndef VR_POOL_STEP_FULL
-#define VR_POOL_STEP_FULL 32      // STEP runs at once when this many slots wait for it
+#ifndef VR_SEG_MAX_ITERS
+#define VR_SEG_MAX_ITERS 64       // ... or after this many loop iterations (bounds the time a waiting event stage is starved)
+#endif
+#ifndef VR_SEG_STEPS
+#define VR_SEG_STEPS 2            // DDA steps per loop iteration
+#endif
+#ifndef VR_SEG_K_COLLIDE
+#define VR_SEG_K_COLLIDE 8        // resolve tentative collisions once this many lanes wait at one (non-TF: cheap 1-tap collision)
+#endif
+#ifndef VR_SEG_K_COLLIDE_TF
+#define VR_SEG_K_COLLIDE_TF 8     // TF: 8-tap trilinear + LUT collision
+#endif
+#ifndef VR_SEG_MIN_STEP
+#define VR_SEG_MIN_STEP 12        // fewer stepping lanes than this: resolve the waiting collisions even below the threshold
 #endif
 
 // fields of a slot (one 32-bit word each; PF_COUNT words per slot)
 enum : int {
-    PF_STAGE = 0,   // stage | flags
-    PF_PIX, PF_SJ, PF_TILE, PF_TITEM, PF_SEED, PF_NPATHS,
+    PF_STAGE = 0,   // stage | flags | STEP visits of the current ray
+    PF_PIX, PF_SJ, PF_SEED, PF_NPATHS,
     PF_POS, PF_DIR = PF_POS + 3, PF_THR = PF_DIR + 3, PF_L = PF_THR + 3, PF_PEND = PF_L + 3,
     PF_FP = PF_PEND + 3, PF_TR,
-    PF_IPOS, PF_IDIR = PF_IPOS + 3, PF_T = PF_IDIR + 3, PF_TFAR, PF_TAU, PF_MIP, PF_MAJ, PF_STEPS,
+    PF_IPOS, PF_IDIR = PF_IPOS + 3, PF_T = PF_IDIR + 3, PF_TFAR,
+    PF_TAU,         // optical depth left to the next tentative collision; while the ray SITS at one (stage COLLIDE): its majorant
+    PF_MIP,
     PF_COUNT
 };
 // flags in the stage word
-enum : uint32_t { PL_STAGE = 7u, PL_SHADOW = 8u, PL_ESCAPED = 16u, PL_ITEM = 32u, PL_LIT = 64u };
+enum : uint32_t { PL_STAGE = 7u, PL_SHADOW = 8u, PL_ESCAPED = 16u, PL_ITEM = 32u, PL_LIT = 64u,
+                  PL_FLAGS = 255u, PL_VISIT = 256u, PL_VISIT_MAX = 0xfff00000u };     // bits 8..31: SEGMENT visits of the current ray (hang guard)
 
 constexpr size_t pool_warp_words() { return size_t(PF_COUNT) * VR_POOL_SLOTS + 32 /* slot list */ + 128 /* prepared block: 32 x float4 */; }
 constexpr size_t pool_smem_bytes() { return pool_warp_words() * 4 * VR_POOL_WARPS; }
@@ -88,40 +108,33 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
     unsigned nxt_block = 0;        // lane 0: id of the prefetched next block
     if (lane == 0) nxt_block = atomicAdd(a.job_counter, 1u);
     const unsigned n_jobs = a.n_live ? (__ldg(a.n_live) << a.sample_bits) : unsigned(a.n_jobs);
+    // slots per stage class (warp-uniform, kept up to date by every stage from the transitions of the slots it processed);
+    // n_seg counts the slots in stage STEP or COLLIDE
+    int n_seg = 0, n_nee = 0, n_scat = 0, n_fin = SL;
 
     while (true) {
         __syncwarp();
-        // ================= scheduler: count the slots per stage, pick one stage, hand its slots to the lanes =================
-        uint32_t st[NS];
-        unsigned bal[5][NS];
-        int n[5] = { 0, 0, 0, 0, 0 };
-#pragma unroll
-        for (int k = 0; k < NS; ++k) st[k] = PU(PF_STAGE, k * 32 + lane) & PL_STAGE;
-#pragma unroll
-        for (int s = 0; s < 5; ++s)
-#pragma unroll
-            for (int k = 0; k < NS; ++k) { bal[s][k] = __ballot_sync(FULL, st[k] == uint32_t(s)); n[s] += __popc(bal[s][k]); }
-        if ((n[0] | n[1] | n[2] | n[3] | n[4]) == 0) break;      // every slot idle
-        int S = SG_STEP;
-        if (n[SG_STEP] < VR_POOL_STEP_FULL) {
-            int best = n[SG_STEP];
-#pragma unroll
-            for (int s = 1; s < 5; ++s) if (n[s] > best) { best = n[s]; S = s; }
+        // ================= scheduler: pick the class with the most waiting slots, hand its slots to the lanes =================
+        if ((n_seg | n_nee | n_scat | n_fin) == 0) break;      // every slot idle
+        int S = SG_STEP, best = n_seg;
+        if (n_seg < VR_SEG_FULL) {
+            if (n_nee > best) { best = n_nee; S = SG_NEE; }
+            if (n_scat > best) { best = n_scat; S = SG_SCATTER; }
+            if (n_fin > best) { best = n_fin; S = SG_FINISH; }
         }
         int base = 0;
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            unsigned b = bal[0][k];
-#pragma unroll
-            for (int s = 1; s < 5; ++s) if (S == s) b = bal[s][k];
-            if (st[k] == uint32_t(S)) {
-                const int r = base + __popc(b & lt);
-                if (r < 32) sel[r] = uint32_t(k * 32 + lane);
-            }
+            const uint32_t st = PU(PF_STAGE, k * 32 + lane) & PL_STAGE;
+            const bool in = S == SG_STEP ? st <= uint32_t(SG_COLLIDE) : st == uint32_t(S);      // SG_STEP = 0, SG_COLLIDE = 1
+            const unsigned b = __ballot_sync(FULL, in);
+            const int r = base + __popc(b & lt);
+            if (in && r < 32) sel[r] = uint32_t(k * 32 + lane);
             base += __popc(b);
         }
         __syncwarp();
-        const bool act = lane < min(base, 32);
+        const int nsel = min(base, 32);
+        const bool act = lane < nsel;
         const int slot = act ? int(sel[lane]) : 0;
 
         bool start = false;            // this lane starts a new ray from (spos, rd) with the stream `seed` below
@@ -129,107 +142,119 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
         uint32_t seed = 0, fl = 0;
 
         if (S == SG_STEP) {
-            // ================= STEP: brick-DDA steps (common.glsl:423-435 / 470-482) =================
+            // ================= SEGMENT: brick-DDA steps + tentative collisions of up to 32 rays, in registers =================
+            // (common.glsl:423-452 / 470-498; one loop body for camera segments and shadow rays)
             float3 ipos = f3(0.f), idir = f3(1.f), ri = f3(1.f);
             float t = 0.f, tfar = -1.f, tau = 0.f, mip = 3.f, majorant = 0.f;
-            uint32_t steps = 0;
-            bool stepping = act;
-            int ns = SG_STEP;
+            int sub = SG_IDLE;         // SG_STEP: stepping, SG_COLLIDE: waits at a tentative collision, other: left the loop (next stage)
             if (act) {
                 fl = PU(PF_STAGE, slot);
+                sub = int(fl & PL_STAGE);
                 ipos = PLOAD3(PF_IPOS, slot); idir = PLOAD3(PF_IDIR, slot);
-                t = PF(PF_T, slot); tfar = PF(PF_TFAR, slot); tau = PF(PF_TAU, slot); mip = PF(PF_MIP, slot);
-                steps = PU(PF_STEPS, slot);
+                t = PF(PF_T, slot); tfar = PF(PF_TFAR, slot); mip = PF(PF_MIP, slot);
+                seed = PU(PF_SEED, slot);
+                const float tm = PF(PF_TAU, slot);
+                if (sub == SG_COLLIDE) majorant = tm; else tau = tm;
+                fl += PL_VISIT;                                  // hang guard: SEGMENT visits of this ray (>= 1 DDA event each)
+                if (fl >= PL_VISIT_MAX) { t = INFINITY; sub = SG_STEP; }      // no finite ray gets here: end it
                 ri = f3(MT::rcp(idir.x), MT::rcp(idir.y), MT::rcp(idir.z));
             }
+            const bool shadow = (fl & PL_SHADOW) != 0u;
+            constexpr int KC = TF ? VR_SEG_K_COLLIDE_TF : VR_SEG_K_COLLIDE;
+            const int waiting = (n_seg - nsel) + n_nee + n_scat + n_fin;      // slots of the pool this visit does not work on
 #pragma unroll 1
-            for (int rep = 0; rep < VR_POOL_MAX_STEPS; ++rep) {
-                if (stepping) {
-                    if (t < tfar) {
-                        const float3 curr = ipos + t * idir;
-                        const int m = round_mip(mip);
-                        cnt.maj();
-                        majorant = table_majorant(a, curr, m);
-                        const float dt = step_dda(curr, ri, m);
-                        t += dt;
-                        tau -= majorant * dt;
-                        mip = fminf(mip + 0.25f, 3.f);
-                        if (!(tau > 0.f)) {
-                            t += MT::div(tau, majorant);
-                            if (!(t >= tfar)) { ns = SG_COLLIDE; stepping = false; }   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
+            for (int iter = 0; iter < VR_SEG_MAX_ITERS; ++iter) {
+                // ---- STEP ----
+#pragma unroll
+                for (int rep = 0; rep < VR_SEG_STEPS; ++rep) {
+                    if (sub == SG_STEP) {
+                        if (t < tfar) {
+                            const float3 curr = ipos + t * idir;
+                            const int m = round_mip(mip);
+                            cnt.maj();
+                            majorant = table_majorant(a, curr, m);
+                            const float dt = step_dda(curr, ri, m);
+                            t += dt;
+                            tau -= majorant * dt;
+                            mip = fminf(mip + 0.25f, 3.f);
+                            if (!(tau > 0.f)) {
+                                t += MT::div(tau, majorant);
+                                if (!(t >= tfar)) sub = SG_COLLIDE;   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
+                            }
                         }
-                        if (++steps > uint32_t(MAX_RAY_STEPS)) { t = INFINITY; ns = SG_STEP; stepping = true; }
-                    }
-                    if (stepping && !(t < tfar)) {       // the ray left the volume
-                        stepping = false;
-                        ns = (fl & PL_SHADOW) ? SG_SCATTER : SG_FINISH;
+                        if (sub == SG_STEP && !(t < tfar)) sub = shadow ? SG_SCATTER : SG_FINISH;     // the ray left the volume
                     }
                 }
-                if (__popc(__ballot_sync(FULL, stepping)) < VR_POOL_STEP_MIN) break;
-            }
-            if (act) {
-                PF(PF_T, slot) = t; PF(PF_TAU, slot) = tau; PF(PF_MIP, slot) = mip;
-                PU(PF_STEPS, slot) = steps;
-                if (ns == SG_COLLIDE) PF(PF_MAJ, slot) = majorant;
-                if (ns != SG_STEP) {
-                    uint32_t f = (fl & ~(PL_STAGE | PL_LIT | PL_ESCAPED)) | uint32_t(ns);
-                    if (ns == SG_SCATTER) f |= PL_LIT;           // shadow ray got through: SCATTER adds pend * Tr first
-                    if (ns == SG_FINISH) f |= PL_ESCAPED;        // camera segment left the volume: environment on escape
-                    PU(PF_STAGE, slot) = f;
-                }
-            }
-        } else if (S == SG_COLLIDE) {
-            // ================= COLLIDE: tentative collision (common.glsl:436-452 / 483-498) =================
-            if (act) {
-                cnt.dens();
-                fl = PU(PF_STAGE, slot);
-                const bool shadow = (fl & PL_SHADOW) != 0u;
-                const float t = PF(PF_T, slot), majorant = PF(PF_MAJ, slot);
-                seed = PU(PF_SEED, slot);
-                const float3 at = PLOAD3(PF_IPOS, slot) + t * PLOAD3(PF_IDIR, slot);
-                int ns = SG_STEP;
-                float d;
-                float3 tf_rgb = f3(1.f);
-                if (TF) {
-                    const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * (MT::decoded ? density_trilinear_decoded(a.density, at) : density_trilinear(a.density, at)) * a.p.vol_inv_majorant);
-                    d = a.p.vol_majorant * rgba.w;
-                    tf_rgb = f3(rgba.x, rgba.y, rgba.z);
-                } else {
-                    const int3 tap = stochastic_tricubic_filter<MT>(at, seed);
-                    d = a.p.vol_density_scale * ((MT::decoded && VR_DECODED_TAP) ? decoded_value(a.density, tap.x, tap.y, tap.z) : brick_value(a.density, tap.x, tap.y, tap.z));
-                }
-                if (!shadow) {
-                    bool fetched;
-                    const float3 em = lookup_emission<MT>(a, at, seed, fetched);
-                    if (fetched) {
-                        cnt.emis();
-                        const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-                        PSTORE3(PF_L, slot, PLOAD3(PF_L, slot) + PLOAD3(PF_THR, slot) * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant);
-                    }
-                    if (rng(seed) * majorant < d) {          // real collision: the segment ends here (common.glsl:490-496)
-                        float3 thr = PLOAD3(PF_THR, slot) * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
-                        if (TF) thr = thr * tf_rgb;
-                        PSTORE3(PF_THR, slot, thr);
-                        ns = SG_NEE;
-                    }
-                } else {
-                    if (rng(seed) * majorant < d) {          // common.glsl:442-450
-                        float Tr = PF(PF_TR, slot);
-                        Tr *= fmaxf(0.f, 1.f - MT::div(a.p.vol_majorant, majorant));
-                        if (Tr < .1f) {
-                            const float prob = 1 - Tr;
-                            if (rng(seed) < prob) { Tr = 0.f; ns = SG_SCATTER; }   // absorbed: `return 0.f`, nothing is added to L
-                            else Tr = MT::div(Tr, 1 - prob);
+                // ---- COLLIDE (batched) ----
+                const int n_col = __popc(__ballot_sync(FULL, sub == SG_COLLIDE)), n_stp = __popc(__ballot_sync(FULL, sub == SG_STEP));
+                if (n_col >= KC || (n_col > 0 && n_stp < VR_SEG_MIN_STEP)) {
+                    if (sub == SG_COLLIDE) {
+                        cnt.dens();
+                        sub = SG_STEP;
+                        const float3 at = ipos + t * idir;
+                        float d;
+                        float3 tf_rgb = f3(1.f);
+                        if (TF) {
+                            const float4 rgba = tf_lookup<MT>(a, a.p.vol_density_scale * (MT::decoded ? density_trilinear_decoded(a.density, at) : density_trilinear(a.density, at)) * a.p.vol_inv_majorant);
+                            d = a.p.vol_majorant * rgba.w;
+                            tf_rgb = f3(rgba.x, rgba.y, rgba.z);
+                        } else {
+                            const int3 tap = stochastic_tricubic_filter<MT>(at, seed);
+                            d = a.p.vol_density_scale * ((MT::decoded && VR_DECODED_TAP) ? decoded_value(a.density, tap.x, tap.y, tap.z) : brick_value(a.density, tap.x, tap.y, tap.z));
                         }
-                        PF(PF_TR, slot) = Tr;
+                        if (!shadow) {
+                            bool fetched;
+                            const float3 em = lookup_emission<MT>(a, at, seed, fetched);
+                            if (fetched) {
+                                cnt.emis();
+                                const float3 albedo = f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                                PSTORE3(PF_L, slot, PLOAD3(PF_L, slot) + PLOAD3(PF_THR, slot) * (f3(1.f) - albedo) * em * d * a.p.vol_inv_majorant);
+                            }
+                            if (rng(seed) * majorant < d) {          // real collision: the segment ends here (common.glsl:490-496)
+                                float3 thr = PLOAD3(PF_THR, slot) * f3(a.p.vol_albedo[0], a.p.vol_albedo[1], a.p.vol_albedo[2]);
+                                if (TF) thr = thr * tf_rgb;
+                                PSTORE3(PF_THR, slot, thr);
+                                sub = SG_NEE;
+                            }
+                        } else {
+                            if (rng(seed) * majorant < d) {          // common.glsl:442-450
+                                float Tr = PF(PF_TR, slot);
+                                Tr *= fmaxf(0.f, 1.f - MT::div(a.p.vol_majorant, majorant));
+                                if (Tr < .1f) {
+                                    const float prob = 1 - Tr;
+                                    if (rng(seed) < prob) { Tr = 0.f; sub = SG_SCATTER + 8; }   // absorbed: `return 0.f`, nothing is added to L
+                                    else Tr = MT::div(Tr, 1 - prob);
+                                }
+                                PF(PF_TR, slot) = Tr;
+                            }
+                        }
+                        if (sub == SG_STEP) {
+                            tau = -MT::log(1.f - rng(seed));
+                            mip = fmaxf(0.f, mip - 2.f);
+                        }
                     }
                 }
-                if (ns == SG_STEP) {
-                    PF(PF_TAU, slot) = -MT::log(1.f - rng(seed));
-                    PF(PF_MIP, slot) = fmaxf(0.f, PF(PF_MIP, slot) - 2.f);
-                }
+                // leave once the lanes freed by finished rays can be refilled from the pool (at the tail of a launch the pool
+                // runs dry and the loop simply keeps its rays)
+                const int live = __popc(__ballot_sync(FULL, sub <= SG_COLLIDE));
+                if (live == 0 || (live < VR_SEG_EXIT && waiting + (nsel - live) >= 32 - live)) break;
+            }
+            // ---- write back, count the transitions ----
+            const bool absorbed = sub == SG_SCATTER + 8;
+            if (absorbed) sub = SG_SCATTER;
+            if (act) {
+                PF(PF_T, slot) = t; PF(PF_MIP, slot) = mip;
+                PF(PF_TAU, slot) = sub == SG_COLLIDE ? majorant : tau;
                 PU(PF_SEED, slot) = seed;
-                PU(PF_STAGE, slot) = (fl & ~(PL_STAGE | PL_LIT)) | uint32_t(ns);
+                uint32_t f = (fl & ~(PL_STAGE | PL_LIT | PL_ESCAPED)) | uint32_t(sub);
+                if (sub == SG_SCATTER && !absorbed) f |= PL_LIT;    // shadow ray got through: SCATTER adds pend * Tr first
+                if (sub == SG_FINISH) f |= PL_ESCAPED;              // camera segment left the volume: environment on escape
+                PU(PF_STAGE, slot) = f;
+            }
+            {
+                const int c_nee = __popc(__ballot_sync(FULL, act && sub == SG_NEE)), c_scat = __popc(__ballot_sync(FULL, act && sub == SG_SCATTER)),
+                          c_fin = __popc(__ballot_sync(FULL, act && sub == SG_FINISH));
+                n_seg -= c_nee + c_scat + c_fin; n_nee += c_nee; n_scat += c_scat; n_fin += c_fin;
             }
         } else if (S == SG_NEE) {
             // ================= NEE: real collision -> next-event estimation (common.glsl:611-626) =================
@@ -252,7 +277,7 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                     PSTORE3(PF_PEND, slot, f3(MT::div(c.x, Le_pdf.w), MT::div(c.y, Le_pdf.w), MT::div(c.z, Le_pdf.w)));
                     PF(PF_FP, slot) = f_p;
                     PF(PF_TR, slot) = 1.f;
-                    fl = (fl & ~(PL_STAGE | PL_LIT)) | PL_SHADOW | uint32_t(SG_STEP);
+                    fl = (fl & PL_FLAGS & ~(PL_STAGE | PL_LIT)) | PL_SHADOW | uint32_t(SG_STEP);     // new ray: visit counter back to 0
                     rd = w_i; start = true;
                 } else {
                     PU(PF_SEED, slot) = seed;
@@ -260,11 +285,15 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                 }
                 PU(PF_STAGE, slot) = fl;
             }
+            {
+                const int c_seg = __popc(__ballot_sync(FULL, start));
+                n_nee -= nsel; n_seg += c_seg; n_scat += nsel - c_seg;
+            }
         } else if (S == SG_SCATTER) {
             // ================= SCATTER: bounce limit, Russian roulette, phase sampling (common.glsl:628-641) =================
             if (act) {
                 fl = PU(PF_STAGE, slot);
-                if (fl & PL_LIT) {                               // the shadow ray reached the environment (deferred from STEP)
+                if (fl & PL_LIT) {                               // the shadow ray reached the environment (deferred from SEGMENT)
                     const float Tr = PF(PF_TR, slot);
                     if (Tr != 0.f) PSTORE3(PF_L, slot, PLOAD3(PF_L, slot) + PLOAD3(PF_PEND, slot) * Tr);     // (x * 0) stays 0 even if pend overflowed, as in the reference's order
                 }
@@ -291,11 +320,15 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                     const float3 scatter_dir = sample_phase_hg<MT>(dir, a.p.vol_phase_g, s0, s1);
                     PF(PF_FP, slot) = phase_hg<MT>(dot(-dir, scatter_dir), a.p.vol_phase_g);
                     PSTORE3(PF_DIR, slot, scatter_dir);
-                    fl = (fl & ~(PL_STAGE | PL_LIT | PL_SHADOW)) | uint32_t(SG_STEP);
+                    fl = (fl & PL_FLAGS & ~(PL_STAGE | PL_LIT | PL_SHADOW)) | uint32_t(SG_STEP);
                     spos = PLOAD3(PF_POS, slot);
                     rd = scatter_dir; start = true;
                 }
                 PU(PF_STAGE, slot) = fl;
+            }
+            {
+                const int c_seg = __popc(__ballot_sync(FULL, start));
+                n_scat -= nsel; n_seg += c_seg; n_fin += nsel - c_seg;
             }
         } else {
             // ================= FINISH: environment on escape, store the sample, take the next one =================
@@ -314,18 +347,17 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                         Lf = Lf + PLOAD3(PF_THR, slot) * mis_weight * Le;
                     }
                     cnt.samp();                                     // pathtracer_brick.glsl:36: sanitize(L), folded by k_fold
-                    const uint32_t sj = PU(PF_SJ, slot);
-                    VR_LBUF_STORE(a.lbuf + size_t(sj) * a.lbuf_stride + PU(PF_PIX, slot),
+                    const uint32_t sj = PU(PF_SJ, slot), pix = PU(PF_PIX, slot);
+                    VR_LBUF_STORE(a.lbuf + size_t(sj) * a.lbuf_stride + pix,
                                   make_float4(sanitize(Lf.x), sanitize(Lf.y), sanitize(Lf.z), sanitize(fminf(float(n_paths), 1.f))));
-                    const uint32_t tile = PU(PF_TILE, slot);
-                    if (a.tile_cost && !(tile & 0x80000000u)) {     // a dithered quarter of the samples is enough to rank tiles
-                        unsigned now;
-                        asm volatile("mov.u32 %0, %%clock;" : "=r"(now));
-                        atomicAdd(a.tile_cost + tile, (now - PU(PF_TITEM, slot)) >> 8);
+                    if (a.tile_cost) {     // what ranks the tiles for the next launch of this view: path vertices of a dithered quarter of the samples
+                        const uint32_t py = pix / uint32_t(W), px = pix - py * uint32_t(W);
+                        if (((px ^ py ^ sj) & 3u) == 0u)
+                            atomicAdd(a.tile_cost + ((int(py) - a.y0) >> 2) * a.tiles_x + ((int(px) - a.x0) >> 3), 1u + min(n_paths, 4095u));
                     }
                 }
             }
-            int px = 0, py = 0;
+            int px = 0, py = 0, sj = 0;
             bool have_item = false;
             float3 dir = f3(0.f, 0.f, -1.f);
             while (true) {
@@ -368,6 +400,7 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                     py = blk_y0 + (i >> 3);
                     if (px < a.x1 && py < a.y1) {
                         const float4 pr = prep[i];
+                        sj = blk_sj;                               // (the loop may switch to the next block for the other lanes)
                         seed = __float_as_uint(pr.w);
                         dir = f3(pr.x, pr.y, pr.z);
                         have_item = true;
@@ -378,12 +411,8 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
             }
             if (act) {
                 if (have_item) {                                   // new sample: camera ray of the prepared sample
-                    unsigned now;
-                    asm volatile("mov.u32 %0, %%clock;" : "=r"(now));
-                    PU(PF_TITEM, slot) = now;
                     PU(PF_PIX, slot) = uint32_t(py) * uint32_t(W) + uint32_t(px);
-                    PU(PF_SJ, slot) = uint32_t(blk_sj);
-                    PU(PF_TILE, slot) = (((px ^ py ^ blk_sj) & 3) == 0 ? 0u : 0x80000000u) | uint32_t(((py - a.y0) >> 2) * a.tiles_x + ((px - a.x0) >> 3));
+                    PU(PF_SJ, slot) = uint32_t(sj);
                     PU(PF_NPATHS, slot) = 0u;
                     spos = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);
                     PSTORE3(PF_POS, slot, spos);
@@ -397,12 +426,15 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                     PU(PF_STAGE, slot) = uint32_t(SG_IDLE);        // the counter is exhausted
                 }
             }
+            {
+                const int c_seg = __popc(__ballot_sync(FULL, start));
+                n_fin -= nsel; n_seg += c_seg;
+            }
         }
 
         // ================= start the new rays: clip + world->index + first free-flight draw (common.glsl:459-468 / 413-421) =================
         if (start) {
             float tn, tf;
-            PU(PF_STEPS, slot) = 0u;
             if (intersect_box<MT>(spos, rd, a.p.vol_bb_min, a.p.vol_bb_max, tn, tf)) {
                 const Mat4& M = *reinterpret_cast<const Mat4*>(a.p.vol_density_inv_transform);
                 PSTORE3(PF_IPOS, slot, mul_point(M, spos));

@@ -9,7 +9,9 @@
 #include "vr_trace.cuh"
 #include "vr_trace2.cuh"
 #include "vr_trace_pool.cuh"
+#include "vr_probe.cuh"
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges show up in Nsight Systems / ncu --nvtx, no-ops otherwise
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -28,12 +30,22 @@ using namespace vr;
 namespace vr {   // vrb200_strict.cu (-fmad=false): the IEEE cross-check kernels
 cudaError_t launch_trace_pixels(const TraceArgs& a, bool tf, bool count, dim3 grid, cudaStream_t stream);
 const void* strict_persistent_kernel(bool tf, bool count);
+cudaError_t launch_majorant_table_strict(const TraceArgs& a, bool tf, int level, float* out, size_t n, int blocks, cudaStream_t stream);
 }
 
 // ------------------------------------------------------------------------------------------------
 // context
 
 namespace {
+
+// NVTX range around a host-side phase (upload, brick build, trace pass, fold, reduce, read-back): stands in for the
+// reference's TimerQueryGL("trace") (src/main.cpp:479,509-511)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct DeviceGrid {
     bool valid = false;
@@ -50,6 +62,7 @@ struct DeviceGrid {
     uint2* recp = nullptr;       // padded (nb + 2)^3 records for the trilinear fetch
     uint8_t* atlas_lin = nullptr;   // n_slots bricks + one all-zero brick
     size_t n_slots = 0;
+    bool decoded_valid = false;     // cslot / datlas describe the current contents
     uint32_t* cslot = nullptr;      // (nb + 1)^3 cells -> decoded apron block (0 = shared zero block)
     float* datlas = nullptr;        // (n_dblocks + 1) x 729 decoded voxels
     size_t n_dblocks = 0;
@@ -84,9 +97,13 @@ struct vrb_ctx {
     float4* lut = nullptr;
     uint32_t tf_size = 0;
     unsigned long long* counters = nullptr;
-    unsigned int* job_counter = nullptr;
+    unsigned int* job_counter = nullptr;     // two block tickets: consecutive passes of a vrb_trace call alternate between two lanes
     float4* lbuf = nullptr;      // per-launch sample buffer of the persistent kernel: lbuf_samples x (w * h) float4
-    int lbuf_samples = 0;
+    float4* lbuf2 = nullptr;     // the second lane's (allocated when a call has more than one pass)
+    int lbuf_samples = 0, lbuf2_samples = 0;
+    cudaStream_t pass_stream = nullptr;      // second lane: pass k + 1 starts in the tail of pass k (persistent kernels fill the SMs one wave deep)
+    cudaEvent_t ev_entry = nullptr, ev_fold[2] = { nullptr, nullptr };
+    int overlap = 1;             // VRB200_OVERLAP / option "overlap": 0 = every pass on the context's stream
     int pass_samples = 32;       // samples per pixel and pass (VRB200_PASS); bounds lbuf (also capped at 1 GiB = 32 samples at 1080p).
                                  // B200, configs[1]: 16 -> 33.6, 32 -> 36.9, 64 -> 36.7, 128 -> 36.5 Gsamples/s (fixed costs + tail per pass)
     // heaviest-tiles-first scheduling (vr_trace2.cuh): per-tile cost of the last launch, its view key, the sorted order
@@ -170,6 +187,7 @@ size_t mip_words(const uint3& nb, int level) { return size_t(nb.x >> (level + 1)
 
 // builds the tracer layout (records + brick-linear atlas) from the canonical buffers
 int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
+    NvtxRange nvtx_("vrb:finalize_grid (records, linear atlas, decoded blocks)");
     const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
     const uint3 ab = make_uint3(g.atlas_dim.x >> 3, g.atlas_dim.y >> 3, g.atlas_dim.z >> 3);
     g.n_slots = size_t(ab.x) * ab.y * ab.z;
@@ -192,47 +210,55 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
         k_linearize_atlas<<<grid_for(g.n_slots * 64, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.atlas, g.atlas_dim, g.atlas_lin, g.n_slots);
         CK_LAUNCH();
     }
-    // decoded apron blocks for the production trilinear fetch (vr_trace.cuh density_trilinear_decoded)
-    {
-        const size_t nc = size_t(g.nb.x + 1) * (g.nb.y + 1) * (g.nb.z + 1);
-        uint32_t *flags = nullptr, *excl = nullptr;
-        void* tmp = nullptr;
-        size_t tmp_bytes = 0;
-        if (!g.cslot) CK(pool_alloc(&g.cslot, nc * 4, ctx->stream));
-        CK(pool_alloc(&flags, nc * 4, ctx->stream));
-        CK(pool_alloc(&excl, (nc + 1) * 4, ctx->stream));
-        k_cell_flags<<<grid_for(nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.rec, g.nb, flags);
-        CK_LAUNCH();
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, excl, nc, ctx->stream));
-        CK(pool_alloc(&tmp, tmp_bytes, ctx->stream));
-        CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, excl, nc, ctx->stream));
-        k_cell_slots<<<grid_for(nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(flags, excl, nc, g.cslot);
-        CK_LAUNCH();
-        size_t n_blocks = nc;           // small lattices (<= 64 MiB of blocks): worst case, no read-back and no host sync
-        if (nc * DBRICK * 4 > (size_t(64) << 20)) {
-            uint32_t last[2] = { 0, 0 };    // exclusive sum and flag of the last cell -> number of blocks
-            CK(cudaMemcpyAsync(&last[0], excl + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(&last[1], flags + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            n_blocks = size_t(last[0]) + last[1];
-        }
-        if (!g.datlas || n_blocks > g.n_dblocks) {
-            pool_free(g.datlas, ctx->stream);
-            g.datlas = nullptr;
-            CK(pool_alloc(&g.datlas, (n_blocks + 1) * DBRICK * 4, ctx->stream));
-            g.n_dblocks = n_blocks;
-        }
-        CK(cudaMemsetAsync(g.datlas, 0, DBRICK * 4, ctx->stream));      // block 0: zeros
-        if (n_blocks) {
-            GridView v;
-            memset(&v, 0, sizeof v);
-            v.nb = g.nb; v.rec = g.rec; v.atlas_lin = g.atlas_lin;
-            k_decode_cells<<<grid_for(nc * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(v, g.cslot, g.datlas);
-            CK_LAUNCH();
-        }
-        pool_free(flags, ctx->stream); pool_free(excl, ctx->stream); pool_free(tmp, ctx->stream);
-    }
+    g.decoded_valid = false;     // the decoded apron blocks (TF kernels only) are rebuilt on first use: ensure_decoded_blocks
     g.valid = true;
+    return VRB_OK;
+}
+
+// Decoded apron blocks for the production trilinear fetch (vr_trace.cuh density_trilinear_decoded): only the TF kernels read
+// them, and they are 11x the atlas (1024^3 fBm: 0.87 GB written, 0.93 ms), so they are built on the first TF trace of a
+// grid (and by the debug sampler) instead of on every upload / build.
+int ensure_decoded_blocks(vrb_ctx* ctx, DeviceGrid& g) {
+    if (g.decoded_valid) return VRB_OK;
+    NvtxRange nvtx_("vrb:decoded_blocks");
+    const size_t nc = size_t(g.nb.x + 1) * (g.nb.y + 1) * (g.nb.z + 1);
+    uint32_t *flags = nullptr, *excl = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    if (!g.cslot) CK(pool_alloc(&g.cslot, nc * 4, ctx->stream));
+    CK(pool_alloc(&flags, nc * 4, ctx->stream));
+    CK(pool_alloc(&excl, (nc + 1) * 4, ctx->stream));
+    k_cell_flags<<<grid_for(nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.rec, g.nb, flags);
+    CK_LAUNCH();
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, excl, nc, ctx->stream));
+    CK(pool_alloc(&tmp, tmp_bytes, ctx->stream));
+    CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, excl, nc, ctx->stream));
+    k_cell_slots<<<grid_for(nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(flags, excl, nc, g.cslot);
+    CK_LAUNCH();
+    size_t n_blocks = nc;           // small lattices (<= 64 MiB of blocks): worst case, no read-back and no host sync
+    if (nc * DBRICK * 4 > (size_t(64) << 20)) {
+        uint32_t last[2] = { 0, 0 };    // exclusive sum and flag of the last cell -> number of blocks
+        CK(cudaMemcpyAsync(&last[0], excl + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&last[1], flags + (nc - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_blocks = size_t(last[0]) + last[1];
+    }
+    if (!g.datlas || n_blocks > g.n_dblocks) {
+        pool_free(g.datlas, ctx->stream);
+        g.datlas = nullptr;
+        CK(pool_alloc(&g.datlas, (n_blocks + 1) * DBRICK * 4, ctx->stream));
+        g.n_dblocks = n_blocks;
+    }
+    CK(cudaMemsetAsync(g.datlas, 0, DBRICK * 4, ctx->stream));      // block 0: zeros
+    if (n_blocks) {
+        GridView v;
+        memset(&v, 0, sizeof v);
+        v.nb = g.nb; v.rec = g.rec; v.atlas_lin = g.atlas_lin;
+        k_decode_cells<<<grid_for(nc * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(v, g.cslot, g.datlas);
+        CK_LAUNCH();
+    }
+    pool_free(flags, ctx->stream); pool_free(excl, ctx->stream); pool_free(tmp, ctx->stream);
+    g.decoded_valid = true;
     return VRB_OK;
 }
 
@@ -260,6 +286,7 @@ int compute_n_bricks(const uint32_t dim[3], uint3& nb) {
 // u8 voxels of a DenseGrid
 int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d_vox, const uint32_t dim[3], float vmin, float vmax,
                              const float* d_values = nullptr) {
+    NvtxRange nvtx_("vrb:brick_build");
     uint3 nb;
     if (compute_n_bricks(dim, nb) != VRB_OK)
         return fail(ctx, VRB_ERR_TOO_MANY_BRICKS, "exceeded max brick count of 1024");
@@ -282,20 +309,16 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
         k_brick_range_values<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_values, nb, g.range, flags);
         CK_LAUNCH();
     } else if ((dim[0] & 7u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 7u) == 0) {
-        // separable, coalesced reduction over the 12^3 windows (x, then y, then z)
-        uint16_t *m1 = nullptr, *m2 = nullptr;
-        const size_t n1 = size_t(dim[2]) * dim[1] * nb.x, n2 = size_t(dim[2]) * nb.y * nb.x;
-        CK(pool_alloc(&m1, n1 * 2, ctx->stream));
+        // separable reduction over the 12^3 windows: x and y fused in one streaming pass over the voxels, then z
+        uint16_t* m2 = nullptr;
+        const size_t n2 = size_t(dim[2]) * nb.y * nb.x;
         CK(pool_alloc(&m2, n2 * 2, ctx->stream));
-        const size_t n_rows = size_t(dim[2]) * dim[1];
-        if (dim[2] > 65535u) return fail(ctx, VRB_ERR_INVALID, "grid too deep");
-        k_range_x<<<dim3(unsigned((n_rows + 7) / 8), (nb.x + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(reinterpret_cast<const uint2*>(d_vox), vdim, nb.x, n_rows, m1);
-        CK_LAUNCH();
-        k_range_y<<<dim3((nb.x + 31) / 32, (nb.y + 7) / 8, dim[2]), dim3(32, 8), 0, ctx->stream>>>(m1, vdim, nb, m2);
+        if ((dim[2] + 3) / 4 > 65535u) return fail(ctx, VRB_ERR_INVALID, "grid too deep");
+        const int vec16 = ((dim[0] & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 15u) == 0) ? 1 : 0;
+        k_range_xy<<<dim3((nb.x + 63) / 64, (nb.y + RANGE_BAND_BY - 1) / RANGE_BAND_BY, (dim[2] + 3) / 4), dim3(32, 4), 0, ctx->stream>>>(d_vox, vdim, nb, m2, vec16);
         CK_LAUNCH();
         k_range_z<<<grid_for(n, 256, ctx->sm_count, 32), 256, 0, ctx->stream>>>(m2, vdim, vmin, vmax, nb, g.range, flags);
         CK_LAUNCH();
-        pool_free(m1, ctx->stream);
         pool_free(m2, ctx->stream);
     } else {
         k_brick_range<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_vox, vdim, vmin, vmax, nb, g.range, flags);
@@ -377,6 +400,10 @@ int fill_trace_args(vrb_ctx* ctx, const vrb_params* p, TraceArgs& a) {
     if (p->use_transferfunc && (!ctx->lut || ctx->tf_size == 0)) return fail(ctx, VRB_ERR_STATE, "use_transferfunc set but no LUT uploaded");
     memset(&a, 0, sizeof(a));
     a.p = *p;
+    if (p->use_transferfunc && (ctx->kernel == 0 || ctx->kernel == 3)) {      // the fast-math TF kernels sample the decoded apron blocks
+        const int st = ensure_decoded_blocks(ctx, it->second.slot[VRB_SLOT_DENSITY]);
+        if (st) return st;
+    }
     a.density = make_view(it->second.slot[VRB_SLOT_DENSITY]);
     if (p->has_emission) {
         if (!it->second.slot[VRB_SLOT_EMISSION].valid) return fail(ctx, VRB_ERR_STATE, "has_emission set but no emission grid for frame %d", p->frame);
@@ -438,7 +465,11 @@ int vrb_create(int device, vrb_ctx** out) {
     DeviceGuard guard(device);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&ctx->counters, 7 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc(&ctx->job_counter, sizeof(unsigned int)) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->pass_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_entry, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fold[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fold[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaMalloc(&ctx->job_counter, 2 * sizeof(unsigned int)) != cudaSuccess) {
         delete ctx;
         return VRB_ERR_CUDA;
     }
@@ -453,6 +484,7 @@ int vrb_create(int device, vrb_ctx** out) {
     if (const char* e = getenv("VRB200_LPT")) ctx->lpt = atoi(e) != 0;
     if (const char* e = getenv("VRB200_CULL")) ctx->cull = atoi(e) != 0;
     if (const char* e = getenv("VRB200_PASS")) ctx->pass_samples = std::max(1, atoi(e));
+    if (const char* e = getenv("VRB200_OVERLAP")) ctx->overlap = atoi(e) != 0;
     if (const char* e = getenv("VRB200_KERNEL")) ctx->kernel = std::min(3, std::max(0, atoi(e)));
     cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream);
     *out = ctx;
@@ -467,7 +499,10 @@ void vrb_destroy(vrb_ctx* ctx) {
     if (!ctx->color_external) cudaFree(ctx->color);
     cudaFree(ctx->tile_cost); cudaFree(ctx->tile_cost_sorted); cudaFree(ctx->tile_iota); cudaFree(ctx->tile_order); cudaFree(ctx->sort_tmp);
     cudaFree(ctx->tile_live); cudaFree(ctx->tile_key); cudaFree(ctx->live_info);
-    cudaFree(ctx->lbuf); cudaFree(ctx->env_stage);
+    cudaFree(ctx->lbuf); cudaFree(ctx->lbuf2); cudaFree(ctx->env_stage);
+    if (ctx->pass_stream) cudaStreamDestroy(ctx->pass_stream);
+    if (ctx->ev_entry) cudaEventDestroy(ctx->ev_entry);
+    for (int i = 0; i < 2; ++i) if (ctx->ev_fold[i]) cudaEventDestroy(ctx->ev_fold[i]);
     cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->env_split); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
     cudaStreamSynchronize(ctx->stream);
     {   // hand the pooled grid memory back to the driver
@@ -501,8 +536,8 @@ int vrb_resize(vrb_ctx* ctx, int w, int h) {
     DeviceGuard guard(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
     if (!ctx->color_external) cudaFree(ctx->color);
-    cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->lbuf);
-    ctx->color = nullptr; ctx->fb = nullptr; ctx->ldr = nullptr; ctx->lbuf = nullptr; ctx->lbuf_samples = 0; ctx->color_external = false;
+    cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->lbuf); cudaFree(ctx->lbuf2);
+    ctx->color = nullptr; ctx->fb = nullptr; ctx->ldr = nullptr; ctx->lbuf = nullptr; ctx->lbuf2 = nullptr; ctx->lbuf_samples = ctx->lbuf2_samples = 0; ctx->color_external = false;
     ctx->w = w; ctx->h = h;
     const size_t n = size_t(w) * h;
     CK(cudaMalloc(&ctx->color, n * sizeof(float4)));
@@ -546,6 +581,7 @@ int vrb_grid_free(vrb_ctx* ctx, int slot, int frame) {
 }
 
 int vrb_grid_upload_brick(vrb_ctx* ctx, int slot, int frame, const vrb_brick_view* v) {
+    NvtxRange nvtx_("vrb:grid_upload_brick");
     int st = check_slot_frame(ctx, slot, frame);
     if (st) return st;
     if (!v || !v->indirection || !v->range || !v->range_mips[0] || !v->range_mips[1] || !v->range_mips[2])
@@ -720,17 +756,20 @@ int vrb_nvdb_open(const void* file, size_t bytes, const char* gridname, vrb_nvdb
         // a raw grid buffer, possibly several grids back to back (GridHandle::read(is, gridName), GridHandle.h:405-426)
         uint32_t n = 0;
         const uint32_t count = rd<uint32_t>(f + G_COUNT);
+        // all offsets are compared in the overflow-safe form `x > bytes - at` (at <= bytes holds throughout): sizes come from the file
         while (true) {
-            if (at + GRID_SIZE > bytes) break;
+            if (at > bytes || GRID_SIZE > bytes - at) break;
             if (strncmp(reinterpret_cast<const char*>(f + at + G_NAME), gridname, G_NAME_LEN) == 0) { found = at; break; }
             if (n++ >= count) break;
-            at += rd<uint64_t>(f + at + G_BYTES);
+            const uint64_t step = rd<uint64_t>(f + at + G_BYTES);
+            if (step < GRID_SIZE || step > bytes - at) break;         // a grid is at least its header; never walk backwards / in place
+            at += step;
         }
         if (found == UINT64_MAX) return nvdb_fail(err, err_len, "No raw grid named \"%s\"", gridname);
     } else {
         // segments: FileHeader (16) + gridCount x (FileMetaData (176) + name) + the grids (io/IO.h:386-431, :568-594)
         const uint64_t key = nvdb_string_hash(gridname);
-        while (found == UINT64_MAX && at + 16 <= bytes) {
+        while (found == UINT64_MAX && at <= bytes && 16 <= bytes - at) {
             const uint64_t magic = rd<uint64_t>(f + at);
             if (magic != MAGIC_NUMB && magic != MAGIC_FILE)
                 return nvdb_fail(err, err_len, "Expected a NanoVDB file, but read a file of unknown type!");
@@ -741,30 +780,36 @@ int vrb_nvdb_open(const void* file, size_t bytes, const char* gridname, vrb_nvdb
             at += 16;
             uint64_t seek = 0, hit = UINT64_MAX;
             for (uint32_t i = 0; i < grid_count; ++i) {
-                if (at + 176 > bytes) return nvdb_fail(err, err_len, "Failed reading FileGridMetaData");
+                if (at > bytes || 176 > bytes - at) return nvdb_fail(err, err_len, "Failed reading FileGridMetaData");
                 const uint64_t file_size = rd<uint64_t>(f + at + 8), name_key = rd<uint64_t>(f + at + 16);
                 const uint32_t name_size = rd<uint32_t>(f + at + 136);
-                if (at + 176 + name_size > bytes) return nvdb_fail(err, err_len, "Failed reading FileGridMetaData");
+                if (name_size > bytes - at - 176) return nvdb_fail(err, err_len, "Failed reading FileGridMetaData");
                 const std::string name(reinterpret_cast<const char*>(f + at + 176), strnlen(reinterpret_cast<const char*>(f + at + 176), name_size));
                 if (hit == UINT64_MAX) {
                     if ((name_key == 0u || name_key == key) && name == gridname) hit = seek;
-                    else seek += file_size;
+                    else {
+                        if (file_size > bytes || seek > bytes - file_size) return nvdb_fail(err, err_len, "Failed reading FileGridMetaData");    // the skipped grids must fit in the file
+                        seek += file_size;
+                    }
                 }
                 at += 176 + name_size;
             }
             if (hit != UINT64_MAX) {
                 if (codec == 1) return nvdb_fail(err, err_len, "ZIP compression codec was disabled during build");
                 if (codec == 2) return nvdb_fail(err, err_len, "BLOSC compression codec was disabled during build");
+                if (hit > bytes - at) return nvdb_fail(err, err_len, "Failed to read Tree from file");
                 found = at + hit;
-            } else
+            } else {
+                if (seek > bytes - at) break;
                 at += seek;
+            }
         }
         if (found == UINT64_MAX) return nvdb_fail(err, err_len, "Grid name '%s' not found in file", gridname);
     }
-    if (found + GRID_SIZE + TREE_SIZE > bytes) return nvdb_fail(err, err_len, "Failed to read Tree from file");
+    if (found > bytes || GRID_SIZE + TREE_SIZE > bytes - found) return nvdb_fail(err, err_len, "Failed to read Tree from file");
     const uint8_t* g = f + found;
     const uint64_t grid_size = rd<uint64_t>(g + G_BYTES);
-    if (grid_size > bytes - found) return nvdb_fail(err, err_len, "Failed to read Tree from file");
+    if (grid_size > bytes - found || grid_size < GRID_SIZE + TREE_SIZE) return nvdb_fail(err, err_len, "Failed to read Tree from file");
     // handle.grid<float>() is null for other value types; !isValid(); !isFogVolume() (grid_nvdb.cpp:10-12)
     if (rd<uint32_t>(g + G_TYPE) != GRID_TYPE_FLOAT || !nvdb_grid_header_valid(g) || rd<uint32_t>(g + G_CLASS) != GRID_CLASS_FOG)
         return nvdb_fail(err, err_len, "Empty or invalid NanoVDB grid!");
@@ -868,6 +913,7 @@ int vrb_debug_sample_density(vrb_ctx* ctx, int slot, int frame, const float* ipo
     if (!ipos_xyz || !out || mode < 0 || mode > 2) return fail(ctx, VRB_ERR_INVALID, "bad arguments");
     if (n == 0) return VRB_OK;
     DeviceGuard guard(ctx->device);
+    if (mode == 1) { st = ensure_decoded_blocks(ctx, it->second.slot[slot]); if (st) return st; }
     float *d_p = nullptr, *d_o = nullptr;
     CK(pool_alloc(&d_p, n * 12, ctx->stream));
     CK(pool_alloc(&d_o, n * 4, ctx->stream));
@@ -924,6 +970,7 @@ int vrb_dense_from_float(vrb_ctx* ctx, const float* data, const uint32_t dim[3],
 }
 
 int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h) {
+    NvtxRange nvtx_("vrb:env_upload (importance map + pyramid)");
     if (!ctx) return VRB_ERR_INVALID;
     if (!rgb || w <= 0 || h <= 0) return fail(ctx, VRB_ERR_INVALID, "bad environment map");
     DeviceGuard guard(ctx->device);
@@ -969,6 +1016,7 @@ int vrb_env_download_impmap(vrb_ctx* ctx, int level, float* out) {
 }
 
 int vrb_tf_upload(vrb_ctx* ctx, const float* rgba, uint32_t n) {
+    NvtxRange nvtx_("vrb:tf_upload");
     if (!ctx) return VRB_ERR_INVALID;
     if (!rgba || n == 0) return fail(ctx, VRB_ERR_INVALID, "empty LUT");
     DeviceGuard guard(ctx->device);
@@ -990,6 +1038,7 @@ int vrb_tf_upload(vrb_ctx* ctx, const float* rgba, uint32_t n) {
 }
 
 int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_samples, const int tile[4], int accum_mode) {
+    NvtxRange nvtx_("vrb:trace");
     if (!ctx) return VRB_ERR_INVALID;
     if (first_sample < 1 || n_samples < 0) return fail(ctx, VRB_ERR_INVALID, "first_sample must be >= 1 (1-based current_sample)");
     if (accum_mode != VRB_ACCUM_MEAN && accum_mode != VRB_ACCUM_SUM) return fail(ctx, VRB_ERR_INVALID, "bad accum_mode");
@@ -1014,6 +1063,8 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     auto mix_key = [&key](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); for (size_t i = 0; i < n; ++i) { key ^= b[i]; key *= 1099511628211ull; } };
     mix_key(&params->vol_density_scale, 4); mix_key(&params->vol_majorant, 4); mix_key(&params->vol_inv_majorant, 4);
     mix_key(&params->use_transferfunc, 4);
+    const int strict_tables = ctx->kernel == 2 ? 1 : 0;      // the IEEE cross-check kernel reads tables filled without FMA contraction
+    mix_key(&strict_tables, 4);
     if (tf) { mix_key(&params->tf_window_left, 4); mix_key(&params->tf_window_width, 4); mix_key(&ctx->lut_version, 8); }
     const size_t n0 = size_t(g.nb.x) * g.nb.y * g.nb.z;
     if (!g.maj[0]) {
@@ -1027,7 +1078,8 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         for (int l = 0; l < 4; ++l) {
             const size_t n = l == 0 ? n0 : mip_words(g.nb, l - 1);
             const int blocks = grid_for(n, 256, ctx->sm_count);
-            if (tf) k_majorant_table<true><<<blocks, 256, 0, ctx->stream>>>(a, l, g.maj[l], n);
+            if (strict_tables) CK(launch_majorant_table_strict(a, tf, l, g.maj[l], n, blocks, ctx->stream));
+            else if (tf) k_majorant_table<true><<<blocks, 256, 0, ctx->stream>>>(a, l, g.maj[l], n);
             else k_majorant_table<false><<<blocks, 256, 0, ctx->stream>>>(a, l, g.maj[l], n);
             CK_LAUNCH();
             ++ctx->trace_launches;
@@ -1045,6 +1097,18 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         ctx->lbuf = nullptr; ctx->lbuf_samples = 0;
         CK(cudaMalloc(&ctx->lbuf, n_px * sizeof(float4) * size_t(want_pass)));
         ctx->lbuf_samples = want_pass;
+    }
+    // two lanes: a call of several passes alternates them between the context's stream and a second one, each with its own
+    // sample buffer and block ticket, so that pass k + 1 starts in the tail of pass k (a persistent kernel fills the SMs exactly one
+    // wave deep: while its last CTAs finish, the next kernel's CTAs take the freed SMs). The folds stay in sample order.
+    const bool two_lanes = ctx->overlap && !ctx->counting && n_samples > pass;
+    if (two_lanes && ctx->lbuf2_samples < pass) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->pass_stream));
+        cudaFree(ctx->lbuf2);
+        ctx->lbuf2 = nullptr; ctx->lbuf2_samples = 0;
+        CK(cudaMalloc(&ctx->lbuf2, n_px * sizeof(float4) * size_t(pass)));
+        ctx->lbuf2_samples = pass;
     }
     a.lbuf = ctx->lbuf;
     a.lbuf_stride = n_px;
@@ -1151,9 +1215,21 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         ctx->trace_blocks[variant] = ctx->sm_count * (per_sm > 0 ? per_sm : 1);   // one resident wave: grid = 148 x blocks/SM
     }
     const int first_end = first_sample + n_samples;
-    for (int s0 = first_sample; s0 < first_end; s0 += pass) {
+    cudaStream_t lane_stream[2] = { ctx->stream, two_lanes ? ctx->pass_stream : ctx->stream };
+    float4* lane_lbuf[2] = { ctx->lbuf, two_lanes ? ctx->lbuf2 : ctx->lbuf };
+    if (two_lanes) {        // the second lane starts behind everything the caller enqueued on the context's stream so far
+        CK(cudaEventRecord(ctx->ev_entry, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->pass_stream, ctx->ev_entry, 0));
+    }
+    int n_pass = 0;
+    bool fold_pending[2] = { false, false };      // ev_fold[lane] marks the end of that lane's latest fold
+    for (int s0 = first_sample; s0 < first_end; s0 += pass, ++n_pass) {
+        const int lane = two_lanes ? (n_pass & 1) : 0;
+        cudaStream_t st_ = lane_stream[lane];
         a.first_sample = s0;
         a.n_samples = std::min(pass, first_end - s0);
+        a.lbuf = lane_lbuf[lane];
+        a.job_counter = ctx->job_counter + lane;
         // 32-bit block counter: tiles * samples blocks per pass (a pass holds at most 2^30 / 16 sample-pixels)
         a.sample_bits = 0;
         while ((1 << a.sample_bits) < a.n_samples) ++a.sample_bits;
@@ -1161,13 +1237,20 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         a.tile_order = ctx->tile_iota;       // natural order
         a.tile_cost = nullptr;
         a.n_live = nullptr;
+        // the fold of pass k comes after the fold of pass k - 1 (other lane): the running mean is sequential in the sample index
+        auto wait_other_fold = [&]() -> cudaError_t {
+            if (two_lanes && fold_pending[lane ^ 1]) return cudaStreamWaitEvent(st_, ctx->ev_fold[lane ^ 1], 0);
+            return cudaSuccess;
+        };
         if (nothing_visible) {
-            k_fold<<<dim3((fold_x1 - fold_x0 + 63) / 64, (fold_y1 - fold_y0 + 3) / 4), 256, 0, ctx->stream>>>(
-                ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode, nullptr, nullptr, 0);
+            CK(wait_other_fold());
+            k_fold<<<dim3((fold_x1 - fold_x0 + 63) / 64, (fold_y1 - fold_y0 + 3) / 4), 256, 0, st_>>>(
+                ctx->color, a.lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode, nullptr, nullptr, 0);
             CK_LAUNCH();
+            if (two_lanes) { CK(cudaEventRecord(ctx->ev_fold[lane], st_)); fold_pending[lane] = true; }
             continue;
         }
-        CK(cudaMemsetAsync(ctx->job_counter, 0, sizeof(unsigned int), ctx->stream));
+        CK(cudaMemsetAsync(a.job_counter, 0, sizeof(unsigned int), st_));
         const bool cost_valid = lpt && ctx->cost_key == vkey;      // the previous pass / launch measured this view
         // The brick mask and the tile order are functions of (view, grid contents, mode): a static view re-uses them and
         // re-sorts from the latest measured costs every ORDER_REUSE passes (mask + keys + 4 radix passes are ~50 us per pass)
@@ -1178,41 +1261,100 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             ++ctx->order_age;
             a.tile_order = ctx->tile_order;
             if (mask) a.n_live = ctx->live_info;
-        } else if (mask) {
+        } else if (mask || cost_valid) {
+            // the order / mask arrays are rewritten: nothing of the other lane may still read them (its tracking kernel reads the
+            // order and the live count, its fold the mask)
+            CK(wait_other_fold());
             ctx->order_key = okey; ctx->order_age = 1;
-            CK(cudaMemsetAsync(ctx->tile_live, 0, size_t(n_tiles) * 4, ctx->stream));
-            CK(cudaMemsetAsync(ctx->live_info, 0, 8, ctx->stream));
-            k_tile_mask<<<grid_for(n0, 128, ctx->sm_count), 128, 0, ctx->stream>>>(a, g.maj[0], ctx->tile_live, ctx->live_info, (a.y1 - a.y0 + 3) / 4);
-            CK_LAUNCH();
-            k_tile_keys<<<grid_for(size_t(n_tiles), 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->tile_live, cost_valid ? ctx->tile_cost : nullptr, ctx->tile_key, ctx->live_info, n_tiles);
-            CK_LAUNCH();
-            ctx->trace_launches += 2;      // k_tile_mask + k_tile_keys
-            size_t tmp_bytes = ctx->sort_tmp_bytes;
-            CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_key, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
+            if (mask) {
+                CK(cudaMemsetAsync(ctx->tile_live, 0, size_t(n_tiles) * 4, st_));
+                CK(cudaMemsetAsync(ctx->live_info, 0, 8, st_));
+                k_tile_mask<<<grid_for(n0, 128, ctx->sm_count), 128, 0, st_>>>(a, g.maj[0], ctx->tile_live, ctx->live_info, (a.y1 - a.y0 + 3) / 4);
+                CK_LAUNCH();
+                k_tile_keys<<<grid_for(size_t(n_tiles), 256, ctx->sm_count), 256, 0, st_>>>(ctx->tile_live, cost_valid ? ctx->tile_cost : nullptr, ctx->tile_key, ctx->live_info, n_tiles);
+                CK_LAUNCH();
+                ctx->trace_launches += 2;      // k_tile_mask + k_tile_keys
+                size_t tmp_bytes = ctx->sort_tmp_bytes;
+                CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_key, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, st_));
+                a.n_live = ctx->live_info;
+            } else {
+                size_t tmp_bytes = ctx->sort_tmp_bytes;
+                CK(cudaStreamSynchronize(st_) == cudaSuccess ? cudaSuccess : cudaGetLastError());
+                CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, st_));
+            }
             a.tile_order = ctx->tile_order;
-            a.n_live = ctx->live_info;
-        } else if (cost_valid) {
-            ctx->order_key = okey; ctx->order_age = 1;
-            size_t tmp_bytes = ctx->sort_tmp_bytes;
-            CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp, tmp_bytes, ctx->tile_cost, ctx->tile_cost_sorted, ctx->tile_iota, ctx->tile_order, n_tiles, 0, 32, ctx->stream));
-            a.tile_order = ctx->tile_order;
+            if (lpt) CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, st_));     // costs accumulate until the next re-sort
         }
         if (lpt) {
+            if (ctx->cost_key != vkey) CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, st_));   // first pass of a new view
             ctx->cost_key = vkey;
-            CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, ctx->stream));
             a.tile_cost = ctx->tile_cost;
         }
         const int per_block = pool ? VR_POOL_WARPS * (VR_POOL_SLOTS / 32) : VR_TRACE_BLOCK / 32;     // blocks of 32 samples one CTA holds at a time
         const int needed = (n_tiles * a.n_samples + per_block - 1) / per_block;
         const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
         void* kargs[] = { (void*)&a };
-        CK(cudaLaunchKernel(fn, dim3(blocks), dim3(block_threads), kargs, dyn_smem, ctx->stream));
+        nvtxRangePushA("vrb:trace pass (tracking kernel)");
+        CK(cudaLaunchKernel(fn, dim3(blocks), dim3(block_threads), kargs, dyn_smem, st_));
+        nvtxRangePop();
+        NvtxRange nvtx_fold("vrb:trace pass (fold)");
         ctx->trace_launches += 2;          // the tracking kernel + k_fold below
-        k_fold<<<dim3((fold_x1 - fold_x0 + 63) / 64, (fold_y1 - fold_y0 + 3) / 4), 256, 0, ctx->stream>>>(
-            ctx->color, ctx->lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode,
+        CK(wait_other_fold());
+        k_fold<<<dim3((fold_x1 - fold_x0 + 63) / 64, (fold_y1 - fold_y0 + 3) / 4), 256, 0, st_>>>(
+            ctx->color, a.lbuf, n_px, ctx->w, fold_x0, fold_y0, fold_x1, fold_y1, a.x0, a.y0, a.x1, a.y1, s0, a.n_samples, accum_mode,
             mask ? ctx->tile_live : nullptr, mask ? ctx->live_info : nullptr, a.tiles_x);
         CK_LAUNCH();
+        if (two_lanes) { CK(cudaEventRecord(ctx->ev_fold[lane], st_)); fold_pending[lane] = true; }
     }
+    // the caller's stream continues behind the second lane's last fold
+    if (two_lanes && fold_pending[1]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fold[1], 0));
+    return VRB_OK;
+}
+
+int vrb_probe_bandwidth(vrb_ctx* ctx, size_t bytes, int mode, double* gbytes_per_s) {
+    if (!ctx) return VRB_ERR_INVALID;
+    if (!gbytes_per_s || bytes < (size_t(1) << 20) || bytes > (size_t(8) << 30) || (mode != 0 && mode != 1)) return fail(ctx, VRB_ERR_INVALID, "bad probe arguments");
+    DeviceGuard guard(ctx->device);
+    uint4* buf = nullptr;
+    uint32_t* sink = nullptr;
+    CK(cudaMalloc(&buf, bytes));
+    CK(cudaMalloc(&sink, 4));
+    CK(cudaMemsetAsync(buf, 1, bytes, ctx->stream));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    double moved = 0;
+    if (mode == 0) {
+        const size_t n16 = bytes / 16;
+        const int passes = int(std::max<size_t>(1, (size_t(8) << 30) / bytes));        // ~8 GiB of traffic per timed launch
+        k_probe_stream<<<ctx->sm_count * 4, 512, 0, ctx->stream>>>(buf, n16, 1, sink);
+        for (int r = 0; r < 5; ++r) {
+            CK(cudaEventRecord(e0, ctx->stream));
+            k_probe_stream<<<ctx->sm_count * 4, 512, 0, ctx->stream>>>(buf, n16, passes, sink);
+            CK(cudaEventRecord(e1, ctx->stream));
+            CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::min(best, ms);
+        }
+        moved = double(n16) * 16.0 * passes;
+    } else {
+        const uint32_t n_sectors = uint32_t(bytes / 32);
+        const int iters = 256, grid = ctx->sm_count * 16;
+        k_probe_gather<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(buf), n_sectors, 8, sink);
+        for (int r = 0; r < 5; ++r) {
+            CK(cudaEventRecord(e0, ctx->stream));
+            k_probe_gather<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(buf), n_sectors, iters, sink);
+            CK(cudaEventRecord(e1, ctx->stream));
+            CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::min(best, ms);
+        }
+        moved = double(grid) * 256.0 * iters * 4.0 * 32.0;      // sectors x 32 B
+    }
+    CK_LAUNCH();
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf); cudaFree(sink);
+    *gbytes_per_s = moved / (double(best) * 1e-3) / 1e9;
     return VRB_OK;
 }
 
@@ -1223,6 +1365,7 @@ int vrb_set_option(vrb_ctx* ctx, const char* name, int value) {
     else if (!strcmp(name, "cull")) ctx->cull = value != 0;
     else if (!strcmp(name, "count_culled")) ctx->count_culled = value != 0;
     else if (!strcmp(name, "async_upload")) ctx->async_upload = value != 0;
+    else if (!strcmp(name, "overlap")) ctx->overlap = value != 0;
     else if (!strcmp(name, "pass")) { if (value < 1) return fail(ctx, VRB_ERR_INVALID, "pass must be >= 1"); ctx->pass_samples = value; }
     else return fail(ctx, VRB_ERR_INVALID, "unknown option '%s'", name);
     return VRB_OK;
@@ -1292,6 +1435,7 @@ int vrb_get_counters(vrb_ctx* ctx, vrb_counters* out) {
 }
 
 int vrb_tonemap(vrb_ctx* ctx, float exposure, float gamma, int in_place, int tonemapping) {
+    NvtxRange nvtx_("vrb:tonemap");
     if (!ctx) return VRB_ERR_INVALID;
     if (!ctx->color) return fail(ctx, VRB_ERR_STATE, "no colour buffer");
     DeviceGuard guard(ctx->device);
@@ -1304,6 +1448,7 @@ int vrb_tonemap(vrb_ctx* ctx, float exposure, float gamma, int in_place, int ton
 }
 
 int vrb_download_color(vrb_ctx* ctx, float* out, int channels) {
+    NvtxRange nvtx_("vrb:download_color");
     if (!ctx) return VRB_ERR_INVALID;
     if (!ctx->color) return fail(ctx, VRB_ERR_STATE, "no colour buffer");
     if (!out || (channels != 3 && channels != 4)) return fail(ctx, VRB_ERR_INVALID, "channels must be 3 or 4");
@@ -1355,6 +1500,7 @@ int vrb_upload_color(vrb_ctx* ctx, const float* rgba) {
 void* vrb_color_device_ptr(vrb_ctx* ctx) { return ctx ? ctx->color : nullptr; }
 
 int vrb_reduce(vrb_ctx* const* ctxs, int n, int root) {
+    NvtxRange nvtx_("vrb:reduce");
     if (!ctxs || n <= 0 || root < 0 || root >= n) return VRB_ERR_INVALID;
     vrb_ctx* ctx = ctxs[root];
     if (!ctx || !ctx->color) return VRB_ERR_INVALID;
@@ -1377,6 +1523,7 @@ int vrb_reduce(vrb_ctx* const* ctxs, int n, int root) {
 }
 
 int vrb_copy_rows(vrb_ctx* dst, vrb_ctx* src, int y0, int y1) {
+    NvtxRange nvtx_("vrb:copy_rows");
     if (!dst || !src) return VRB_ERR_INVALID;
     vrb_ctx* ctx = dst;
     if (!dst->color || !src->color || dst->w != src->w || dst->h != src->h) return fail(ctx, VRB_ERR_INVALID, "contexts do not share a resolution");

@@ -26,6 +26,14 @@ cudaError_t launch_trace_pixels(const TraceArgs& a, bool tf, bool count, dim3 gr
     return cudaGetLastError();
 }
 
+// the per-level majorant tables the persistent kernel reads, filled with THIS unit's arithmetic (kind 1 evaluates the same
+// expression inline, majorant_at): one rounding difference in a majorant moves every later collision point of a ray
+cudaError_t launch_majorant_table_strict(const TraceArgs& a, bool tf, int level, float* out, size_t n, int blocks, cudaStream_t stream) {
+    if (tf) k_majorant_table<true><<<blocks, 256, 0, stream>>>(a, level, out, n);
+    else k_majorant_table<false><<<blocks, 256, 0, stream>>>(a, level, out, n);
+    return cudaGetLastError();
+}
+
 // the lane-resident persistent kernel with StrictMath (kind 2): must reproduce kind 1 path for path
 const void* strict_persistent_kernel(bool tf, bool count) {
     if (count) return tf ? (const void*)k_trace_persistent<true, true, StrictMath> : (const void*)k_trace_persistent<false, true, StrictMath>;

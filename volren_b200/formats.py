@@ -120,7 +120,30 @@ def load_brick(path) -> BrickGridData:
     if n_mips != 3:
         raise ValueError(f"expected 3 range mipmaps, found {n_mips}")
     ad = (atlas.shape[2], atlas.shape[1], atlas.shape[0])
-    return BrickGridData(n_bricks, ad, count, ind, rng, atlas, mips, min_maj, transform)
+    g = BrickGridData(n_bricks, ad, count, ind, rng, atlas, mips, min_maj, transform)
+    check_brick_layout(g)
+    return g
+
+
+def check_brick_layout(g) -> None:
+    """The buffer shapes BrickGrid's constructor produces (grid_brick.cpp:60-141) and the upload relies on: it copies
+    n_bricks-sized blocks out of these arrays, so a corrupt file must be rejected before it gets there."""
+    nb = tuple(int(v) for v in g.n_bricks)
+    if any(n == 0 or n >= 1024 or n % 8 for n in nb):
+        raise ValueError(f"n_bricks {nb} must be multiples of 8 in [8, 1016]")
+    want = (nb[2], nb[1], nb[0])
+    for name in ("indirection", "range"):
+        a = np.asarray(getattr(g, name))
+        if a.shape != want:
+            raise ValueError(f"{name} has shape {a.shape}, n_bricks needs {want}")
+    atlas = np.asarray(g.atlas)
+    if atlas.ndim != 3 or any(s % 8 for s in atlas.shape) or tuple(int(v) for v in g.atlas_dim) != (atlas.shape[2], atlas.shape[1], atlas.shape[0]):
+        raise ValueError(f"atlas shape {atlas.shape} does not match atlas_dim {tuple(g.atlas_dim)} / multiples of 8")
+    if len(g.mips) != 3:
+        raise ValueError(f"expected 3 range mipmaps, found {len(g.mips)}")
+    for i, m in enumerate(g.mips):
+        if np.asarray(m).shape != tuple(n >> (i + 1) for n in want):
+            raise ValueError(f"range mipmap {i} has shape {np.asarray(m).shape}, n_bricks needs {tuple(n >> (i + 1) for n in want)}")
 
 
 def _w_buf3d(out, a):

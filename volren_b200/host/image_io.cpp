@@ -27,6 +27,8 @@ std::string read_line(const std::vector<uint8_t>& d, size_t& pos) {
     return s;
 }
 
+constexpr uint64_t MAX_IMAGE_PIXELS = uint64_t(1) << 28;     // 16k x 16k: far above any environment map, far below size_t overflow
+
 }  // namespace
 
 ImageF load_hdr(const std::string& path, bool flip) {
@@ -46,6 +48,7 @@ ImageF load_hdr(const std::string& path, bool flip) {
     int h = 0, w = 0;
     const std::string res = read_line(d, pos);
     if (sscanf(res.c_str(), "-Y %d +X %d", &h, &w) != 2 || h <= 0 || w <= 0) throw std::runtime_error("Unsupported HDR orientation: " + path);
+    if (uint64_t(w) * uint64_t(h) > MAX_IMAGE_PIXELS) throw std::runtime_error("HDR image too large (" + std::to_string(w) + " x " + std::to_string(h) + "): " + path);
     std::vector<uint8_t> rgbe(size_t(w) * h * 4);
     auto need = [&](size_t n) { if (pos + n > d.size()) throw std::runtime_error("truncated HDR data: " + path); };
     bool flat = w < 8 || w >= 32768;
@@ -135,6 +138,9 @@ ImageF load_png_rgb(const std::string& path, bool flip) {
     const int comps = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!w || !h || !comps || (depth != 8 && depth != 16) || (ctype == 3 && depth != 8) || interlace)
         throw std::runtime_error("unsupported PNG (need 8/16-bit, non-interlaced gray / RGB / palette / alpha variants): " + path);
+    // sizes come from the file: cap them before any product is formed (a crafted IHDR would otherwise wrap size_t and leave
+    // undersized buffers for the unfilter loop)
+    if (uint64_t(w) * uint64_t(h) > MAX_IMAGE_PIXELS) throw std::runtime_error("PNG too large (" + std::to_string(w) + " x " + std::to_string(h) + "): " + path);
     const size_t bpp = size_t(comps) * (depth / 8), stride = size_t(w) * bpp;
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf raw_len = uLongf(raw.size());

@@ -39,7 +39,8 @@ void upload_grid(vrb_ctx* ctx, int slot, int frame, const voldata::Volume::GridP
         return;
     }
     const auto brick = voldata::Volume::to_brick_grid(grid);
-    if (brick->range_mipmaps.size() != 3) throw std::runtime_error("brick grid without 3 range mipmaps");
+    const std::string why = brick->check_layout();     // the upload copies n_bricks-sized blocks out of these vectors
+    if (!why.empty()) throw std::runtime_error("malformed brick grid: " + why);
     vrb_brick_view v;
     memset(&v, 0, sizeof v);
     for (int a = 0; a < 3; ++a) {

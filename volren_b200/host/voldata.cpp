@@ -290,7 +290,27 @@ std::shared_ptr<BrickGrid> load_brick_grid(const std::string& path) {
     if (n_mips > 16) throw std::runtime_error("corrupt brick grid: " + path);
     g->range_mipmaps.resize(n_mips);
     for (auto& m : g->range_mipmaps) r.buf3d(m);
+    const std::string why = g->check_layout();
+    if (!why.empty()) throw std::runtime_error("corrupt brick grid (" + why + "): " + path);
     return g;
+}
+
+// The invariants of a BrickGrid the constructor establishes (grid_brick.cpp:60-141) and the uploads rely on: a file or a
+// hand-assembled grid that breaks them would make the upload read past its host buffers.
+std::string BrickGrid::check_layout() const {
+    for (int a = 0; a < 3; ++a)
+        if (n_bricks[a] == 0 || n_bricks[a] >= 1024u || (n_bricks[a] & 7u)) return "n_bricks must be multiples of 8 in [8, 1016]";
+    const size_t n = size_t(n_bricks.x) * n_bricks.y * n_bricks.z;
+    if (!(indirection.stride == n_bricks) || indirection.data.size() != n) return "indirection does not match n_bricks";
+    if (!(range.stride == n_bricks) || range.data.size() != n) return "range does not match n_bricks";
+    if ((atlas.stride.x & 7u) || (atlas.stride.y & 7u) || (atlas.stride.z & 7u) ||
+        atlas.data.size() != size_t(atlas.stride.x) * atlas.stride.y * atlas.stride.z) return "atlas stride / size mismatch";
+    if (range_mipmaps.size() != 3) return "expected 3 range mipmaps";
+    for (uint32_t i = 0; i < 3; ++i) {
+        const uvec3 d(n_bricks.x >> (i + 1), n_bricks.y >> (i + 1), n_bricks.z >> (i + 1));
+        if (!(range_mipmaps[i].stride == d) || range_mipmaps[i].data.size() != size_t(d.x) * d.y * d.z) return "range mipmap " + std::to_string(i) + " does not match n_bricks";
+    }
+    return std::string();
 }
 
 void write_grid(const std::shared_ptr<Grid>& grid, const std::string& path) {

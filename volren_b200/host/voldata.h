@@ -85,6 +85,7 @@ public:
     size_t num_voxels() const override;
     size_t size_bytes() const override;
     std::string to_string(const std::string& indent = "") const override;
+    std::string check_layout() const;            // "" when the buffers have the shapes the constructor produces, else what is wrong
     uvec3 n_bricks;
     std::pair<float, float> min_maj;
     size_t brick_counter;

@@ -1,6 +1,7 @@
 """Multi-GPU rendering, one process per GPU (torch.distributed): the scene is replicated on every rank, the work is
-split by spp slice or by image tile and the RGBA32F accumulation buffers are combined with ONE
-collective per batch -- `reduce(SUM)` over NCCL/NVLink on GPUs, gloo in the CPU tests. Every (pixel, sample) depends only
+split by spp slice or by image tile and the RGBA32F accumulation buffers are combined with ONE exchange
+per frame -- spp slices: `reduce(SUM)` of the float4 images; tiles: every rank sends just its own row band to the
+destination rank (point-to-point, no arithmetic) -- over NCCL/NVLink on GPUs, gloo in the CPU tests. Every (pixel, sample) depends only
 on (seed, pixel, W, sample index, scene) (reference shader/pathtracer_brick.glsl:28), so no other exchange exists.
 
 The tracer is injected (`trace_fn`): on a GPU box it is `Context.trace` rendering into the bound colour tensor; the
@@ -85,12 +86,9 @@ class PartitionedRenderer:
             if reduce:
                 self.finish()
             return mine
-        # tiles: every rank owns a band of rows and keeps the reference running mean there; rows outside the band are
-        # zero, so the SUM reduction assembles the image exactly (x + 0 == x)
+        # tiles: every rank owns a band of rows and keeps the reference running mean there (bit-identical to the single-GPU
+        # image); the other rows of its buffer are scratch
         y0, y1 = row_bands(H, self.world)[self.rank]
-        if self.samples > 0 and not self.pending:     # rows that are not this rank's own (gathered or scratch) must not enter the next sum
-            self.color[:y0].zero_()
-            self.color[y1:].zero_()
         if y0 < y1:
             self.trace_fn(first, n_samples, (0, y0, W, y1), ACCUM_MEAN)
         self.samples += n_samples
@@ -113,11 +111,20 @@ class PartitionedRenderer:
             return
         if not self.pending:
             return
+        # gather the bands: rank r sends rows [y0_r, y1_r) to dst, which receives them in place (contiguous row slices of
+        # the (H, W, 4) image) -- (world - 1) / world of one image moves instead of a full-image reduce of mostly zeros
         H = int(self.color.shape[0])
-        y0, y1 = row_bands(H, self.world)[self.rank]
-        keep = self.color[y0:y1].clone() if self.rank != self.dst else None
-        self.dist.reduce(self.color, dst=self.dst, op=self.dist.ReduceOp.SUM, group=self.group)
-        if keep is not None:     # reduce() may scribble partial sums into non-destination buffers (gloo does)
-            self.color.zero_()
-            self.color[y0:y1] = keep
+        bands = row_bands(H, self.world)
+        ops = []
+        if self.rank == self.dst:
+            for r, (y0, y1) in enumerate(bands):
+                if r != self.dst and y0 < y1:
+                    ops.append(self.dist.P2POp(self.dist.irecv, self.color[y0:y1], r, self.group))
+        else:
+            y0, y1 = bands[self.rank]
+            if y0 < y1:
+                ops.append(self.dist.P2POp(self.dist.isend, self.color[y0:y1], self.dst, self.group))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
         self.pending = False
