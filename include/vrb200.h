@@ -135,7 +135,8 @@ int vrb_grid_upload_brick(vrb_ctx* ctx, int slot, int frame, const vrb_brick_vie
  * voxels_u8: dim[0]*dim[1]*dim[2] bytes, HOST memory; (vmin, vmax) = DenseGrid::min_value/max_value. */
 int vrb_grid_build_from_dense(vrb_ctx* ctx, int slot, int frame, const uint8_t* voxels_u8,
                               const uint32_t dim[3], float vmin, float vmax);
-/* same, voxels already resident in DEVICE memory of ctx's device */
+/* same, voxels already resident in DEVICE memory of ctx's device. The build runs on the context's stream (vrb_set_stream): the
+ * voxels must be complete with respect to THAT stream -- written on it, or the writer synchronised -- like any CUDA consumer. */
 int vrb_grid_build_from_dense_device(vrb_ctx* ctx, int slot, int frame, const void* d_voxels_u8,
                                      const uint32_t dim[3], float vmin, float vmax);
 /* voldata::BrickGrid::BrickGrid(const Grid&) for ANY Grid source (grid_brick.cpp:60-142 with the virtual Grid::lookup,

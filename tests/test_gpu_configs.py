@@ -62,6 +62,7 @@ def test_c3_shaped_fbm_cloud(ctx, oracle, env_rgb, env_pyramid):
     import workloads as wl
     n = 512
     vox = wl.fbm_cloud(n)
+    torch.cuda.synchronize()              # the voxels are written on torch's stream, the build reads them on the context's own
     ctx.grid_clear()
     ctx.grid_build_from_dense_device(vox.data_ptr(), (n, n, n), 0.0, 1.0)
     ctx.env_upload(env_rgb)
@@ -90,6 +91,7 @@ def test_c4_shaped_ct_phantom_with_turbo_lut(ctx, oracle, env_rgb, env_pyramid):
     import workloads as wl
     dims = (512, 512, 1800)
     vox = wl.ct_phantom(*dims)
+    torch.cuda.synchronize()              # the voxels are written on torch's stream, the build reads them on the context's own
     ctx.grid_clear()
     ctx.grid_build_from_dense_device(vox.data_ptr(), dims, 0.0, 1.0)
     del vox
@@ -117,6 +119,8 @@ def test_c5_shaped_animated_frames(ctx, oracle, env_rgb, env_pyramid):
     import workloads as wl
     n, frames = 64, 4
     vols = wl.fbm_frames(n, frames, threshold=0.25)
+    import torch
+    torch.cuda.synchronize()              # the voxels are written on torch's stream, the build reads them on the context's own
     ctx.grid_clear()
     for i, v in enumerate(vols):
         ctx.grid_build_from_dense_device(v.data_ptr(), (n, n, n), 0.0, 1.0, frame=i)
@@ -185,7 +189,11 @@ def test_two_gib_atlas_addressing(ctx, env_rgb):
     dims = (1024, 1024, 2048)
     w, h, d = dims
     g = torch.Generator(device="cuda").manual_seed(5)
-    vox = torch.randint(1, 256, (d, h, w), device="cuda", dtype=torch.uint8, generator=g)   # no zero voxel: (almost) no brick stays empty
+    vox = torch.empty((d, h, w), device="cuda", dtype=torch.uint8)
+    for z0 in range(0, d, 256):           # filled in slabs of 2^28 voxels
+        vox[z0:z0 + 256] = torch.randint(1, 256, (256, h, w), device="cuda", dtype=torch.uint8, generator=g)   # no zero voxel: no brick stays empty
+    assert int(vox[-8:].min()) >= 1 and int(vox[1024:1032].min()) >= 1
+    torch.cuda.synchronize()              # the voxels are written on torch's stream, the build reads them on the context's own
     ctx.grid_clear()
     ctx.grid_build_from_dense_device(vox.data_ptr(), dims, 0.0, 1.0)
     nb, ad, count = ctx.grid_info()

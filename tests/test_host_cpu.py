@@ -342,3 +342,27 @@ def test_files_written_by_the_reference_serialisation(volpy, golden):
     for _ in range(300):
         x, y, z = int(rng.integers(0, 70)), int(rng.integers(0, 33)), int(rng.integers(0, 20))
         assert hb.lookup(volpy.uvec3(x, y, z)) == dec[z, y, x]
+
+
+def test_range_xy_kernel_on_the_cpu(tmp_path):
+    """volren_b200/csrc/vr_brick_range.cuh (x/y part of the brick build's 12^3 window min/max, u16x2 packed) uses no shuffles and
+    no shared memory: tests/cpu_harness/range_xy_host.cpp compiles the SAME source as plain C++ and checks every (z, by, bx)
+    entry against a brute-force loop -- ragged widths, padding columns / rows of n_bricks, several y-bands, dense and sparse data."""
+    import subprocess
+    exe = tmp_path / "range_xy_host"
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpu_harness", "range_xy_host.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-o", str(exe), src], check=True)
+    res = subprocess.run([str(exe), "11"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "FAIL" not in res.stdout, res.stdout[-2000:]
+
+
+def test_fast_encode_expression_on_the_cpu(tmp_path):
+    """encode_code_fast (vr_brick.cuh: division by the brick's correctly rounded reciprocal + two fma corrections, trunc-based
+    round) is the brick build's table entry; tests/cpu_harness/encode_fast_host.c evaluates the same IEEE operations in C against
+    the reference's plain expression (grid_brick.cpp:45-48) on random fp16 ranges, incl. collapsed (span == 0) ones."""
+    import subprocess
+    exe = tmp_path / "encode_fast_host"
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpu_harness", "encode_fast_host.c")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), src, "-lm"], check=True)
+    res = subprocess.run([str(exe), "20000000"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "bad 0" in res.stdout, res.stdout[-2000:]

@@ -59,7 +59,8 @@ struct DeviceGrid {
     uint32_t* mips[3] = { nullptr, nullptr, nullptr };
     // tracer layout
     uint2* rec = nullptr;
-    uint2* recp = nullptr;       // padded (nb + 2)^3 records for the trilinear fetch
+    uint2* recp = nullptr;       // padded (nb + 2)^3 records for the trilinear fetch (ensure_padded_records)
+    bool recp_valid = false;
     uint8_t* atlas_lin = nullptr;   // n_slots bricks + one all-zero brick
     size_t n_slots = 0;
     bool decoded_valid = false;     // cslot / datlas describe the current contents
@@ -186,7 +187,7 @@ inline int grid_for(size_t n, int block, int sm_count, int per_sm = 16) {
 size_t mip_words(const uint3& nb, int level) { return size_t(nb.x >> (level + 1)) * (nb.y >> (level + 1)) * (nb.z >> (level + 1)); }
 
 // builds the tracer layout (records + brick-linear atlas) from the canonical buffers
-int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
+int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false, bool lin_done = false) {     // lin_done: the builder wrote rec and atlas_lin itself
     NvtxRange nvtx_("vrb:finalize_grid (records, linear atlas, decoded blocks)");
     const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
     const uint3 ab = make_uint3(g.atlas_dim.x >> 3, g.atlas_dim.y >> 3, g.atlas_dim.z >> 3);
@@ -195,18 +196,17 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
     if (!reuse) {
         CK(pool_alloc(&g.rec, n * sizeof(uint2), ctx->stream));
         CK(pool_alloc(&g.atlas_lin, (g.n_slots + 1) * 512, ctx->stream));
-        CK(pool_alloc(&g.recp, size_t(g.nb.x + 2) * (g.nb.y + 2) * (g.nb.z + 2) * sizeof(uint2), ctx->stream));
     }
     g.maj_key = 0;   // the majorant tables (if any) belong to the previous contents
     static uint64_t grid_versions = 0;
     g.version = ++grid_versions;
-    CK(cudaMemsetAsync(g.atlas_lin + g.n_slots * 512, 0, 512, ctx->stream));   // the all-zero brick
-    k_make_records<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.indirection, g.range, n, ab, g.rec);
-    CK_LAUNCH();
-    const size_t np = size_t(g.nb.x + 2) * (g.nb.y + 2) * (g.nb.z + 2);
-    k_make_records_padded<<<grid_for(np, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.rec, g.nb, uint32_t(g.n_slots), g.recp);
-    CK_LAUNCH();
-    if (g.n_slots) {
+    if (!lin_done) CK(cudaMemsetAsync(g.atlas_lin + g.n_slots * 512, 0, 512, ctx->stream));   // the all-zero brick
+    if (!lin_done) {
+        k_make_records<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.indirection, g.range, n, ab, g.rec);
+        CK_LAUNCH();
+    }
+    g.recp_valid = false;        // padded records (8-tap fetch through the u8 atlas: IEEE cross-check kernels, debug sampler): built on first use
+    if (g.n_slots && !lin_done) {
         k_linearize_atlas<<<grid_for(g.n_slots * 64, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.atlas, g.atlas_dim, g.atlas_lin, g.n_slots);
         CK_LAUNCH();
     }
@@ -218,6 +218,16 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false) {
 // Decoded apron blocks for the production trilinear fetch (vr_trace.cuh density_trilinear_decoded): only the TF kernels read
 // them, and they are 11x the atlas (1024^3 fBm: 0.87 GB written, 0.93 ms), so they are built on the first TF trace of a
 // grid (and by the debug sampler) instead of on every upload / build.
+int ensure_padded_records(vrb_ctx* ctx, DeviceGrid& g) {
+    if (g.recp_valid) return VRB_OK;
+    const size_t np = size_t(g.nb.x + 2) * (g.nb.y + 2) * (g.nb.z + 2);
+    if (!g.recp) CK(pool_alloc(&g.recp, np * sizeof(uint2), ctx->stream));
+    k_make_records_padded<<<grid_for(np, 256, ctx->sm_count), 256, 0, ctx->stream>>>(g.rec, g.nb, uint32_t(g.n_slots), g.recp);
+    CK_LAUNCH();
+    g.recp_valid = true;
+    return VRB_OK;
+}
+
 int ensure_decoded_blocks(vrb_ctx* ctx, DeviceGrid& g) {
     if (g.decoded_valid) return VRB_OK;
     NvtxRange nvtx_("vrb:decoded_blocks");
@@ -295,16 +305,18 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
     g.nb = nb;
     const size_t n = size_t(nb.x) * nb.y * nb.z;
     const uint3 vdim = make_uint3(dim[0], dim[1], dim[2]);
-    uint32_t *flags = nullptr, *brick_id = nullptr, *block_sums = nullptr;
+    uint32_t *flags = nullptr, *brick_id = nullptr, *block_sums = nullptr, *brick_of_id = nullptr;
     unsigned long long* d_total = nullptr;
     const int n_blocks = int((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
     CK(pool_alloc(&g.indirection, n * 4, ctx->stream));
     CK(pool_alloc(&g.range, n * 4, ctx->stream));
     CK(pool_alloc(&flags, n * 4, ctx->stream));
     CK(pool_alloc(&brick_id, n * 4, ctx->stream));
+    CK(pool_alloc(&brick_of_id, n * 4, ctx->stream));
     CK(pool_alloc(&block_sums, size_t(n_blocks) * 4, ctx->stream));
     CK(pool_alloc(&d_total, 8, ctx->stream));
     // A: ranges
+    bool counted = false;          // block_sums already filled by the range pass
     if (d_values) {
         k_brick_range_values<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_values, nb, g.range, flags);
         CK_LAUNCH();
@@ -313,23 +325,32 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
         uint16_t* m2 = nullptr;
         const size_t n2 = size_t(dim[2]) * nb.y * nb.x;
         CK(pool_alloc(&m2, n2 * 2, ctx->stream));
-        if ((dim[2] + 3) / 4 > 65535u) return fail(ctx, VRB_ERR_INVALID, "grid too deep");
         const int vec16 = ((dim[0] & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 15u) == 0) ? 1 : 0;
-        k_range_xy<<<dim3((nb.x + 63) / 64, (nb.y + RANGE_BAND_BY - 1) / RANGE_BAND_BY, (dim[2] + 3) / 4), dim3(32, 4), 0, ctx->stream>>>(d_vox, vdim, nb, m2, vec16);
+        const size_t items = size_t(dim[2]) * (nb.x >> 1);       // (z-slice, pair of brick columns): < 2^31 / RANGE_XY_THREADS blocks for any grid below the 1024-brick limit
+        k_range_xy<<<dim3(unsigned((items + RANGE_XY_THREADS - 1) / RANGE_XY_THREADS), (nb.y + RANGE_BAND_BY - 1) / RANGE_BAND_BY), RANGE_XY_THREADS, 0, ctx->stream>>>(d_vox, vdim, nb, m2, vec16);
         CK_LAUNCH();
-        k_range_z<<<grid_for(n, 256, ctx->sm_count, 32), 256, 0, ctx->stream>>>(m2, vdim, vmin, vmax, nb, g.range, flags);
+        k_range_z_count<<<n_blocks, SCAN_BLOCK / 2, 0, ctx->stream>>>(m2, vdim, vmin, vmax, nb, g.range, flags, block_sums);
         CK_LAUNCH();
         pool_free(m2, ctx->stream);
+        counted = true;
     } else {
         k_brick_range<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_vox, vdim, vmin, vmax, nb, g.range, flags);
         CK_LAUNCH();
     }
-    // B: ordered allocation
-    k_scan_block_sums<<<n_blocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, n, block_sums);
+    // D: range mips (they depend on the ranges only: issued here so that they run while the host waits for the brick count below)
+    for (int i = 0; i < 3; ++i) CK(pool_alloc(&g.mips[i], mip_words(nb, i) * 4, ctx->stream));
+    k_range_mips3<<<unsigned(mip_words(nb, 2)), 64, 0, ctx->stream>>>(g.range, nb, g.mips[0], g.mips[1], g.mips[2]);     // one CTA per 8^3-brick region
     CK_LAUNCH();
+    // B: ordered allocation
+    if (!counted) {
+        k_scan_block_sums<<<n_blocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, n, block_sums);
+        CK_LAUNCH();
+    }
     k_scan_sums<<<1, 1024, 0, ctx->stream>>>(block_sums, n_blocks, d_total);
     CK_LAUNCH();
-    k_scan_assign<<<n_blocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, n, block_sums, nb, g.indirection, brick_id);
+    const bool aligned8 = !d_values && (dim[0] & 7u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 7u) == 0;
+    if (aligned8) CK(pool_alloc(&g.rec, n * sizeof(uint2), ctx->stream));      // fast path: the scan writes the tracer's records as well
+    k_scan_assign<<<n_blocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, n, block_sums, nb, g.indirection, brick_id, brick_of_id, g.range, d_total, aligned8 ? g.rec : nullptr);
     CK_LAUNCH();
     unsigned long long total = 0;
     CK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -340,9 +361,23 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
     g.atlas_dim = make_uint3(nb.x * 8, nb.y * 8, az);
     const size_t atlas_bytes = size_t(g.atlas_dim.x) * g.atlas_dim.y * g.atlas_dim.z;
     CK(pool_alloc(&g.atlas, atlas_bytes, ctx->stream));
-    if (atlas_bytes) CK(cudaMemsetAsync(g.atlas, 0, atlas_bytes, ctx->stream));
+    const bool enc_lut = aligned8;                 // table-driven encode that also writes the brick-linear tracer atlas
+    if (enc_lut) {
+        // every allocated brick is written whole: only the unused tail of the last brick layer needs zeros
+        const size_t layer = size_t(g.atlas_dim.x) * g.atlas_dim.y * 8;
+        if (atlas_bytes) CK(cudaMemsetAsync(g.atlas + atlas_bytes - layer, 0, layer, ctx->stream));
+        const size_t n_slots = size_t(nb.x) * nb.y * (az >> 3);
+        CK(pool_alloc(&g.atlas_lin, (n_slots + 1) * 512, ctx->stream));
+        CK(cudaMemsetAsync(g.atlas_lin + size_t(total) * 512, 0, (n_slots + 1 - size_t(total)) * 512, ctx->stream));   // unused slots + the all-zero brick
+        if (total) {
+            k_brick_encode_lut<<<grid_for(size_t(total) * 32, ENC_WARPS * 32, ctx->sm_count, 8), ENC_WARPS * 32, 0, ctx->stream>>>(
+                d_vox, vdim, vmin, vmax, nb, g.range, flags, g.indirection, brick_of_id, uint32_t(total), g.atlas, g.atlas_dim, g.atlas_lin);
+            CK_LAUNCH();
+        }
+    } else if (atlas_bytes) CK(cudaMemsetAsync(g.atlas, 0, atlas_bytes, ctx->stream));
     // C: encode
-    if (total && d_values) {
+    if (enc_lut) {
+    } else if (total && d_values) {
         k_brick_encode_values<<<grid_for(n * 32, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_values, nb, g.range, brick_id, g.atlas, g.atlas_dim);
         CK_LAUNCH();
     } else if (total) {
@@ -350,21 +385,10 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
                                                                                                  ((dim[0] & 7u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 7u) == 0) ? 1 : 0);
         CK_LAUNCH();
     }
-    // D: range mips
-    const uint32_t* src = g.range;
-    uint3 sdim = nb;
-    for (int i = 0; i < 3; ++i) {
-        const uint3 ddim = make_uint3(nb.x >> (i + 1), nb.y >> (i + 1), nb.z >> (i + 1));
-        const size_t words = mip_words(nb, i);
-        CK(pool_alloc(&g.mips[i], words * 4, ctx->stream));
-        k_range_mip<<<grid_for(words, 256, ctx->sm_count), 256, 0, ctx->stream>>>(src, sdim, g.mips[i], ddim);
-        CK_LAUNCH();
-        src = g.mips[i];
-        sdim = ddim;
-    }
-    const int st = finalize_grid(ctx, g);
+
+    const int st = finalize_grid(ctx, g, enc_lut, enc_lut);
     CK(cudaStreamSynchronize(ctx->stream));
-    pool_free(flags, ctx->stream); pool_free(brick_id, ctx->stream); pool_free(block_sums, ctx->stream); pool_free(d_total, ctx->stream);
+    pool_free(flags, ctx->stream); pool_free(brick_id, ctx->stream); pool_free(brick_of_id, ctx->stream); pool_free(block_sums, ctx->stream); pool_free(d_total, ctx->stream);
     return st;
 }
 
@@ -402,6 +426,10 @@ int fill_trace_args(vrb_ctx* ctx, const vrb_params* p, TraceArgs& a) {
     a.p = *p;
     if (p->use_transferfunc && (ctx->kernel == 0 || ctx->kernel == 3)) {      // the fast-math TF kernels sample the decoded apron blocks
         const int st = ensure_decoded_blocks(ctx, it->second.slot[VRB_SLOT_DENSITY]);
+        if (st) return st;
+    }
+    if (p->use_transferfunc) {      // every TF kernel is compiled with the 8-tap fetch through the padded records (the IEEE cross-checks use it)
+        const int st = ensure_padded_records(ctx, it->second.slot[VRB_SLOT_DENSITY]);
         if (st) return st;
     }
     a.density = make_view(it->second.slot[VRB_SLOT_DENSITY]);
@@ -914,6 +942,7 @@ int vrb_debug_sample_density(vrb_ctx* ctx, int slot, int frame, const float* ipo
     if (n == 0) return VRB_OK;
     DeviceGuard guard(ctx->device);
     if (mode == 1) { st = ensure_decoded_blocks(ctx, it->second.slot[slot]); if (st) return st; }
+    if (mode == 0) { st = ensure_padded_records(ctx, it->second.slot[slot]); if (st) return st; }
     float *d_p = nullptr, *d_o = nullptr;
     CK(pool_alloc(&d_p, n * 12, ctx->stream));
     CK(pool_alloc(&d_o, n * 4, ctx->stream));
