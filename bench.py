@@ -594,7 +594,8 @@ def main():
             try:
                 out["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])
             except Exception:
-                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: " + (r.stderr or "")[-300:]}
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
+                                       "sample": f"failed: rc {r.returncode} " + (r.stderr or r.stdout or "")[-300:]}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

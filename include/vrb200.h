@@ -221,7 +221,10 @@ int vrb_set_kernel(vrb_ctx* ctx, int kind);
  * "async_upload" (default 0) changes the ownership rule of vrb_grid_upload_brick / vrb_env_upload / vrb_tf_upload: with 1
  * they only enqueue (cudaMemcpyAsync semantics) -- the host buffers must stay valid and unchanged until the next vrb_sync
  * or download on this context; pass pinned memory so that the copies really are asynchronous. A pipelined caller can
- * then enqueue the uploads and the trace of the next frame while the previous one is still running. */
+ * then enqueue the uploads and the trace of the next frame while the previous one is still running.
+ * "overlap" (default 1): the passes of one vrb_trace call alternate between two streams so that pass k + 1 starts in the tail
+ * of pass k. "l2_persist" (default 0, VRB200_L2_PERSIST): MiB of L2 set aside for persisting lines, with an access-policy
+ * window over the grid's brick records + majorant tables (what every DDA step fetches first); measured flat on B200. */
 int vrb_set_option(vrb_ctx* ctx, const char* name, int value);
 /* measurement aid (new; SURVEY 8(d): the L2 roofline "must be micro-benchmarked on the box"): read bandwidth of this device over
  * a working set of `bytes` (1 MiB ... 8 GiB; below the 126 MB L2 it measures L2, 1 GiB measures HBM), best of 5 launches timed

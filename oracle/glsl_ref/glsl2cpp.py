@@ -30,6 +30,11 @@ Every rewrite is purely lexical and listed here; none touches an arithmetic expr
      arguments left to right (4.50 spec 5.9 / 6.1: "in order, from left to right"); C++ leaves call arguments
      unsequenced (g++ goes right to left) but orders a braced list. These are the only expressions in the five files
      with two side effects in one argument list.
+ R10 the scalar conversion `int(x)` -> `glsl_int(x)` (glsl_shim.h): for a float argument the GPU conversion -- saturating,
+     NaN -> 0 -- instead of the C++ cast, which is undefined there (x86 yields INT_MIN). GLSL leaves the case undefined too and
+     the reference reaches it: rng() == 0 under a zero majorant makes t = 0 / 0 (common.glsl:434/481), the next lookups run
+     on NaN positions and `tf_lut[int(floor(NaN))]` (common.glsl:209) must not index wildly. Same decision as f2i() of
+     oracle/vr_oracle.c and as cvt.rzi.s32.f32 on the device; identical results wherever the argument is a finite in-range value.
 """
 import hashlib
 import os
@@ -68,6 +73,7 @@ def lexical_rewrites(src: str, entry: bool) -> str:
             if m:
                 out.append("#undef " + m.group(1))                               # R8
         code = re.sub(r"\b(vec[234])\((rng\(previous\)(?:,\s*rng\(previous\))+)\)", r"\1{\2}", code)   # R9
+        code = re.sub(r"(?<![\w.])int\(", "glsl_int(", code)                        # R10
         if entry:                                                                 # R7
             code = re.sub(r"^int seed;", "int u_seed;", code)
             code = code.replace("uint seed = tea(seed * (", "uint seed = tea(u_seed * (")

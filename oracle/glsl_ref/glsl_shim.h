@@ -150,4 +150,14 @@ inline vec4 texelFetch(const sampler3D& s, const ivec3& p, int lod) {
 
 struct invocation_id { uvec2 xy; };           /* only `.xy` is read (ivec2(gl_GlobalInvocationID.xy)) */
 extern thread_local invocation_id gl_GlobalInvocationID;
+
+/* R10 of glsl2cpp.py: `int(x)` of the shader text. float -> int as the GPU converts (saturating, NaN -> 0); integers pass through. */
+inline int glsl_int(float x) {
+    if (x != x) return 0;
+    if (x >= 2147483648.f) return 2147483647;
+    if (x <= -2147483648.f) return -2147483647 - 1;
+    return static_cast<int>(x);
+}
+inline int glsl_int(int x) { return x; }
+inline int glsl_int(uint x) { return static_cast<int>(x); }
 }  // namespace glsl

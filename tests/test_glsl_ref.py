@@ -2,7 +2,7 @@
 reference's OWN shader text.
 
 oracle/_ref/libglsl_ref.so is the UNMODIFIED /root/reference/shader/{common,pathtracer_brick,pathtracer_brick_tf,env_setup,
-tonemap}.glsl compiled as C++ (oracle/glsl_ref/glsl2cpp.py: nine lexical rewrites, listed there; glsl_shim.h: the reference's
+tonemap}.glsl compiled as C++ (oracle/glsl_ref/glsl2cpp.py: ten lexical rewrites, listed there; glsl_shim.h: the reference's
 own glm + the GL fixed-function decisions). The restatement must equal it BIT FOR BIT -- every pixel, every case:
 TF and non-TF programs, bounces 1 / 3 / 128, with and without an emission grid, clipped + rotated volumes, hidden
 environment, several dispatches into the running mean. The same images are committed as golden vectors
@@ -182,3 +182,21 @@ def test_tonemap_equals_compiled_glsl(glsl, oracle, glsl_golden):
     for exposure, gamma in [(3.0, 2.0), (10.0, 2.2), (0.5, 1.0)]:
         assert np.array_equal(bits(glsl.tonemap(img, exposure, gamma)), bits(oracle.tonemap_inplace(img, exposure, gamma)))
     assert np.array_equal(bits(glsl_golden["tonemap_out"]), bits(oracle.tonemap_inplace(glsl_golden["tonemap_in"], 3.0, 2.0)))
+
+
+def test_nan_path_rng_zero_under_a_zero_majorant(glsl, oracle, assets):
+    """rng() == 0 makes the free-flight draw tau = -log(1 - 0) = 0; under a zero majorant the shader then computes t = 0 / 0
+    (common.glsl:434/481) and goes on to `tf_lut[int(floor(NaN))]` (common.glsl:209). Sample 1436 of the headline frame at
+    480x270 (bench.py's CPU leg) contains such a path: a plain C++ cast there indexed the LUT at INT_MIN and crashed the
+    compiled shaders (found by the bench run on the GPU box); with the GPU conversion pinned for `int(x)` (R10 of glsl2cpp.py,
+    the same decision as f2i() in vr_oracle.c and cvt.rzi on the device) both sides agree bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import workloads as wl
+    grid = assets["grid"]
+    p = wl.default_params(grid, 480, 270, bounces=128, use_tf=True)
+    sc = oracle.make_scene(grid, assets["env"], assets["pyr"], assets["lut"])
+    want = glsl.trace(sc, p, 1436, 1)
+    got, _ = oracle.trace(sc, p, 1436, 1)
+    assert np.isfinite(want).all() and want[..., 3].max() > 0
+    assert np.array_equal(bits(got), bits(want))

@@ -27,6 +27,7 @@ ap.add_argument("--count", type=int, default=0)
 ap.add_argument("--kernel", type=int, default=0)
 ap.add_argument("--lib", default=None)
 ap.add_argument("--json", type=int, default=0)
+ap.add_argument("--l2-persist", type=int, default=0, help="MiB of persisting L2 with a window over records + majorant tables (vrb_set_option l2_persist)")
 a = ap.parse_args()
 if a.lib:
     os.environ["VRB200_LIB"] = a.lib
@@ -68,6 +69,8 @@ else:
     p = wl.synthetic_params(dims, W, H, tf)
 ctx.resize(W, H)
 ctx.set_kernel(a.kernel)
+if a.l2_persist:
+    ctx.set_option("l2_persist", a.l2_persist)
 if a.count:
     ctx.set_counting(True)
 ms = []
@@ -77,7 +80,7 @@ for i in range(a.launches):
     ctx.sync(); dt = time.perf_counter() - t
     ms.append(dt * 1e3)
     print(f"launch {i}: {dt*1e3:.2f} ms  {W*H*a.spp/dt/1e6:.1f} Msamples/s", flush=True)
-out = {"scene": name, "kernel": a.kernel, "lib": os.path.basename(a.lib) if a.lib else "default", "res": [W, H], "spp": a.spp,
+out = {"scene": name, "kernel": a.kernel, "l2_persist_MiB": a.l2_persist, "lib": os.path.basename(a.lib) if a.lib else "default", "res": [W, H], "spp": a.spp,
        "best_ms": min(ms[1:]) if len(ms) > 1 else ms[0]}
 out["gsamples_per_s"] = W * H * a.spp / (out["best_ms"] * 1e-3) / 1e9
 if a.count:

@@ -4,7 +4,7 @@
 // are bit-identical -- but the lanes of a warp no longer OWN a path. The lane-resident kernel ran its stages at 12-17 of 32
 // active lanes (profiles/r01_v11_trace_*_summary.txt): a lane whose path waited for a rare event (NEE, scatter, finish +
 // regeneration) was lost to the hot brick-DDA loop, and every threshold / occupancy / two-rays-per-lane variant ended within
-// a few percent, because 32 paths simply are asynchronous. Here every warp keeps a POOL of VR_POOL_SLOTS (64) path states in
+// a few percent, because 32 paths simply are asynchronous. Here every warp keeps a POOL of VR_POOL_SLOTS (48) path states in
 // shared memory, struct-of-arrays so that 32 lanes touching 32 different slots are (at worst two-way) bank-conflict free, and
 // a scheduler iteration
 //   1. picks the stage class with the most waiting slots -- SEGMENT (a ray that steps or sits at a tentative collision), NEE,
@@ -29,19 +29,20 @@
 namespace vr {
 
 #ifndef VR_POOL_SLOTS
-#define VR_POOL_SLOTS 64          // path states per warp (multiple of 32)
+#define VR_POOL_SLOTS 48          // path states per warp (multiple of 16). B200 sweep (profiles/r02_pool_v4_sweep.txt): 32 slots lose 25 % (the
+                                  // event stages starve), 64 slots x 6 CTAs/SM and 48 x 8 are within 2 %, 48 x 8 with VR_SEG_EXIT 16 is best on all four configs
 #endif
 #ifndef VR_POOL_WARPS
 #define VR_POOL_WARPS 4           // warps per CTA
 #endif
 #ifndef VR_POOL_MIN_BLOCKS
-#define VR_POOL_MIN_BLOCKS 6      // CTAs per SM the register allocation must allow (shared memory: 6 x 34.5 KiB at 64 slots)
+#define VR_POOL_MIN_BLOCKS 8      // CTAs per SM the register allocation must allow: 64 registers (shared memory: 8 x 26.5 KiB at 48 slots)
 #endif
 #ifndef VR_SEG_FULL
 #define VR_SEG_FULL 32            // SEGMENT runs at once when this many slots wait for it
 #endif
 #ifndef VR_SEG_EXIT
-#define VR_SEG_EXIT 20            // leave the SEGMENT loop when fewer of its lanes still have a live ray
+#define VR_SEG_EXIT 16            // leave the SEGMENT loop when fewer of its lanes still have a live ray (12 ... 28 are within 4 %)
 #endif
 #ifndef VR_SEG_MAX_ITERS
 #define VR_SEG_MAX_ITERS 64       // ... or after this many loop iterations (bounds the time a waiting event stage is starved)
@@ -62,7 +63,7 @@ namespace vr {
 // fields of a slot (one 32-bit word each; PF_COUNT words per slot)
 enum : int {
     PF_STAGE = 0,   // stage | flags | STEP visits of the current ray
-    PF_PIX, PF_SJ, PF_SEED, PF_NPATHS,
+    PF_PIX /* y << 16 | x */, PF_SJ, PF_SEED, PF_NPATHS,
     PF_POS, PF_DIR = PF_POS + 3, PF_THR = PF_DIR + 3, PF_L = PF_THR + 3, PF_PEND = PF_L + 3,
     PF_FP = PF_PEND + 3, PF_TR,
     PF_IPOS, PF_IDIR = PF_IPOS + 3, PF_T = PF_IDIR + 3, PF_TFAR,
@@ -80,8 +81,8 @@ constexpr size_t pool_smem_bytes() { return pool_warp_words() * 4 * VR_POOL_WARP
 template <bool TF, bool COUNT, class MT>
 __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trace_pool(const __grid_constant__ TraceArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int SL = VR_POOL_SLOTS, NS = VR_POOL_SLOTS / 32;
-    static_assert(VR_POOL_SLOTS % 32 == 0 && VR_POOL_SLOTS >= 32, "whole rows of 32 slots");
+    constexpr int SL = VR_POOL_SLOTS, NS = (VR_POOL_SLOTS + 31) / 32;
+    static_assert(VR_POOL_SLOTS % 16 == 0 && VR_POOL_SLOTS >= 32, "the last row of 32 slots may be half full (48, 80 ... slots)");
     static_assert((pool_warp_words() * 4) % 16 == 0, "float4 alignment of the prepared block");
     extern __shared__ float4 pool_smem[];
     const int lane = threadIdx.x & 31;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
 #define PSTORE3(f, s, v) do { const float3 v_ = (v); PF((f), s) = v_.x; PF((f) + 1, s) = v_.y; PF((f) + 2, s) = v_.z; } while (0)
 
 #pragma unroll
-    for (int k = 0; k < NS; ++k) PU(PF_STAGE, k * 32 + lane) = SG_FINISH;      // every slot starts by asking for a sample
+    for (int k = 0; k < NS; ++k) if (k * 32 + lane < SL) PU(PF_STAGE, k * 32 + lane) = SG_FINISH;      // every slot starts by asking for a sample
 
     // ---- warp state: the current block of 32 samples (one tile, one sample index), prepared in shared memory ----
     int blk_x0 = 0, blk_y0 = 0, blk_sj = 0;
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
         int base = 0;
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            const uint32_t st = PU(PF_STAGE, k * 32 + lane) & PL_STAGE;
+            const bool have = (k + 1) * 32 <= SL || k * 32 + lane < SL;       // compile-time true for full rows
+            const uint32_t st = have ? (PU(PF_STAGE, k * 32 + lane) & PL_STAGE) : uint32_t(SG_IDLE);
             const bool in = S == SG_STEP ? st <= uint32_t(SG_COLLIDE) : st == uint32_t(S);      // SG_STEP = 0, SG_COLLIDE = 1
             const unsigned b = __ballot_sync(FULL, in);
             const int r = base + __popc(b & lt);
@@ -347,11 +349,10 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                         Lf = Lf + PLOAD3(PF_THR, slot) * mis_weight * Le;
                     }
                     cnt.samp();                                     // pathtracer_brick.glsl:36: sanitize(L), folded by k_fold
-                    const uint32_t sj = PU(PF_SJ, slot), pix = PU(PF_PIX, slot);
-                    VR_LBUF_STORE(a.lbuf + size_t(sj) * a.lbuf_stride + pix,
+                    const uint32_t sj = PU(PF_SJ, slot), pxy = PU(PF_PIX, slot), px = pxy & 0xffffu, py = pxy >> 16;     // (no division by W)
+                    VR_LBUF_STORE(a.lbuf + size_t(sj) * a.lbuf_stride + (py * uint32_t(W) + px),
                                   make_float4(sanitize(Lf.x), sanitize(Lf.y), sanitize(Lf.z), sanitize(fminf(float(n_paths), 1.f))));
                     if (a.tile_cost) {     // what ranks the tiles for the next launch of this view: path vertices of a dithered quarter of the samples
-                        const uint32_t py = pix / uint32_t(W), px = pix - py * uint32_t(W);
                         if (((px ^ py ^ sj) & 3u) == 0u)
                             atomicAdd(a.tile_cost + ((int(py) - a.y0) >> 2) * a.tiles_x + ((int(px) - a.x0) >> 3), 1u + min(n_paths, 4095u));
                     }
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
             }
             if (act) {
                 if (have_item) {                                   // new sample: camera ray of the prepared sample
-                    PU(PF_PIX, slot) = uint32_t(py) * uint32_t(W) + uint32_t(px);
+                    PU(PF_PIX, slot) = (uint32_t(py) << 16) | uint32_t(px);      // image sides < 65536 (checked by the host)
                     PU(PF_SJ, slot) = uint32_t(sj);
                     PU(PF_NPATHS, slot) = 0u;
                     spos = f3(a.p.cam_pos[0], a.p.cam_pos[1], a.p.cam_pos[2]);

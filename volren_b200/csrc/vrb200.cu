@@ -57,8 +57,11 @@ struct DeviceGrid {
     uint32_t* range = nullptr;
     uint8_t* atlas = nullptr;
     uint32_t* mips[3] = { nullptr, nullptr, nullptr };
-    // tracer layout
-    uint2* rec = nullptr;
+    // tracer layout. `hot` is ONE allocation holding the structures every DDA step / tentative collision fetches first -- the records
+    // and the four majorant tables -- so that a single L2 access-policy window (option "l2_persist") can cover them
+    void* hot = nullptr;
+    size_t hot_bytes = 0;
+    uint2* rec = nullptr;           // = hot
     uint2* recp = nullptr;       // padded (nb + 2)^3 records for the trilinear fetch (ensure_padded_records)
     bool recp_valid = false;
     uint8_t* atlas_lin = nullptr;   // n_slots bricks + one all-zero brick
@@ -67,7 +70,7 @@ struct DeviceGrid {
     uint32_t* cslot = nullptr;      // (nb + 1)^3 cells -> decoded apron block (0 = shared zero block)
     float* datlas = nullptr;        // (n_dblocks + 1) x 729 decoded voxels
     size_t n_dblocks = 0;
-    // majorant tables of the persistent kernel, valid for maj_key
+    // majorant tables of the persistent kernel (inside `hot`, behind the records), valid for maj_key
     float* maj[4] = { nullptr, nullptr, nullptr, nullptr };
     uint64_t maj_key = 0;
     uint64_t version = 0;           // bumped whenever the contents change (keys the cached tile order / brick mask)
@@ -103,8 +106,13 @@ struct vrb_ctx {
     float4* lbuf2 = nullptr;     // the second lane's (allocated when a call has more than one pass)
     int lbuf_samples = 0, lbuf2_samples = 0;
     cudaStream_t pass_stream = nullptr;      // second lane: pass k + 1 starts in the tail of pass k (persistent kernels fill the SMs one wave deep)
-    cudaEvent_t ev_entry = nullptr, ev_fold[2] = { nullptr, nullptr };
+    cudaEvent_t ev_entry = nullptr, ev_fold[2] = { nullptr, nullptr }, ev_order = nullptr;   // ev_order: the latest rebuild of the brick mask / tile order
     int overlap = 1;             // VRB200_OVERLAP / option "overlap": 0 = every pass on the context's stream
+    // L2 access-policy window over the grid's `hot` allocation (records + majorant tables): option "l2_persist" = MiB of L2 set
+    // aside for persisting lines (0 = off, the default: measured flat on C3 / C4, profiles/r02_l2_persist.txt)
+    int l2_persist_mb = 0;
+    const void* l2_window_ptr = nullptr;      // what the streams' attribute currently covers
+    size_t l2_window_bytes = 0;
     int pass_samples = 32;       // samples per pixel and pass (VRB200_PASS); bounds lbuf (also capped at 1 GiB = 32 samples at 1080p).
                                  // B200, configs[1]: 16 -> 33.6, 32 -> 36.9, 64 -> 36.7, 128 -> 36.5 Gsamples/s (fixed costs + tail per pass)
     // heaviest-tiles-first scheduling (vr_trace2.cuh): per-tile cost of the last launch, its view key, the sorted order
@@ -172,9 +180,8 @@ inline void pool_free(void* p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
 void free_grid(DeviceGrid& g, cudaStream_t s) {
     pool_free(g.indirection, s); pool_free(g.range, s); pool_free(g.atlas, s);
     for (auto& m : g.mips) pool_free(m, s);
-    pool_free(g.rec, s); pool_free(g.recp, s); pool_free(g.atlas_lin, s);
+    pool_free(g.hot, s); pool_free(g.recp, s); pool_free(g.atlas_lin, s);
     pool_free(g.cslot, s); pool_free(g.datlas, s);
-    for (auto& m : g.maj) pool_free(m, s);
     g = DeviceGrid();
 }
 
@@ -186,6 +193,22 @@ inline int grid_for(size_t n, int block, int sm_count, int per_sm = 16) {
 
 size_t mip_words(const uint3& nb, int level) { return size_t(nb.x >> (level + 1)) * (nb.y >> (level + 1)) * (nb.z >> (level + 1)); }
 
+// records + majorant tables (level 0 with one extra entry for the out-of-bounds majorant) in one allocation
+cudaError_t alloc_hot(DeviceGrid& g, cudaStream_t s) {
+    const size_t n = size_t(g.nb.x) * g.nb.y * g.nb.z;
+    size_t words[4] = { n + 1, mip_words(g.nb, 0), mip_words(g.nb, 1), mip_words(g.nb, 2) };
+    size_t bytes = n * sizeof(uint2);
+    for (size_t w : words) bytes += ((w * 4 + 255) / 256) * 256;
+    const cudaError_t e = pool_alloc(&g.hot, bytes, s);
+    if (e != cudaSuccess) return e;
+    g.hot_bytes = bytes;
+    g.rec = static_cast<uint2*>(g.hot);
+    char* p = static_cast<char*>(g.hot) + n * sizeof(uint2);
+    for (int l = 0; l < 4; ++l) { g.maj[l] = reinterpret_cast<float*>(p); p += ((words[l] * 4 + 255) / 256) * 256; }
+    g.maj_key = 0;
+    return cudaSuccess;
+}
+
 // builds the tracer layout (records + brick-linear atlas) from the canonical buffers
 int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false, bool lin_done = false) {     // lin_done: the builder wrote rec and atlas_lin itself
     NvtxRange nvtx_("vrb:finalize_grid (records, linear atlas, decoded blocks)");
@@ -194,7 +217,7 @@ int finalize_grid(vrb_ctx* ctx, DeviceGrid& g, bool reuse = false, bool lin_done
     g.n_slots = size_t(ab.x) * ab.y * ab.z;
     if (g.n_slots >= 0xffffffffull) return fail(ctx, VRB_ERR_INVALID, "atlas too large");
     if (!reuse) {
-        CK(pool_alloc(&g.rec, n * sizeof(uint2), ctx->stream));
+        CK(alloc_hot(g, ctx->stream));
         CK(pool_alloc(&g.atlas_lin, (g.n_slots + 1) * 512, ctx->stream));
     }
     g.maj_key = 0;   // the majorant tables (if any) belong to the previous contents
@@ -349,7 +372,7 @@ int build_from_device_voxels(vrb_ctx* ctx, int slot, int frame, const uint8_t* d
     k_scan_sums<<<1, 1024, 0, ctx->stream>>>(block_sums, n_blocks, d_total);
     CK_LAUNCH();
     const bool aligned8 = !d_values && (dim[0] & 7u) == 0 && (reinterpret_cast<uintptr_t>(d_vox) & 7u) == 0;
-    if (aligned8) CK(pool_alloc(&g.rec, n * sizeof(uint2), ctx->stream));      // fast path: the scan writes the tracer's records as well
+    if (aligned8) CK(alloc_hot(g, ctx->stream));      // fast path: the scan writes the tracer's records as well
     k_scan_assign<<<n_blocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, n, block_sums, nb, g.indirection, brick_id, brick_of_id, g.range, d_total, aligned8 ? g.rec : nullptr);
     CK_LAUNCH();
     unsigned long long total = 0;
@@ -497,6 +520,7 @@ int vrb_create(int device, vrb_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev_entry, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fold[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fold[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc(&ctx->job_counter, 2 * sizeof(unsigned int)) != cudaSuccess) {
         delete ctx;
         return VRB_ERR_CUDA;
@@ -513,6 +537,7 @@ int vrb_create(int device, vrb_ctx** out) {
     if (const char* e = getenv("VRB200_CULL")) ctx->cull = atoi(e) != 0;
     if (const char* e = getenv("VRB200_PASS")) ctx->pass_samples = std::max(1, atoi(e));
     if (const char* e = getenv("VRB200_OVERLAP")) ctx->overlap = atoi(e) != 0;
+    if (const char* e = getenv("VRB200_L2_PERSIST")) ctx->l2_persist_mb = std::max(0, atoi(e));
     if (const char* e = getenv("VRB200_KERNEL")) ctx->kernel = std::min(3, std::max(0, atoi(e)));
     cudaMemsetAsync(ctx->counters, 0, 7 * sizeof(unsigned long long), ctx->stream);
     *out = ctx;
@@ -531,6 +556,7 @@ void vrb_destroy(vrb_ctx* ctx) {
     if (ctx->pass_stream) cudaStreamDestroy(ctx->pass_stream);
     if (ctx->ev_entry) cudaEventDestroy(ctx->ev_entry);
     for (int i = 0; i < 2; ++i) if (ctx->ev_fold[i]) cudaEventDestroy(ctx->ev_fold[i]);
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     cudaFree(ctx->fb); cudaFree(ctx->ldr); cudaFree(ctx->env_rgb); cudaFree(ctx->impmap); cudaFree(ctx->env_split); cudaFree(ctx->lut); cudaFree(ctx->counters); cudaFree(ctx->job_counter);
     cudaStreamSynchronize(ctx->stream);
     {   // hand the pooled grid memory back to the driver
@@ -548,6 +574,7 @@ int vrb_set_stream(vrb_ctx* ctx, void* cuda_stream, int external) {
     DeviceGuard guard(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = external ? cudaStream_t(cuda_stream) : ctx->own_stream;   // external + NULL = the legacy default stream
+    ctx->l2_window_ptr = nullptr; ctx->l2_window_bytes = 0;                 // the L2 access-policy window is a per-stream attribute: re-applied by the next trace
     return VRB_OK;
 }
 
@@ -1096,11 +1123,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     mix_key(&strict_tables, 4);
     if (tf) { mix_key(&params->tf_window_left, 4); mix_key(&params->tf_window_width, 4); mix_key(&ctx->lut_version, 8); }
     const size_t n0 = size_t(g.nb.x) * g.nb.y * g.nb.z;
-    if (!g.maj[0]) {
-        CK(pool_alloc(&g.maj[0], (n0 + 1) * 4, ctx->stream));   // + 1: the out-of-bounds majorant
-        for (int l = 1; l < 4; ++l) CK(pool_alloc(&g.maj[l], mip_words(g.nb, l - 1) * 4, ctx->stream));
-        g.maj_key = 0;
-    }
+    if (!g.maj[0]) return fail(ctx, VRB_ERR_STATE, "grid without tracer layout");      // allocated with the records (alloc_hot)
     for (int l = 0; l < 4; ++l) a.maj[l] = g.maj[l];
     a.maj_oob = g.maj[0] + n0;
     if (g.maj_key != key) {
@@ -1116,6 +1139,30 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         g.maj_key = key;
     }
     a.job_counter = ctx->job_counter;
+    {
+        // L2 policy: the records and majorant tables (g.hot) are the first, dependent fetch of every DDA step and tentative
+        // collision; on the HBM-resident configs the atlas sectors streaming through L2 compete with them. One window per stream.
+        const void* want_ptr = ctx->l2_persist_mb > 0 ? g.hot : nullptr;
+        const size_t want_bytes = want_ptr ? g.hot_bytes : 0;
+        if (want_ptr != ctx->l2_window_ptr || want_bytes != ctx->l2_window_bytes) {
+            int max_window = 0, max_persist = 0;
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+            const size_t carve = std::min<size_t>(size_t(ctx->l2_persist_mb) << 20, size_t(max_persist));
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = const_cast<void*>(want_ptr);
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(want_bytes, size_t(max_window));
+            attr.accessPolicyWindow.hitRatio = want_bytes ? float(std::min(1.0, double(carve) / double(std::max<size_t>(want_bytes, 1)))) : 0.f;
+            attr.accessPolicyWindow.hitProp = want_ptr ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+            attr.accessPolicyWindow.missProp = want_ptr ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+            CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+            if (ctx->pass_stream) CK(cudaStreamSetAttribute(ctx->pass_stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+            if (!want_ptr) cudaCtxResetPersistingL2Cache();
+            ctx->l2_window_ptr = want_ptr; ctx->l2_window_bytes = want_bytes;
+        }
+    }
     // ---- per-launch sample buffer: passes of at most `pass` samples per pixel (16 B per sample and pixel) ----
     const size_t n_px = size_t(ctx->w) * ctx->h;
     const int pass = int(std::max<size_t>(1, std::min<size_t>(size_t(ctx->pass_samples), (size_t(1) << 30) / (n_px * sizeof(float4)))));
@@ -1184,7 +1231,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     // ---- heaviest tiles first: order the blocks by the per-tile cost the previous launch of this view measured ----
     const bool lpt = ctx->lpt && !ctx->counting && (ctx->kernel == 0 || ctx->kernel == 3);    // the fast-math production schedules
     uint64_t vkey = key;
-    if (a.tiles_x >= 65536 || n_tiles / a.tiles_x >= 65536) return fail(ctx, VRB_ERR_INVALID, "image too large");
+    if (a.tiles_x >= 65536 || n_tiles / a.tiles_x >= 65536 || ctx->w > 65535 || ctx->h > 65535) return fail(ctx, VRB_ERR_INVALID, "image too large");   // (the ray pool packs a pixel as y << 16 | x)
     {
         // the cost landscape depends on everything but the seed and the sample range
         auto mix2 = [&vkey](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); for (size_t i = 0; i < n; ++i) { vkey ^= b[i]; vkey *= 1099511628211ull; } };
@@ -1251,6 +1298,7 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
         CK(cudaStreamWaitEvent(ctx->pass_stream, ctx->ev_entry, 0));
     }
     int n_pass = 0;
+    int order_lane = -1;                          // lane whose stream rebuilt the mask / order arrays last in this call (ev_order)
     bool fold_pending[2] = { false, false };      // ev_fold[lane] marks the end of that lane's latest fold
     for (int s0 = first_sample; s0 < first_end; s0 += pass, ++n_pass) {
         const int lane = two_lanes ? (n_pass & 1) : 0;
@@ -1290,6 +1338,8 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             ++ctx->order_age;
             a.tile_order = ctx->tile_order;
             if (mask) a.n_live = ctx->live_info;
+            // the arrays may have been (re)built on the OTHER lane's stream by the previous pass: read them behind that build
+            if (two_lanes && order_lane >= 0 && order_lane != lane) CK(cudaStreamWaitEvent(st_, ctx->ev_order, 0));
         } else if (mask || cost_valid) {
             // the order / mask arrays are rewritten: nothing of the other lane may still read them (its tracking kernel reads the
             // order and the live count, its fold the mask)
@@ -1313,13 +1363,14 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
             }
             a.tile_order = ctx->tile_order;
             if (lpt) CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, st_));     // costs accumulate until the next re-sort
+            if (two_lanes) { CK(cudaEventRecord(ctx->ev_order, st_)); order_lane = lane; }
         }
         if (lpt) {
             if (ctx->cost_key != vkey) CK(cudaMemsetAsync(ctx->tile_cost, 0, size_t(n_tiles) * 4, st_));   // first pass of a new view
             ctx->cost_key = vkey;
             a.tile_cost = ctx->tile_cost;
         }
-        const int per_block = pool ? VR_POOL_WARPS * (VR_POOL_SLOTS / 32) : VR_TRACE_BLOCK / 32;     // blocks of 32 samples one CTA holds at a time
+        const int per_block = pool ? VR_POOL_WARPS * ((VR_POOL_SLOTS + 31) / 32) : VR_TRACE_BLOCK / 32;     // blocks of 32 samples one CTA holds at a time
         const int needed = (n_tiles * a.n_samples + per_block - 1) / per_block;
         const int blocks = needed < ctx->trace_blocks[variant] ? (needed > 0 ? needed : 1) : ctx->trace_blocks[variant];
         void* kargs[] = { (void*)&a };
@@ -1395,6 +1446,7 @@ int vrb_set_option(vrb_ctx* ctx, const char* name, int value) {
     else if (!strcmp(name, "count_culled")) ctx->count_culled = value != 0;
     else if (!strcmp(name, "async_upload")) ctx->async_upload = value != 0;
     else if (!strcmp(name, "overlap")) ctx->overlap = value != 0;
+    else if (!strcmp(name, "l2_persist")) { if (value < 0) return fail(ctx, VRB_ERR_INVALID, "l2_persist must be >= 0 (MiB)"); ctx->l2_persist_mb = value; }
     else if (!strcmp(name, "pass")) { if (value < 1) return fail(ctx, VRB_ERR_INVALID, "pass must be >= 1"); ctx->pass_samples = value; }
     else return fail(ctx, VRB_ERR_INVALID, "unknown option '%s'", name);
     return VRB_OK;
