@@ -19,8 +19,9 @@ roofline  headline kernel (C2 is L2-resident by nature: 27 MB working set): EXEC
 configs   C1, C3, C4 (samples/s, roofline, counters) and C5 (frames/s) measured in the same run; at N > 1 they are split the way
           BASELINE.json names (spp slices + reduce per frame for C1/C3/C4, frames dealt to the ranks for C5): strong scaling.
 strong    N > 1: ONE 1024-spp frame of the headline config split over the N ranks with its per-frame reduce.
-cpu_baseline / --impl reference: the CPU port of the reference shaders (oracle/vr_oracle.c, pinned bit for bit against the
-          reference's GLSL compiled as C++) on all host threads, bounded sample of the same frame.
+cpu_baseline / --impl reference: the reference's OWN tracking code on all host threads -- its unmodified GLSL compiled as C++
+          (oracle/_ref/libglsl_ref.so, kind "reference"; the restated port oracle/vr_oracle.c, bit-identical to it, only where
+          that library is absent, kind "port") -- on a bounded sample of the same frame (480x270, same camera).
 """
 from __future__ import annotations
 

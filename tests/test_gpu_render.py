@@ -45,7 +45,9 @@ def test_deterministic_mode_T1(smoke_ctx, oracle, smoke_grid, env_rgb, env_pyram
 
 @pytest.mark.parametrize("use_tf", [False, True])
 def test_same_seed_replay_T2(smoke_ctx, oracle, smoke_grid, env_rgb, env_pyramid, lut_raw, use_tf):
-    """1 spp, few bounces, same TEA/LCG seeds: most pixels agree to 1e-3; the rest are fp branch flips."""
+    """1 spp, few bounces, same TEA/LCG seeds: the production (fast-math) kernel replays the oracle pixel for pixel to 1e-3 --
+    measured 1.0000 of the pixels on B200 for both programs (round 1 asked for 0.97); a last-bit difference of a MUFU function
+    can flip a comparison, hence >= 0.999 rather than all."""
     W, H = 128, 96
     lut, _ = oracle.lut_upload(lut_raw)
     smoke_ctx.tf_upload(lut)
@@ -57,7 +59,7 @@ def test_same_seed_replay_T2(smoke_ctx, oracle, smoke_grid, env_rgb, env_pyramid
     ok = np.all(rel_err(got, want, eps=1e-3) < 1e-3, axis=-1)
     frac = ok.mean()
     print(f"T2 same-seed pixel match fraction (tf={use_tf}): {frac:.4f}")
-    assert frac > 0.97
+    assert frac >= 0.999
     assert np.array_equal(got[..., 3] > 0, want[..., 3] > 0) or (got[..., 3] != want[..., 3]).mean() < 0.01
 
 
