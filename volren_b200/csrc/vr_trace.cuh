@@ -73,6 +73,8 @@ struct TraceArgs {
     // persistent kernel only
     const float* maj[4];           // per-level majorant tables (final value used by the tracking loop)
     const float* maj_oob;          // majorant of an out-of-bounds fetch (one float)
+    uint32_t maj_off[4];           // the same tables as element offsets from maj[0] (they share one allocation); maj_off_oob: the out-of-bounds entry
+    uint32_t maj_off_oob;
     unsigned int* job_counter;     // block ticket: block b = (tile slot b >> sample_bits, sample b & mask), 32 samples each
     int tiles_x, n_jobs;           // n_jobs = number of block ids = tiles << sample_bits (ids with sample >= n_samples are padding)
     int sample_bits;               // ceil(log2(n_samples))

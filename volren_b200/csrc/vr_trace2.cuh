@@ -52,6 +52,17 @@ VR_GLOBAL void k_majorant_table      // (internal linkage in the strict unit: th
     }
 }
 
+// The same lookup with one base pointer: the four tables and the out-of-bounds entry live in one allocation (alloc_hot), so the
+// level selects a 32-bit element offset instead of a 64-bit pointer and the out-of-bounds case selects an INDEX instead of a
+// second load site -- one IMAD.WIDE + one LDG instead of LDC.64 + four address instructions + two predicated loads.
+VR_DEV float table_majorant_idx(const TraceArgs& a, float3 ipos, int mip) {
+    const int bx = int(floorf(ipos.x)) >> (3 + mip), by = int(floorf(ipos.y)) >> (3 + mip), bz = int(floorf(ipos.z)) >> (3 + mip);
+    const uint32_t nx = a.density.nb.x >> mip, ny = a.density.nb.y >> mip, nz = a.density.nb.z >> mip;
+    const bool in = unsigned(bx) < nx && unsigned(by) < ny && unsigned(bz) < nz;
+    const uint32_t idx = in ? a.maj_off[mip] + (uint32_t(bz) * ny + uint32_t(by)) * nx + uint32_t(bx) : a.maj_off_oob;
+    return __ldg(a.maj[0] + idx);
+}
+
 VR_DEV float table_majorant(const TraceArgs& a, float3 ipos, int mip) {
     const int bx = int(floorf(ipos.x)) >> (3 + mip), by = int(floorf(ipos.y)) >> (3 + mip), bz = int(floorf(ipos.z)) >> (3 + mip);
     const uint32_t nx = a.density.nb.x >> mip, ny = a.density.nb.y >> mip, nz = a.density.nb.z >> mip;

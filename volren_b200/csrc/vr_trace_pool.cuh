@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                 ri = f3(MT::rcp(idir.x), MT::rcp(idir.y), MT::rcp(idir.z));
             }
             const bool shadow = (fl & PL_SHADOW) != 0u;
+            const int sub_left = shadow ? SG_SCATTER : SG_FINISH;      // where a ray goes when it leaves the volume
             constexpr int KC = TF ? VR_SEG_K_COLLIDE_TF : VR_SEG_K_COLLIDE;
             const int waiting = (n_seg - nsel) + n_nee + n_scat + n_fin;      // slots of the pool this visit does not work on
 #pragma unroll 1
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                             const float3 curr = ipos + t * idir;
                             const int m = round_mip(mip);
                             cnt.maj();
-                            majorant = table_majorant(a, curr, m);
+                            majorant = table_majorant_idx(a, curr, m);
                             const float dt = step_dda(curr, ri, m);
                             t += dt;
                             tau -= majorant * dt;
@@ -183,8 +184,9 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
                                 t += MT::div(tau, majorant);
                                 if (!(t >= tfar)) sub = SG_COLLIDE;   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
                             }
+                        } else {
+                            sub = sub_left;      // `while (t < far)` ended: the ray left the volume (seen one step later than it happened -- one test per step)
                         }
-                        if (sub == SG_STEP && !(t < tfar)) sub = shadow ? SG_SCATTER : SG_FINISH;     // the ray left the volume
                     }
                 }
                 // ---- COLLIDE (batched) ----

@@ -1126,6 +1126,8 @@ int vrb_trace(vrb_ctx* ctx, const vrb_params* params, int first_sample, int n_sa
     if (!g.maj[0]) return fail(ctx, VRB_ERR_STATE, "grid without tracer layout");      // allocated with the records (alloc_hot)
     for (int l = 0; l < 4; ++l) a.maj[l] = g.maj[l];
     a.maj_oob = g.maj[0] + n0;
+    for (int l = 0; l < 4; ++l) a.maj_off[l] = uint32_t(g.maj[l] - g.maj[0]);       // one allocation (alloc_hot): < 2^31 floats
+    a.maj_off_oob = uint32_t(n0);
     if (g.maj_key != key) {
         for (int l = 0; l < 4; ++l) {
             const size_t n = l == 0 ? n0 : mip_words(g.nb, l - 1);
