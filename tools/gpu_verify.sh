@@ -1,4 +1,4 @@
-# final verification: smoke(), the whole GPU suite, the reference arm, bench N = 1
+# GPU-box job (gpurun): smoke(), the whole GPU suite, the reference arm, bench N = 1
 mkdir -p gpurun_out
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
