@@ -114,6 +114,21 @@ def test_too_many_bricks_is_an_error(ctx):
     assert e.value.status == _capi.VRB_ERR_TOO_MANY_BRICKS and "1024" in str(e.value)
 
 
+@pytest.mark.parametrize("lo,hi", [(-3.0, 7.5), (1e-30, 3e-30), (5.0, 5.0), (2.0, -1.0), (0.0, 70000.0), (-1e20, 1e20)],
+                         ids=["negative", "tiny", "collapsed", "reversed", "beyond-fp16", "huge"])
+def test_fast_path_value_ranges(ctx, oracle, lo, hi):
+    """The table-driven encode (k_brick_encode_lut: division by the brick's rounded reciprocal + fma corrections, with the IEEE
+    division as the guarded fallback) against the oracle for DenseGrid value ranges that leave the comfortable regime: negative
+    minima (sign-extended range words), denormal-scale spans, min == max, min > max, values beyond fp16 (infinite range halves),
+    1e20 (the fallback). Widths that take the fast path, with padding bricks and a ragged last chunk."""
+    rng = np.random.default_rng(7)
+    vox = (rng.random((21, 30, 136)) * 255).astype(np.uint8)
+    vox[rng.random(vox.shape) < 0.5] = 0
+    vox[:, :, 100:] = 0                                  # whole empty bricks as well
+    ctx.grid_build_from_dense(vox, lo, hi)
+    _assert_same(ctx.grid_download(), oracle.brick_build(vox, lo, hi))
+
+
 @pytest.mark.parametrize("name", ["smoke", "blobs"])
 def test_decoded_apron_blocks_equal_the_canonical_fetch(ctx, smoke_grid, name):
     """The production kernel's trilinear fetch reads DECODED 9^3 apron blocks (one slot load + 8 fp32 loads); it must
