@@ -497,6 +497,25 @@ def main():
                          "brick_build": {"ms": build_ms, "algorithmic_GBps": build_bytes / (build_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                          "frac": build_bytes / (build_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                          "bytes": "1 B/voxel read + 1 B/allocated voxel written + 8 B/brick (SURVEY 8(d))"}}
+                if name == "C3":
+                    # the pipeline SURVEY 8(d) names for C3: fp32 field -> DenseGrid(float*) (global min/max + 8-bit quantisation)
+                    # -> BrickGrid, all on the GPU (vrb_grid_build_from_float_device). The u8 codes of `vox` as floats give the
+                    # same DenseGrid (min 0, max 255 -> the identical codes), so the grid the frame is traced on does not change.
+                    f32 = vox.float()
+                    torch.cuda.synchronize()
+                    c2.grid_build_from_float_device(f32.data_ptr(), dims, frame=1)
+                    a, b = ev_pair()
+                    a.record()
+                    mm = c2.grid_build_from_float_device(f32.data_ptr(), dims, frame=1)
+                    b.record()
+                    torch.cuda.synchronize()
+                    f_ms = a.elapsed_time(b)
+                    f_bytes = 9 * n_vox + build_bytes
+                    extra["dense_from_float_and_brick_build"] = {
+                        "ms": f_ms, "algorithmic_GBps": f_bytes / (f_ms * 1e-3) / 1e9, "frac": f_bytes / (f_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "min_max": list(mm), "bytes": "DenseGrid(float*): 4 B/voxel read twice + 1 B/voxel written, then the brick build's bytes"}
+                    c2.lib.vrb_grid_free(c2.handle, 0, 1)
+                    del f32
                 del vox
                 torch.cuda.empty_cache()
                 p = wl.synthetic_params(dims, w, h, tf)

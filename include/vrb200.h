@@ -139,6 +139,12 @@ int vrb_grid_build_from_dense(vrb_ctx* ctx, int slot, int frame, const uint8_t* 
  * voxels must be complete with respect to THAT stream -- written on it, or the writer synchronised -- like any CUDA consumer. */
 int vrb_grid_build_from_dense_device(vrb_ctx* ctx, int slot, int frame, const void* d_voxels_u8,
                                      const uint32_t dim[3], float vmin, float vmax);
+/* voldata::DenseGrid(w,h,d,const float*) (grid_dense.cpp:57-95) followed by BrickGrid(const Grid&) for FLOAT voxels resident in
+ * device memory (the C3 pipeline: a synthetic fp32 field -> DenseGrid -> bricks without leaving the GPU): global min/max with
+ * the reference's initial values, 8-bit quantisation, brick build. out_minmax (may be NULL) receives DenseGrid::min_value /
+ * max_value. Same stream rule as vrb_grid_build_from_dense_device. */
+int vrb_grid_build_from_float_device(vrb_ctx* ctx, int slot, int frame, const void* d_voxels_f32,
+                                     const uint32_t dim[3], float out_minmax[2]);
 /* voldata::BrickGrid::BrickGrid(const Grid&) for ANY Grid source (grid_brick.cpp:60-142 with the virtual Grid::lookup,
  * e.g. NanoVDBGrid, grid_nvdb.cpp:64-67): the caller evaluates grid.lookup(uvec3(x, y, z)) once for every voxel of the
  * padded lattice x in [-2, 8 n_bricks.x + 2) (likewise y, z; negative coordinates wrap to uint32 as in the reference's

@@ -228,3 +228,27 @@ def test_two_gib_atlas_addressing(ctx, env_rgb):
     del vox
     ctx.grid_clear()
     torch.cuda.empty_cache()
+
+
+def test_float_field_to_bricks_on_the_device(ctx, oracle):
+    """The C3 pipeline as SURVEY 8(d) writes it: an fp32 field in device memory -> DenseGrid(float*) (grid_dense.cpp:57-95: global
+    min / max with the reference's FLT_MAX / FLT_MIN start values, 8-bit quantisation) -> BrickGrid(const Grid&), without leaving
+    the GPU (vrb_grid_build_from_float_device), bit for bit against the oracle's two steps; a width that takes the float4 kernels
+    and one that does not, negative values, and an all-negative field (the FLT_MIN quirk: max stays 1.17e-38)."""
+    import torch
+    for shape, shift in (((48, 40, 64), 0.0), ((21, 30, 50), -0.3), ((16, 16, 32), -5.0)):
+        g = torch.Generator(device="cuda").manual_seed(sum(shape))
+        f = torch.rand(shape, device="cuda", generator=g, dtype=torch.float32)
+        f = torch.where(f < 0.6, torch.zeros_like(f), f) * 3.0 + shift
+        torch.cuda.synchronize()
+        d, h, w = shape
+        ctx.grid_clear()
+        mm = ctx.grid_build_from_float_device(f.data_ptr(), (w, h, d))
+        got = ctx.grid_download()
+        q, mm_want = oracle.dense_from_float(f.cpu().numpy())
+        assert mm == mm_want
+        want = oracle.brick_build(q, mm_want[0], mm_want[1])
+        assert np.array_equal(got.range, want.range) and np.array_equal(got.indirection, want.indirection) and np.array_equal(got.atlas, want.atlas)
+        for i in range(3):
+            assert np.array_equal(got.mips[i], want.mips[i])
+    ctx.grid_clear()

@@ -19,7 +19,7 @@ ACCUM_MEAN, ACCUM_SUM = 0, 1
 SYMBOLS = [
     "vrb_create", "vrb_destroy", "vrb_last_error", "vrb_status_string", "vrb_abi_version", "vrb_set_stream", "vrb_sync",
     "vrb_resize", "vrb_grid_clear", "vrb_grid_free", "vrb_grid_upload_brick", "vrb_grid_build_from_dense",
-    "vrb_grid_build_from_dense_device", "vrb_brick_lattice", "vrb_grid_build_from_values", "vrb_nvdb_open", "vrb_nvdb_lookup", "vrb_grid_build_from_nvdb", "vrb_grid_info", "vrb_grid_download", "vrb_debug_sample_density", "vrb_dense_from_float",
+    "vrb_grid_build_from_dense_device", "vrb_grid_build_from_float_device", "vrb_brick_lattice", "vrb_grid_build_from_values", "vrb_nvdb_open", "vrb_nvdb_lookup", "vrb_grid_build_from_nvdb", "vrb_grid_info", "vrb_grid_download", "vrb_debug_sample_density", "vrb_dense_from_float",
     "vrb_env_upload", "vrb_env_download_impmap", "vrb_tf_upload", "vrb_trace", "vrb_trace_deterministic", "vrb_set_kernel", "vrb_set_option", "vrb_get_stat", "vrb_probe_bandwidth", "vrb_scale",
     "vrb_clear", "vrb_set_counting", "vrb_get_counters", "vrb_tonemap", "vrb_download_color", "vrb_download_color_ldr",
     "vrb_download_framebuffer", "vrb_upload_color", "vrb_color_device_ptr", "vrb_bind_color", "vrb_reduce", "vrb_copy_rows",
@@ -111,6 +111,7 @@ def load_library(path: str = LIB_PATH):
     L.vrb_grid_upload_brick.argtypes = [vp, ci, ci, C.POINTER(BrickView)]
     L.vrb_grid_build_from_dense.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3, cf, cf]
     L.vrb_grid_build_from_dense_device.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3, cf, cf]
+    L.vrb_grid_build_from_float_device.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3, C.c_float * 2]
     L.vrb_brick_lattice.argtypes = [C.c_uint32 * 3, C.c_uint32 * 3, C.c_uint32 * 3]
     L.vrb_grid_build_from_values.argtypes = [vp, ci, ci, vp, C.c_uint32 * 3]
     L.vrb_nvdb_open.argtypes = [vp, C.c_size_t, C.c_char_p, C.POINTER(NvdbInfo), C.c_char_p, C.c_size_t]
@@ -265,6 +266,12 @@ class Context:
 
     def grid_build_from_dense_device(self, dev_ptr, dim_whd, vmin, vmax, slot=SLOT_DENSITY, frame=0):
         self._ck(self.lib.vrb_grid_build_from_dense_device(self.handle, slot, frame, dev_ptr, (C.c_uint32 * 3)(*dim_whd), vmin, vmax))
+
+    def grid_build_from_float_device(self, dev_ptr, dim_whd, slot=SLOT_DENSITY, frame=0):
+        """DenseGrid(float*) + BrickGrid for fp32 voxels in device memory -> (min_value, max_value)"""
+        mm = (C.c_float * 2)()
+        self._ck(self.lib.vrb_grid_build_from_float_device(self.handle, slot, frame, dev_ptr, (C.c_uint32 * 3)(*dim_whd), mm))
+        return float(mm[0]), float(mm[1])
 
     def grid_build_from_values(self, padded_values, extent_whd, slot=SLOT_DENSITY, frame=0):
         """BrickGrid(const Grid&) for any source: lookup() values on the padded lattice [-2, 8 nb + 2)^3, array [z][y][x]."""

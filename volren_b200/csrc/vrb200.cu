@@ -998,31 +998,69 @@ int vrb_grid_download(vrb_ctx* ctx, int slot, int frame, vrb_brick_view* out) {
     return VRB_OK;
 }
 
+static int dense_quantize_device(vrb_ctx* ctx, const float* d_data, size_t n, uint8_t* d_out, float* d_mm);
+
 int vrb_dense_from_float(vrb_ctx* ctx, const float* data, const uint32_t dim[3], uint8_t* out_u8, float out_minmax[2]) {
     if (!ctx) return VRB_ERR_INVALID;
     if (!data || !dim || !out_u8 || !out_minmax || !dim[0] || !dim[1] || !dim[2]) return fail(ctx, VRB_ERR_INVALID, "bad arguments");
     DeviceGuard guard(ctx->device);
     const size_t n = size_t(dim[0]) * dim[1] * dim[2];
-    float *d_data = nullptr, *d_bmin = nullptr, *d_bmax = nullptr, *d_mm = nullptr;
+    float *d_data = nullptr, *d_mm = nullptr;
     uint8_t* d_out = nullptr;
-    const int blocks = grid_for(n, 256, ctx->sm_count, 8);
     CK(cudaMalloc(&d_data, n * 4));
     CK(cudaMalloc(&d_out, n));
-    CK(cudaMalloc(&d_bmin, blocks * 4));
-    CK(cudaMalloc(&d_bmax, blocks * 4));
     CK(cudaMalloc(&d_mm, 8));
     CK(cudaMemcpyAsync(d_data, data, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    k_dense_minmax<<<blocks, 256, 0, ctx->stream>>>(d_data, n, d_bmin, d_bmax);
+    const int st = dense_quantize_device(ctx, d_data, n, d_out, d_mm);
+    if (st == VRB_OK) {
+        CK(cudaMemcpyAsync(out_u8, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(out_minmax, d_mm, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_data); cudaFree(d_out); cudaFree(d_mm);
+    return st;
+}
+
+// min/max + quantisation of float voxels that are already on the device (both on ctx->stream); d_mm: two floats on the device
+static int dense_quantize_device(vrb_ctx* ctx, const float* d_data, size_t n, uint8_t* d_out, float* d_mm) {
+    float *d_bmin = nullptr, *d_bmax = nullptr;
+    const bool vec4 = (n & 3u) == 0 && (reinterpret_cast<uintptr_t>(d_data) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3u) == 0;
+    const int blocks = grid_for(vec4 ? n / 4 : n, 256, ctx->sm_count, 8);
+    CK(pool_alloc(&d_bmin, size_t(blocks) * 4, ctx->stream));
+    CK(pool_alloc(&d_bmax, size_t(blocks) * 4, ctx->stream));
+    if (vec4) k_dense_minmax4<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_data), n / 4, d_bmin, d_bmax);
+    else k_dense_minmax<<<blocks, 256, 0, ctx->stream>>>(d_data, n, d_bmin, d_bmax);
     CK_LAUNCH();
     k_dense_minmax_final<<<1, 32, 0, ctx->stream>>>(d_bmin, d_bmax, blocks, d_mm);
     CK_LAUNCH();
-    k_dense_quantize<<<blocks, 256, 0, ctx->stream>>>(d_data, n, d_mm, d_out);
+    if (vec4) k_dense_quantize4<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(d_data), n / 4, d_mm, reinterpret_cast<uint32_t*>(d_out));
+    else k_dense_quantize<<<blocks, 256, 0, ctx->stream>>>(d_data, n, d_mm, d_out);
     CK_LAUNCH();
-    CK(cudaMemcpyAsync(out_u8, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(out_minmax, d_mm, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_data); cudaFree(d_out); cudaFree(d_bmin); cudaFree(d_bmax); cudaFree(d_mm);
+    pool_free(d_bmin, ctx->stream); pool_free(d_bmax, ctx->stream);
     return VRB_OK;
+}
+
+int vrb_grid_build_from_float_device(vrb_ctx* ctx, int slot, int frame, const void* d_voxels_f32, const uint32_t dim[3], float out_minmax[2]) {
+    NvtxRange nvtx_("vrb:grid_build_from_float_device (DenseGrid(float*) + BrickGrid)");
+    int st = check_slot_frame(ctx, slot, frame);
+    if (st) return st;
+    if (!d_voxels_f32 || !dim || !dim[0] || !dim[1] || !dim[2]) return fail(ctx, VRB_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(ctx->device);
+    const size_t n = size_t(dim[0]) * dim[1] * dim[2];
+    uint8_t* d_u8 = nullptr;
+    float* d_mm = nullptr;
+    CK(pool_alloc(&d_u8, n, ctx->stream));
+    CK(pool_alloc(&d_mm, 8, ctx->stream));
+    st = dense_quantize_device(ctx, static_cast<const float*>(d_voxels_f32), n, d_u8, d_mm);
+    float mm[2] = { 0.f, 0.f };
+    if (st == VRB_OK) {
+        CK(cudaMemcpyAsync(mm, d_mm, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));      // DenseGrid::min_value / max_value parameterise the brick build
+        if (out_minmax) { out_minmax[0] = mm[0]; out_minmax[1] = mm[1]; }
+        st = build_from_device_voxels(ctx, slot, frame, d_u8, dim, mm[0], mm[1]);
+    }
+    pool_free(d_u8, ctx->stream); pool_free(d_mm, ctx->stream);
+    return st;
 }
 
 int vrb_env_upload(vrb_ctx* ctx, const float* rgb, int w, int h) {
