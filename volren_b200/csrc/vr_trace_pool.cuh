@@ -47,9 +47,6 @@ namespace vr {
 #ifndef VR_SEG_MAX_ITERS
 #define VR_SEG_MAX_ITERS 64       // ... or after this many loop iterations (bounds the time a waiting event stage is starved)
 #endif
-#ifndef VR_SEG_STEPS
-#define VR_SEG_STEPS 2            // DDA steps per loop iteration
-#endif
 #ifndef VR_SEG_K_COLLIDE
 #define VR_SEG_K_COLLIDE 8        // resolve tentative collisions once this many lanes wait at one (non-TF: cheap 1-tap collision)
 #endif
@@ -168,25 +165,45 @@ __global__ void __launch_bounds__(VR_POOL_WARPS * 32, VR_POOL_MIN_BLOCKS) k_trac
 #pragma unroll 1
             for (int iter = 0; iter < VR_SEG_MAX_ITERS; ++iter) {
                 // ---- STEP ----
-#pragma unroll
-                for (int rep = 0; rep < VR_SEG_STEPS; ++rep) {
-                    if (sub == SG_STEP) {
-                        if (t < tfar) {
-                            const float3 curr = ipos + t * idir;
-                            const int m = round_mip(mip);
+                // two steps whose majorant loads are in flight TOGETHER: the second step's position t + dt and level do not depend on
+                // the first step's majorant (dt is geometry), only on whether the first step ends in a tentative collision -- so its
+                // table address is computed and its load issued before the first majorant is consumed; a collision / exit in the
+                // first step just drops it. Same operations per ray in the same order (bit-identical); the fetch latency of a
+                // loop iteration halves: +0.5 ... +1.5 % on the four configs against two plain steps (profiles/r02_pool_v4_sweep.txt).
+                if (sub == SG_STEP) {
+                    if (t < tfar) {
+                        const float3 curr_a = ipos + t * idir;
+                        const int m_a = round_mip(mip);
+                        const float maj_a = table_majorant_idx(a, curr_a, m_a);
+                        const float dt_a = step_dda(curr_a, ri, m_a);
+                        const float t_a = t + dt_a, mip_a = fminf(mip + 0.25f, 3.f);
+                        const float3 curr_b = ipos + t_a * idir;
+                        const int m_b = round_mip(mip_a);
+                        const float maj_b = table_majorant_idx(a, curr_b, m_b);          // speculative: issued before maj_a is used
+                        cnt.maj();
+                        majorant = maj_a;
+                        t = t_a;
+                        tau -= maj_a * dt_a;
+                        mip = mip_a;
+                        if (!(tau > 0.f)) {
+                            t += MT::div(tau, maj_a);
+                            if (!(t >= tfar)) sub = SG_COLLIDE;   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
+                        } else if (t < tfar) {
+                            const float dt_b = step_dda(curr_b, ri, m_b);
                             cnt.maj();
-                            majorant = table_majorant_idx(a, curr, m);
-                            const float dt = step_dda(curr, ri, m);
-                            t += dt;
-                            tau -= majorant * dt;
+                            majorant = maj_b;
+                            t += dt_b;
+                            tau -= maj_b * dt_b;
                             mip = fminf(mip + 0.25f, 3.f);
                             if (!(tau > 0.f)) {
-                                t += MT::div(tau, majorant);
-                                if (!(t >= tfar)) sub = SG_COLLIDE;   // the reference tests `if (t >= far) break;` (a NaN t goes on to the lookup)
+                                t += MT::div(tau, maj_b);
+                                if (!(t >= tfar)) sub = SG_COLLIDE;
                             }
                         } else {
-                            sub = sub_left;      // `while (t < far)` ended: the ray left the volume (seen one step later than it happened -- one test per step)
+                            sub = sub_left;
                         }
+                    } else {
+                        sub = sub_left;      // `while (t < far)` ended: the ray left the volume
                     }
                 }
                 // ---- COLLIDE (batched) ----
